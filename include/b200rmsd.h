@@ -1,0 +1,175 @@
+/*
+ * b200rmsd.h -- C ABI of the B200-native replacement for mdtraj's `_rmsd` hot path.
+ *
+ * Everything the reference's Cython boundary (mdtraj/rmsd/_rmsd.pyx) obtains from
+ * its three C headers
+ *     mdtraj/rmsd/include/center.h:7            inplace_center_and_trace_atom_major
+ *     mdtraj/rmsd/include/theobald_rmsd.h:13-18 msd_axis_major / msd_atom_major
+ *     mdtraj/rmsd/include/rotation.h:7-12       rot_atom_major / rot_msd_atom_major
+ * is provided here, batched over frames (a per-frame call makes no sense across PCIe):
+ * each entry point replaces one *frame loop* of _rmsd.pyx together with the per-frame
+ * C calls inside it.  The entry cites the loop it replaces.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints.  No torch / numpy types.  Every function returns
+ *     0 on success or a negative B200RMSD_E* code; b200rmsd_last_error() gives a
+ *     thread-local message.  Nothing throws across the boundary.
+ *   - "_dev" entry points take DEVICE pointers, run asynchronously on `stream`
+ *     (a cudaStream_t passed as void*; NULL = default stream) of the calling thread's
+ *     current device, and never allocate.  Scratch is caller-provided.
+ *   - "_host" entry points take HOST pointers (pageable or pinned), stage through an
+ *     internal per-device workspace, pipeline H2D copies against kernels, and return
+ *     when the results are in the caller's host buffers.
+ *   - staged trajectory layout ("padded atom-major"): float32, frame f starts at
+ *     xyz + f*frame_stride, holds n_atoms x 3 floats followed by zeros up to
+ *     n_pad = 4*ceil(n_atoms/4) atoms; frame_stride >= 3*n_pad and frame_stride % 4 == 0;
+ *     xyz is 16-byte aligned.  For n_atoms % 4 == 0 this is exactly mdtraj's
+ *     (F, N, 3) C-contiguous xyz.  This is the reference's own nrealatoms/npaddedatoms
+ *     convention (theobald_rmsd_sse.h:192-222).
+ *   - there is no CPU fallback: without a CUDA device every call fails with
+ *     B200RMSD_ENODEVICE.
+ */
+#ifndef B200RMSD_H_
+#define B200RMSD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RMSD_ABI_VERSION 1
+
+#define B200RMSD_OK 0
+#define B200RMSD_EINVAL (-1)    /* bad argument (NULL, misaligned, non-positive size)   */
+#define B200RMSD_ECUDA (-2)     /* a CUDA runtime call failed; see b200rmsd_last_error() */
+#define B200RMSD_ENODEVICE (-3) /* no usable sm_100 device                              */
+#define B200RMSD_ENOMEM (-4)    /* workspace allocation failed                          */
+
+/* flags for b200rmsd_rmsd_dev / b200rmsd_rmsd_host */
+#define B200RMSD_PRECENTERED 1u /* trust `traces`, skip centring (_rmsd.pyx:203-205)    */
+
+/* Opaque per-reference-frame record produced by b200rmsd_prepare_reference_dev
+ * (device memory, B200RMSD_REFSTATS_BYTES bytes, 8-byte aligned). */
+#define B200RMSD_REFSTATS_BYTES 56
+
+int b200rmsd_abi_version(void);
+const char* b200rmsd_last_error(void);
+
+/* Number of CUDA devices; sm_count/hbm_bytes of `device` (any pointer may be NULL). */
+int b200rmsd_device_info(int device, int* n_devices, int* sm_count, size_t* hbm_bytes, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- device API */
+
+/* Bytes of scratch the _dev entry points below may need for a trajectory of this shape
+ * (segment partial sums for very long frames; rotations + centroids for superpose). */
+size_t b200rmsd_scratch_bytes(int64_t n_frames, int n_atoms);
+
+/* Centre frames in place and write their traces (traces may be NULL).
+ * Replaces: inplace_center_and_trace_atom_major, center.h:7 (called at
+ * _rmsd.pyx:212 and :490). */
+int b200rmsd_center_trace_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, float* traces,
+                              void* stream);
+
+/* Prepare the single reference conformation: gather `idx` (int32, may be NULL = all
+ * n_sel atoms), centre it (do_center != 0; otherwise keep as is and take its trace from
+ * `given_trace`, the precentered path), write it zero-padded to ref_out
+ * (3*4*ceil(n_sel/4) floats) and its statistics to ref_stats.
+ * Replaces: the n_frames == 1 call at _rmsd.pyx:213 and the ref_align_xyz preparation
+ * at core/trajectory.py:1129-1147,1150. */
+int b200rmsd_prepare_reference_dev(const float* ref_frame, const int32_t* idx, int n_sel, int do_center,
+                                   float given_trace, float* ref_out, void* ref_stats, void* stream);
+
+/* RMSD of every frame to the prepared reference after optimal superposition.
+ *   idx == NULL : all n_atoms atoms of each frame take part (TMA streaming kernel)
+ *   idx != NULL : the n_sel listed atoms (int32, any order, repeats allowed) take part
+ *   flags & B200RMSD_PRECENTERED : frames are already centred and `traces` holds their
+ *                                  traces (only honoured when idx == NULL)
+ *   out_rot (F,9) / out_centroid (F,3 doubles) may be NULL; when given they receive the
+ *   optimal row-major rotation (apply as x' = x . R) and the removed centroid.
+ *   n_degenerate (device uint32, may be NULL) counts identity-fallback rotations.
+ * Replaces: the prange loop _rmsd.pyx:217-224 (msd_atom_major + sqrtf per frame) together
+ * with the centring pass :212 and the fancy-index copy :197; with out_rot also the
+ * msd_atom_major(..., computeRot=1) half of _rmsd.pyx:663-674. */
+int b200rmsd_rmsd_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const int32_t* idx,
+                      int n_sel, const float* ref, const void* ref_stats, const float* traces, unsigned flags,
+                      float* out_rmsd, float* out_rot, double* out_centroid, unsigned* n_degenerate, void* scratch,
+                      size_t scratch_bytes, void* stream);
+
+/* RMSD without superposition against the raw (uncentred) reference selection `ref_raw`
+ * (n_sel x 3 floats).  Replaces: the prange loop _rmsd.pyx:234-241 + msd_nosuperpose
+ * (:765-793). */
+int b200rmsd_rmsd_nosuperpose_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride,
+                                  const int32_t* idx, int n_sel, const float* ref_raw, float* out_rmsd, void* stream);
+
+/* Superpose every frame onto the prepared reference, in place:
+ *     xyz'[f] = (xyz[f] - centroid_sel(f)) . R_f + centroid_ref
+ * with R_f the optimal rotation of the selected atoms.  out_rmsd / out_rot may be NULL.
+ * Replaces: superpose_atom_major, _rmsd.pyx:620-674 (msd_atom_major computeRot=1 +
+ * rot_atom_major per frame), and the numpy passes of Trajectory.superpose around it
+ * (core/trajectory.py:1127, 1135-1150, 1171). */
+int b200rmsd_superpose_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const int32_t* idx,
+                           int n_sel, const float* ref, const void* ref_stats, float* out_rmsd, float* out_rot,
+                           unsigned* n_degenerate, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Apply caller-supplied rotations:  xyz[f] <- xyz[f] . rot[f]  (no translation).
+ * Replaces: rot_atom_major, rotation.h:7 (loop body _rmsd.pyx:668). */
+int b200rmsd_rotate_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const float* rot,
+                        void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------ all-pairs matrix */
+
+/* The reference has no all-pairs function; clustering code loops md.rmsd(traj, traj, i)
+ * over i (examples/clustering.ipynb:78-81, examples/centroids.ipynb:80-82).  These two
+ * entry points replace that loop:  D[i][j] = md.rmsd(traj, traj, i, atom_indices=idx)[j].
+ *
+ * workspace: caller-owned device memory, 256-byte aligned, at least
+ * b200rmsd_allpairs_workspace_bytes(n_frames, n_sel) bytes; opaque contents (centred
+ * K-major operands, traces).  With multiple GPUs every rank prepares (or receives by
+ * broadcast) the same workspace and computes its own row block. */
+#define B200RMSD_DIAG_ZERO 1u /* D[i][i] = 0 exactly, like the reference's same-pointer shortcut */
+
+size_t b200rmsd_allpairs_workspace_bytes(int64_t n_frames, int n_sel);
+
+/* Centre every frame (selection idx, int32, may be NULL = all atoms; then pass n_sel = n_atoms)
+ * as inplace_center_and_trace_atom_major does (center.h:7) and lay it out for the contraction. */
+int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride,
+                                  const int32_t* idx, int n_sel, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Rows [row0, row1) of the matrix:  out[(i-row0)*ld + j], j in [0, n_frames), float32.
+ * n_sel must equal the value used in prepare. */
+int b200rmsd_allpairs_rows_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,
+                               int64_t row0, int64_t row1, float* out, int64_t ld, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------ host API */
+
+/* md.rmsd on host arrays.  target: (n_frames, n_atoms_target, 3) float32 C-contiguous
+ * (mdtraj's xyz, unpadded); ref_frame: (n_atoms_ref, 3).  idx/ref_idx: int32 selections
+ * of length n_sel or both NULL (then n_atoms_target == n_atoms_ref == n_sel).
+ * superpose == 0 selects the no-alignment branch.  precentered != 0 requires `traces`
+ * (n_frames) and ref_trace and idx == NULL.  Frames are streamed through the device in
+ * chunks; host buffers are never modified.  out: (n_frames) float32.
+ * Replaces: the body of rmsd(), _rmsd.pyx:197-241. */
+int b200rmsd_rmsd_host(const float* target, int64_t n_frames, int n_atoms_target, const float* ref_frame,
+                       int n_atoms_ref, const int32_t* idx, const int32_t* ref_idx, int n_sel, int superpose,
+                       int precentered, const float* traces, float ref_trace, float* out, int device);
+
+/* Trajectory.superpose on host arrays, in place on `xyz` (n_frames, n_atoms, 3).
+ * out_rot (n_frames*9) / out_rmsd (n_frames) may be NULL.
+ * Replaces: core/trajectory.py:1127-1172. */
+int b200rmsd_superpose_host(float* xyz, int64_t n_frames, int n_atoms, const float* ref_frame, int n_atoms_ref,
+                            const int32_t* idx, const int32_t* ref_idx, int n_sel, float* out_rot, float* out_rmsd,
+                            unsigned* n_degenerate, int device);
+
+/* _center_inplace_atom_major on a host array (n_frames, n_atoms, 3), in place; traces
+ * (n_frames) may be NULL.  Replaces: _rmsd.pyx:487-491. */
+int b200rmsd_center_host(float* xyz, int64_t n_frames, int n_atoms, float* traces, int device);
+
+/* Release the internal per-device workspaces of the host API. */
+void b200rmsd_release_workspaces(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RMSD_H_ */

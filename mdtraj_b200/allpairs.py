@@ -1,0 +1,88 @@
+"""All-pairs RMSD matrix: ``D[i, j] = md.rmsd(traj, traj, i, atom_indices=...)[j]``.
+
+The reference obtains it with a Python loop of ``F`` one-vs-many calls
+(``examples/clustering.ipynb:78-81``, ``examples/centroids.ipynb:80-82``); here the
+frames are centred and laid out once (``b200rmsd_allpairs_prepare_dev``) and the
+matrix comes from one tiled contraction with the QCP solve fused into its epilogue
+(``b200rmsd_allpairs_rows_dev``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _capi
+from .device import DeviceTrajectory, _stream_ptr, _torch
+
+DIAG_ZERO = 1
+_MAX_ROWS_PER_CALL = 65535 * 32
+
+
+class PreparedAllPairs:
+    """Opaque device workspace (centred operands + traces) for one trajectory/selection."""
+
+    def __init__(self, workspace, n_frames, n_sel):
+        self.workspace = workspace
+        self.n_frames = int(n_frames)
+        self.n_sel = int(n_sel)
+
+    @property
+    def device(self):
+        return self.workspace.device
+
+
+def prepare(traj: DeviceTrajectory, atom_indices=None) -> PreparedAllPairs:
+    torch = _torch()
+    dev = traj.device
+    idx = traj._index_tensor(atom_indices, traj.n_atoms, "atom_indices")
+    n_sel = traj.n_atoms if idx is None else int(idx.numel())
+    if n_sel == 0:
+        raise ValueError("Number of atom indices must be greater than 0")
+    L = _capi.lib()
+    nbytes = L.b200rmsd_allpairs_workspace_bytes(traj.n_frames, n_sel)
+    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)  # torch allocations are >= 256-byte aligned
+    with torch.cuda.device(dev):
+        rc = L.b200rmsd_allpairs_prepare_dev(traj.xyz_dev.data_ptr(), traj.n_frames, traj.n_atoms, traj.frame_stride,
+                                             None if idx is None else idx.data_ptr(), n_sel, ws.data_ptr(),
+                                             ws.numel(), _stream_ptr(torch, dev))
+    _capi.check(rc, "b200rmsd_allpairs_prepare_dev")
+    return PreparedAllPairs(ws, traj.n_frames, n_sel)
+
+
+def rows(prep: PreparedAllPairs, row0: int, row1: int, out=None, diag_zero=True):
+    """Rows ``[row0, row1)`` as a CUDA float32 tensor of shape ``(row1-row0, F)``."""
+    torch = _torch()
+    dev = prep.device
+    F = prep.n_frames
+    if not (0 <= row0 <= row1 <= F):
+        raise ValueError("row block out of range")
+    if out is None:
+        out = torch.empty((row1 - row0, F), dtype=torch.float32, device=dev)
+    assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (row1 - row0, F)
+    L = _capi.lib()
+    with torch.cuda.device(dev):
+        stream = _stream_ptr(torch, dev)
+        for r0 in range(row0, row1, _MAX_ROWS_PER_CALL):
+            r1 = min(row1, r0 + _MAX_ROWS_PER_CALL)
+            sub = out[r0 - row0: r1 - row0]
+            rc = L.b200rmsd_allpairs_rows_dev(prep.workspace.data_ptr(), prep.workspace.numel(), F, prep.n_sel, r0,
+                                              r1, sub.data_ptr(), out.stride(0), DIAG_ZERO if diag_zero else 0,
+                                              stream)
+            _capi.check(rc, "b200rmsd_allpairs_rows_dev")
+    return out
+
+
+def rmsd_matrix_device(traj: DeviceTrajectory, atom_indices=None, row_block=None, diag_zero=True):
+    """Full (or ``row_block=(r0, r1)``) matrix as a CUDA tensor; nothing is copied to the host."""
+    prep = prepare(traj, atom_indices)
+    r0, r1 = (0, traj.n_frames) if row_block is None else row_block
+    return rows(prep, r0, r1, diag_zero=diag_zero)
+
+
+def rmsd_matrix(traj, atom_indices=None, diag_zero=True) -> np.ndarray:
+    """All-pairs RMSD matrix of ``traj`` (host ``Trajectory``/``mdtraj.Trajectory`` or ``DeviceTrajectory``).
+
+    Returns a float32 ndarray ``(F, F)`` with ``D[i, j] == rmsd(traj, traj, i, atom_indices)[j]``.
+    """
+    if not isinstance(traj, DeviceTrajectory):
+        traj = DeviceTrajectory.from_trajectory(traj)
+    return rmsd_matrix_device(traj, atom_indices, None, diag_zero).cpu().numpy()

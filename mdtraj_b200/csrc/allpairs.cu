@@ -1,0 +1,235 @@
+// allpairs.cu -- all-pairs RMSD matrix  D[i][j] = rmsd(frame j onto frame i).
+//
+// The reference has no such function: clustering code loops `md.rmsd(traj, traj, i)` over
+// every i (examples/clustering.ipynb:78-81, centroids.ipynb:80-82), i.e. F one-vs-many
+// passes, O(F^2 N) work behind O(F) Python calls.  Here it is one dense contraction
+// (3F x A).(A x 3F) whose 3x3 blocks go straight into the QCP solve; the inner products
+// are never written to HBM.
+//
+//   allpairs_prepare_kernel  centre every frame (selection applied) exactly like
+//                            inplace_center_and_trace_atom_major (center_generic.h:3-44),
+//                            store it axis-major (F,3,K) -- the layout of the reference's
+//                            msd_axis_major (theobald_rmsd_generic.h:7-60), K-contiguous
+//                            so it is a GEMM operand -- and its trace.
+//   allpairs_simt_kernel     fp32 FMA tiles (32x32 frame pairs per CTA, 2x2 pairs per
+//                            thread), float64 QCP epilogue.  Exact-arithmetic path: used
+//                            for small problems and as the on-device accuracy check of the
+//                            tensor-core path (allpairs_tc.cu).
+#include "../../include/b200rmsd.h"
+#include "common.cuh"
+#include "kernels.cuh"
+#include "qcp.cuh"
+
+namespace b200 {
+
+struct ApHeader {        // first 256 bytes of the workspace
+    uint64_t magic;
+    int64_t n_frames;
+    int32_t n_sel;
+    int32_t k_pad;       // atoms padded to a multiple of 32
+    int64_t traces_off;  // byte offsets from the workspace base
+    int64_t x_off;       // axis-major fp32 operand (F,3,k_pad)
+    int64_t hi_off;      // tf32 split operands for the tensor path (0 if absent)
+    int64_t lo_off;
+    int64_t rows_pad;    // rows of the split operands
+};
+constexpr uint64_t kApMagic = 0x42323030524d5344ull;  // "B200RMSD"
+
+__host__ __device__ inline int ap_kpad(int n_sel) { return (n_sel + 31) / 32 * 32; }
+
+// one warp per frame
+__global__ void __launch_bounds__(256) allpairs_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames,
+                                                               int64_t frame_stride, const int* __restrict__ idx,
+                                                               int n_sel, int k_pad, float* __restrict__ X,
+                                                               float* __restrict__ traces)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    for (int64_t f = (int64_t)blockIdx.x * 8 + warp; f < n_frames; f += n_warps) {
+        const float* fr = xyz + f * frame_stride;
+        double sx = 0, sy = 0, sz = 0;
+        for (int k = lane; k < n_sel; k += 32) {
+            const int a = idx ? __ldg(idx + k) : k;
+            sx += (double)__ldg(fr + 3 * a); sy += (double)__ldg(fr + 3 * a + 1); sz += (double)__ldg(fr + 3 * a + 2);
+        }
+        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+        const float mx = (float)(sx / n_sel), my = (float)(sy / n_sel), mz = (float)(sz / n_sel);
+        float* out = X + (size_t)f * 3 * k_pad;
+        double tr = 0;
+        for (int k = lane; k < k_pad; k += 32) {
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (k < n_sel) {
+                const int a = idx ? __ldg(idx + k) : k;
+                x = __ldg(fr + 3 * a) - mx; y = __ldg(fr + 3 * a + 1) - my; z = __ldg(fr + 3 * a + 2) - mz;
+                tr += (double)(x * x); tr += (double)(y * y); tr += (double)(z * z);
+            }
+            out[k] = x; out[k_pad + k] = y; out[2 * k_pad + k] = z;
+        }
+        tr = warp_sum(tr);
+        if (lane == 0) traces[f] = (float)tr;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// SIMT tile kernel.  CTA = 256 threads = 16 (ti) x 16 (tj); thread owns i-frames
+// {ti, ti+16} and j-frames {tj, tj+16} of a 32x32 tile.
+// smem per operand: 32 frames x 3 comps x (32+4) floats (row pad keeps 128-bit loads
+// conflict-free: frame stride 108 floats = 12 banks mod 32).
+// ---------------------------------------------------------------------------
+constexpr int kTile = 32, kKc = 32, kRow = kKc + 4;
+
+__global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restrict__ X, const float* __restrict__ traces,
+                                                            int64_t n_frames, int n_sel, int k_pad, int64_t row0,
+                                                            int64_t row1, float* __restrict__ out, int64_t ld,
+                                                            unsigned flags)
+{
+    __shared__ __align__(16) float As[kTile * 3 * kRow];
+    __shared__ __align__(16) float Bs[kTile * 3 * kRow];
+    const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+    const int64_t i0 = row0 + (int64_t)blockIdx.y * kTile, j0 = (int64_t)blockIdx.x * kTile;
+
+    float acc[2][2][9];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 9; ++c) acc[a][b][c] = 0.f;
+
+    for (int k0 = 0; k0 < k_pad; k0 += kKc) {
+        // 96 rows x 8 float4 per operand, 3 float4 per thread
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int q = tid + r * 256;          // 0..767
+            const int row = q >> 3, c4 = q & 7;   // row = frame*3 + comp
+            const int fl = row / 3, comp = row - fl * 3;
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+            const int64_t fi = i0 + fl, fj = j0 + fl;
+            if (fi < row1) va = *reinterpret_cast<const float4*>(X + ((size_t)fi * 3 + comp) * k_pad + k0 + c4 * 4);
+            if (fj < n_frames) vb = *reinterpret_cast<const float4*>(X + ((size_t)fj * 3 + comp) * k_pad + k0 + c4 * 4);
+            *reinterpret_cast<float4*>(&As[row * kRow + c4 * 4]) = va;
+            *reinterpret_cast<float4*>(&Bs[row * kRow + c4 * 4]) = vb;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int kk = 0; kk < kKc; kk += 4) {
+            float4 a[2][3], b[2][3];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    a[s][c] = *reinterpret_cast<const float4*>(&As[((ti + 16 * s) * 3 + c) * kRow + kk]);
+                    b[s][c] = *reinterpret_cast<const float4*>(&Bs[((tj + 16 * s) * 3 + c) * kRow + kk]);
+                }
+            // M[3*p+q] = sum_k a_k[p] * b_k[q] with a = frame j (column), b = frame i (row): D[i][j] = rmsd(j onto i)
+#pragma unroll
+            for (int si = 0; si < 2; ++si)
+#pragma unroll
+                for (int sj = 0; sj < 2; ++sj)
+#pragma unroll
+                    for (int p = 0; p < 3; ++p)
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            float m = acc[si][sj][3 * p + q];
+                            m = fmaf(b[sj][p].x, a[si][q].x, m);
+                            m = fmaf(b[sj][p].y, a[si][q].y, m);
+                            m = fmaf(b[sj][p].z, a[si][q].z, m);
+                            m = fmaf(b[sj][p].w, a[si][q].w, m);
+                            acc[si][sj][3 * p + q] = m;
+                        }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int si = 0; si < 2; ++si)
+#pragma unroll
+        for (int sj = 0; sj < 2; ++sj) {
+            const int64_t i = i0 + ti + 16 * si, j = j0 + tj + 16 * sj;
+            if (i >= row1 || j >= n_frames) continue;
+            float r;
+            if (i == j && (flags & 1u)) {
+                r = 0.f;  // a frame against itself in the same memory: theobald_rmsd_sse.h:256-262
+            } else {
+                QcpInput q;
+                q.n_atoms = n_sel;
+                q.Ga = (double)traces[j];
+                q.Gb = (double)traces[i];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) q.M[c] = (double)acc[si][sj][c];
+                r = (float)sqrt(qcp_solve(q, nullptr, nullptr));
+            }
+            out[(size_t)(i - row0) * ld + j] = r;
+        }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+#define fail b200::set_error
+
+extern "C" {
+
+size_t b200rmsd_allpairs_workspace_bytes(int64_t n_frames, int n_sel)
+{
+    if (n_frames <= 0 || n_sel <= 0) return 256;
+    const size_t kp = (size_t)ap_kpad(n_sel);
+    const size_t tr = ((size_t)n_frames * 4 + 255) / 256 * 256;
+    const size_t x = ((size_t)n_frames * 3 * kp * 4 + 255) / 256 * 256;
+    return 256 + tr + x;
+}
+
+int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride,
+                                  const int32_t* idx, int n_sel, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!xyz || !workspace || n_frames <= 0 || n_atoms <= 0) return fail(B200RMSD_EINVAL, "allpairs_prepare: bad arguments");
+    const int ns = idx ? n_sel : n_atoms;
+    if (ns <= 0) return fail(B200RMSD_EINVAL, "allpairs_prepare: empty selection");
+    if (workspace_bytes < b200rmsd_allpairs_workspace_bytes(n_frames, ns))
+        return fail(B200RMSD_EINVAL, "allpairs_prepare: workspace too small (need %zu bytes)", b200rmsd_allpairs_workspace_bytes(n_frames, ns));
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return fail(B200RMSD_EINVAL, "allpairs_prepare: workspace must be 256-byte aligned");
+    ApHeader h{};
+    h.magic = kApMagic;
+    h.n_frames = n_frames;
+    h.n_sel = ns;
+    h.k_pad = ap_kpad(ns);
+    h.traces_off = 256;
+    h.x_off = 256 + (int64_t)(((size_t)n_frames * 4 + 255) / 256 * 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(workspace, &h, sizeof(h), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(B200RMSD_ECUDA, "allpairs_prepare: %s", cudaGetErrorString(e));
+    int dev = 0, sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    int64_t ctas = (int64_t)sm * 8;
+    const int64_t need = (n_frames + 7) / 8;
+    if (ctas > need) ctas = need;
+    char* base = (char*)workspace;
+    allpairs_prepare_kernel<<<(unsigned)ctas, 256, 0, st>>>(xyz, n_frames, frame_stride, idx, ns, h.k_pad,
+                                                            (float*)(base + h.x_off), (float*)(base + h.traces_off));
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "allpairs_prepare: %s", cudaGetErrorString(e));
+}
+
+int b200rmsd_allpairs_rows_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,
+                               int64_t row0, int64_t row1, float* out, int64_t ld, unsigned flags, void* stream)
+{
+    if (!workspace || !out || n_frames <= 0 || n_sel <= 0 || row0 < 0 || row1 > n_frames || row0 > row1 || ld < n_frames)
+        return fail(B200RMSD_EINVAL, "allpairs_rows: bad arguments");
+    if (workspace_bytes < b200rmsd_allpairs_workspace_bytes(n_frames, n_sel)) return fail(B200RMSD_EINVAL, "allpairs_rows: workspace too small");
+    if (row0 == row1) return 0;
+    const int kp = ap_kpad(n_sel);
+    const char* base = (const char*)workspace;
+    const int64_t traces_off = 256;
+    const int64_t x_off = 256 + (int64_t)(((size_t)n_frames * 4 + 255) / 256 * 256);
+    dim3 grid((unsigned)((n_frames + kTile - 1) / kTile), (unsigned)((row1 - row0 + kTile - 1) / kTile));
+    if (grid.y > 65535) return fail(B200RMSD_EINVAL, "allpairs_rows: at most 65535*32 rows per call");
+    allpairs_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)(base + x_off),
+                                                                 (const float*)(base + traces_off), n_frames, n_sel, kp,
+                                                                 row0, row1, out, ld, flags);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "allpairs_rows: %s", cudaGetErrorString(e));
+}
+
+}  // extern "C"

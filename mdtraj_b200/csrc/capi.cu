@@ -1,0 +1,585 @@
+// capi.cu -- extern "C" entry points declared in include/b200rmsd.h.
+//
+// Device API: thin argument checking + kernel configuration.  Host API: chunked,
+// double-buffered H2D -> kernel -> D2H pipeline over two streams with a per-device
+// workspace, so PCIe transfers of chunk c+1 overlap the kernels of chunk c.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/b200rmsd.h"
+#include "kernels.cuh"
+
+using namespace b200;
+
+static_assert(sizeof(RefStats) == B200RMSD_REFSTATS_BYTES, "RefStats layout is part of the ABI");
+
+static thread_local char g_err_buf[512] = "";
+namespace b200 {
+int set_error(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err_buf, sizeof(g_err_buf), fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace b200
+
+namespace {
+
+#define fail b200::set_error
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? B200RMSD_ENODEVICE \
+                                                                                     : B200RMSD_ECUDA,   \
+                        "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));            \
+    } while (0)
+
+struct DevInfo {
+    int sm_count = 0;
+    bool ok = false;
+};
+DevInfo g_dev[64];
+std::mutex g_dev_mu;
+
+int current_sm_count(int* sm)
+{
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(B200RMSD_EINVAL, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (!g_dev[dev].ok) {
+        int major = 0;
+        CU(cudaDeviceGetAttribute(&g_dev[dev].sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        if (major != 10)
+            return fail(B200RMSD_ENODEVICE, "device %d has compute capability %d.x; this library is sm_100a only", dev,
+                        major);
+        g_dev[dev].ok = true;
+    }
+    *sm = g_dev[dev].sm_count;
+    return 0;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int env_int(const char* name, int dflt)
+{
+    const char* s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+
+// choose segmenting / ring geometry of the TMA kernel for n_atoms
+void configure_tma(OvmParams& p)
+{
+    p.total_units = (p.n_atoms + 3) / 4;
+    const int max_seg = env_int("B200RMSD_MAX_SEG_UNITS", kMaxSegUnits);
+    p.n_seg = (p.total_units + max_seg - 1) / max_seg;
+    p.seg_units = (p.total_units + p.n_seg - 1) / p.n_seg;
+    const size_t budget = 232448;  // 227 KB opt-in shared memory per CTA
+    const size_t ref_bytes = ((size_t)p.seg_units * 48 + 127) / 128 * 128;
+    const size_t fixed = (size_t)kWarpsPerCta * kBatch * kSumStride * sizeof(float) + 2048;
+    const size_t per_warp = (budget - ref_bytes - fixed) / kWarpsPerCta;
+    int chunk = std::min(p.seg_units, env_int("B200RMSD_CHUNK_UNITS", 64));
+    int stages = (int)std::min<size_t>(8, per_warp / ((size_t)chunk * 48));
+    if (stages < 3 && chunk > 32) {
+        chunk = 32;
+        stages = (int)std::min<size_t>(8, per_warp / ((size_t)chunk * 48));
+    }
+    const int forced = env_int("B200RMSD_STAGES", 0);
+    if (forced > 0) stages = std::min<int>(forced, (int)(per_warp / ((size_t)chunk * 48)));
+    p.chunk_units = chunk;
+    p.stages = std::max(stages, 1);
+}
+
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace
+
+extern "C" {
+
+int b200rmsd_abi_version(void) { return B200RMSD_ABI_VERSION; }
+const char* b200rmsd_last_error(void) { return g_err_buf; }
+
+int b200rmsd_device_info(int device, int* n_devices, int* sm_count, size_t* hbm_bytes, int* cc_major, int* cc_minor)
+{
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (n_devices) *n_devices = n;
+    if (n == 0) return fail(B200RMSD_ENODEVICE, "no CUDA device");
+    if (device < 0 || device >= n) return fail(B200RMSD_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (hbm_bytes) *hbm_bytes = prop.totalGlobalMem;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+size_t b200rmsd_scratch_bytes(int64_t n_frames, int n_atoms)
+{
+    if (n_frames <= 0 || n_atoms <= 0) return 256;
+    OvmParams p{};
+    p.n_atoms = n_atoms;
+    configure_tma(p);
+    size_t partial = p.n_seg > 1 ? (size_t)n_frames * p.n_seg * 16 * sizeof(float) : 0;
+    size_t rot = (size_t)n_frames * 9 * sizeof(float);
+    size_t cen = (size_t)n_frames * 3 * sizeof(double);
+    return align256(partial) + align256(rot) + align256(cen) + 256;
+}
+
+int b200rmsd_center_trace_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, float* traces,
+                              void* stream)
+{
+    if (!xyz || n_frames < 0 || n_atoms <= 0) return fail(B200RMSD_EINVAL, "center_trace: bad arguments");
+    if (!aligned16(xyz) || frame_stride % 4 != 0 || frame_stride < 3 * (int64_t)((n_atoms + 3) / 4 * 4))
+        return fail(B200RMSD_EINVAL, "center_trace: xyz must be the padded atom-major layout (16-byte aligned, "
+                                     "frame_stride %% 4 == 0, >= 3*n_pad)");
+    int sm = 0;
+    if (int rc = current_sm_count(&sm)) return rc;
+    CU(launch_center_trace(xyz, n_frames, n_atoms, frame_stride, traces, sm, (cudaStream_t)stream));
+    return 0;
+}
+
+int b200rmsd_prepare_reference_dev(const float* ref_frame, const int32_t* idx, int n_sel, int do_center,
+                                   float given_trace, float* ref_out, void* ref_stats, void* stream)
+{
+    if (!ref_frame || !ref_out || !ref_stats || n_sel <= 0) return fail(B200RMSD_EINVAL, "prepare_reference: bad arguments");
+    int sm = 0;
+    if (int rc = current_sm_count(&sm)) return rc;
+    CU(launch_prepare_ref(ref_frame, idx, n_sel, do_center, given_trace, ref_out, (RefStats*)ref_stats,
+                          (cudaStream_t)stream));
+    return 0;
+}
+
+int b200rmsd_rmsd_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const int32_t* idx,
+                      int n_sel, const float* ref, const void* ref_stats, const float* traces, unsigned flags,
+                      float* out_rmsd, float* out_rot, double* out_centroid, unsigned* n_degenerate, void* scratch,
+                      size_t scratch_bytes, void* stream)
+{
+    if (!xyz || !ref || !ref_stats || !out_rmsd || n_frames < 0 || n_atoms <= 0)
+        return fail(B200RMSD_EINVAL, "rmsd: bad arguments");
+    if (idx && n_sel <= 0) return fail(B200RMSD_EINVAL, "rmsd: empty selection");
+    const bool pre = (flags & B200RMSD_PRECENTERED) && !idx;
+    if (pre && !traces) return fail(B200RMSD_EINVAL, "rmsd: B200RMSD_PRECENTERED needs traces");
+    int sm = 0;
+    if (int rc = current_sm_count(&sm)) return rc;
+
+    OvmParams p{};
+    p.xyz = xyz;
+    p.n_frames = n_frames;
+    p.frame_stride = frame_stride;
+    p.n_atoms = idx ? n_sel : n_atoms;
+    p.idx = idx;
+    p.ref = ref;
+    p.ref_stats = (const RefStats*)ref_stats;
+    p.traces = pre ? traces : nullptr;
+    p.out_rmsd = out_rmsd;
+    p.out_rot = out_rot;
+    p.out_centroid = out_centroid;
+    p.degenerate = n_degenerate;
+    p.n_seg = 1;
+
+    const int n_pad = (n_atoms + 3) / 4 * 4;
+    const bool staged = aligned16(xyz) && aligned16(ref) && frame_stride % 4 == 0 && frame_stride >= 3 * (int64_t)n_pad;
+    if (!idx && staged && !env_int("B200RMSD_FORCE_GATHER", 0)) {
+        configure_tma(p);
+        if (p.stages < 2) return fail(B200RMSD_EINVAL, "rmsd: could not fit a shared-memory ring for n_atoms=%d", n_atoms);
+        if (p.n_seg > 1) {
+            const size_t need = (size_t)n_frames * p.n_seg * 16 * sizeof(float);
+            if (!scratch || scratch_bytes < need || !aligned16(scratch))
+                return fail(B200RMSD_EINVAL, "rmsd: n_atoms=%d needs %zu bytes of 16-byte aligned scratch", n_atoms, need);
+            p.partials = (float*)scratch;
+        }
+        CU(launch_ovm_tma(p, pre, sm, (cudaStream_t)stream));
+    } else {
+        if (!idx && frame_stride < 3 * (int64_t)n_atoms) return fail(B200RMSD_EINVAL, "rmsd: frame_stride too small");
+        CU(launch_ovm_gather(p, pre, sm, (cudaStream_t)stream));
+    }
+    return 0;
+}
+
+int b200rmsd_rmsd_nosuperpose_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride,
+                                  const int32_t* idx, int n_sel, const float* ref_raw, float* out_rmsd, void* stream)
+{
+    if (!xyz || !ref_raw || !out_rmsd || n_frames < 0 || n_atoms <= 0) return fail(B200RMSD_EINVAL, "nosuperpose: bad arguments");
+    int sm = 0;
+    if (int rc = current_sm_count(&sm)) return rc;
+    CU(launch_nosuperpose(xyz, n_frames, idx ? n_sel : n_atoms, frame_stride, idx, ref_raw, out_rmsd, sm,
+                          (cudaStream_t)stream));
+    return 0;
+}
+
+int b200rmsd_superpose_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const int32_t* idx,
+                           int n_sel, const float* ref, const void* ref_stats, float* out_rmsd, float* out_rot,
+                           unsigned* n_degenerate, void* scratch, size_t scratch_bytes, void* stream)
+{
+    if (!xyz || !ref || !ref_stats || n_frames < 0 || n_atoms <= 0) return fail(B200RMSD_EINVAL, "superpose: bad arguments");
+    if (!aligned16(xyz) || frame_stride % 4 != 0 || frame_stride < 3 * (int64_t)((n_atoms + 3) / 4 * 4))
+        return fail(B200RMSD_EINVAL, "superpose: xyz must be the padded atom-major layout");
+    const size_t need = b200rmsd_scratch_bytes(n_frames, n_atoms);
+    if (!scratch || scratch_bytes < need || !aligned16(scratch))
+        return fail(B200RMSD_EINVAL, "superpose: needs %zu bytes of 16-byte aligned scratch (b200rmsd_scratch_bytes)", need);
+    // carve scratch: [segment partials][rotations][centroids]
+    OvmParams cfg{};
+    cfg.n_atoms = n_atoms;
+    configure_tma(cfg);
+    char* base = (char*)scratch;
+    const size_t partial = cfg.n_seg > 1 ? align256((size_t)n_frames * cfg.n_seg * 16 * sizeof(float)) : 0;
+    float* rot = out_rot ? out_rot : (float*)(base + partial);
+    double* cen = (double*)(base + partial + align256((size_t)n_frames * 9 * sizeof(float)));
+    // rmsd output is mandatory for the kernel; park it at the head of the centroid block's tail if not wanted
+    float* rms = out_rmsd;
+    if (!rms) return fail(B200RMSD_EINVAL, "superpose: out_rmsd must not be NULL in the device API");
+    int rc = b200rmsd_rmsd_dev(xyz, n_frames, n_atoms, frame_stride, idx, n_sel, ref, ref_stats, nullptr, 0u, rms, rot,
+                               cen, n_degenerate, partial ? base : nullptr, partial, stream);
+    if (rc) return rc;
+    int sm = 0;
+    if ((rc = current_sm_count(&sm))) return rc;
+    ApplyParams a{};
+    a.xyz = xyz;
+    a.n_frames = n_frames;
+    a.frame_stride = frame_stride;
+    a.n_atoms = n_atoms;
+    a.rot = rot;
+    a.centroid = cen;
+    a.ref_stats = (const RefStats*)ref_stats;
+    CU(launch_apply_transform(a, sm, (cudaStream_t)stream));
+    return 0;
+}
+
+int b200rmsd_rotate_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const float* rot,
+                        void* scratch, size_t scratch_bytes, void* stream)
+{
+    (void)scratch;
+    (void)scratch_bytes;
+    if (!xyz || !rot || n_frames < 0 || n_atoms <= 0) return fail(B200RMSD_EINVAL, "rotate: bad arguments");
+    if (!aligned16(xyz) || frame_stride % 4 != 0 || frame_stride < 3 * (int64_t)((n_atoms + 3) / 4 * 4))
+        return fail(B200RMSD_EINVAL, "rotate: xyz must be the padded atom-major layout");
+    int sm = 0;
+    if (int rc = current_sm_count(&sm)) return rc;
+    ApplyParams a{};
+    a.xyz = xyz;
+    a.n_frames = n_frames;
+    a.frame_stride = frame_stride;
+    a.n_atoms = n_atoms;
+    a.rot = rot;
+    a.centroid = nullptr;
+    a.ref_stats = nullptr;
+    CU(launch_apply_transform(a, sm, (cudaStream_t)stream));
+    return 0;
+}
+
+}  // extern "C"
+
+// ===========================================================================
+// Host API: per-device workspace + chunked pipeline
+// ===========================================================================
+namespace {
+
+struct Workspace {
+    bool init = false;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t ref_ready = nullptr;
+    // two chunk slots
+    float* xyz[2] = {nullptr, nullptr};
+    size_t xyz_bytes = 0;
+    float* out[2] = {nullptr, nullptr};   // rmsd per chunk
+    float* rot[2] = {nullptr, nullptr};
+    float* trc[2] = {nullptr, nullptr};
+    void* scratch[2] = {nullptr, nullptr};
+    size_t per_frame_cap = 0;             // frames the small per-frame buffers can hold
+    size_t scratch_bytes = 0;
+    // reference
+    float* ref_raw = nullptr;             // full reference frame as uploaded
+    float* ref_sel = nullptr;             // prepared (centred / packed)
+    size_t ref_cap = 0;                   // in atoms
+    int32_t* idx = nullptr;
+    int32_t* ref_idx = nullptr;
+    size_t idx_cap = 0;
+    RefStats* stats = nullptr;
+    unsigned* degen = nullptr;
+    std::mutex mu;
+    void reset()
+    {
+        init = false;
+        ref_ready = nullptr;
+        for (int i = 0; i < 2; ++i) { stream[i] = nullptr; xyz[i] = out[i] = rot[i] = trc[i] = nullptr; scratch[i] = nullptr; }
+        xyz_bytes = per_frame_cap = scratch_bytes = ref_cap = idx_cap = 0;
+        ref_raw = ref_sel = nullptr; idx = ref_idx = nullptr; stats = nullptr; degen = nullptr;
+    }
+};
+Workspace g_ws[64];
+
+template <class T>
+cudaError_t regrow(T*& p, size_t bytes)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+    return cudaMalloc((void**)&p, bytes);
+}
+
+int ws_prepare(Workspace& w, size_t chunk_bytes, size_t chunk_frames, size_t scratch_bytes, size_t ref_atoms,
+               size_t n_idx)
+{
+    if (!w.init) {
+        for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithFlags(&w.stream[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&w.ref_ready, cudaEventDisableTiming));
+        CU(cudaMalloc((void**)&w.stats, sizeof(RefStats)));
+        CU(cudaMalloc((void**)&w.degen, sizeof(unsigned)));
+        w.init = true;
+    }
+    if (chunk_bytes > w.xyz_bytes) {
+        for (int i = 0; i < 2; ++i)
+            if (regrow(w.xyz[i], chunk_bytes) != cudaSuccess) return fail(B200RMSD_ENOMEM, "workspace: %zu bytes", chunk_bytes);
+        w.xyz_bytes = chunk_bytes;
+    }
+    if (chunk_frames > w.per_frame_cap) {
+        for (int i = 0; i < 2; ++i) {
+            if (regrow(w.out[i], chunk_frames * sizeof(float)) != cudaSuccess ||
+                regrow(w.rot[i], chunk_frames * 9 * sizeof(float)) != cudaSuccess ||
+                regrow(w.trc[i], chunk_frames * sizeof(float)) != cudaSuccess)
+                return fail(B200RMSD_ENOMEM, "workspace: per-frame buffers");
+        }
+        w.per_frame_cap = chunk_frames;
+    }
+    if (scratch_bytes > w.scratch_bytes) {
+        for (int i = 0; i < 2; ++i)
+            if (regrow(w.scratch[i], scratch_bytes) != cudaSuccess) return fail(B200RMSD_ENOMEM, "workspace: scratch");
+        w.scratch_bytes = scratch_bytes;
+    }
+    if (ref_atoms > w.ref_cap) {
+        const size_t b = (ref_atoms + 4) * 3 * sizeof(float);
+        if (regrow(w.ref_raw, b) != cudaSuccess || regrow(w.ref_sel, b) != cudaSuccess)
+            return fail(B200RMSD_ENOMEM, "workspace: reference");
+        w.ref_cap = ref_atoms;
+    }
+    if (n_idx > w.idx_cap) {
+        if (regrow(w.idx, n_idx * sizeof(int32_t)) != cudaSuccess || regrow(w.ref_idx, n_idx * sizeof(int32_t)) != cudaSuccess)
+            return fail(B200RMSD_ENOMEM, "workspace: index lists");
+        w.idx_cap = n_idx;
+    }
+    return 0;
+}
+
+// frames per chunk: ~B200RMSD_CHUNK_MB (default 64 MB) of padded coordinates
+int64_t frames_per_chunk(int64_t n_frames, int n_pad)
+{
+    const size_t frame_bytes = (size_t)n_pad * 12;
+    const size_t target = (size_t)env_int("B200RMSD_CHUNK_MB", 64) << 20;
+    int64_t fpc = (int64_t)std::max<size_t>(1, target / frame_bytes);
+    return std::min<int64_t>(fpc, std::max<int64_t>(n_frames, 1));
+}
+
+// H2D of frames [f0, f0+nf) into the padded device layout
+cudaError_t upload_chunk(float* dst, const float* src_host, int64_t f0, int64_t nf, int n_atoms, int n_pad, cudaStream_t st)
+{
+    const float* src = src_host + (size_t)f0 * n_atoms * 3;
+    if (n_pad == n_atoms) return cudaMemcpyAsync(dst, src, (size_t)nf * n_atoms * 12, cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)nf * n_pad * 12, st);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy2DAsync(dst, (size_t)n_pad * 12, src, (size_t)n_atoms * 12, (size_t)n_atoms * 12, (size_t)nf,
+                             cudaMemcpyHostToDevice, st);
+}
+cudaError_t download_chunk(float* dst_host, const float* src, int64_t f0, int64_t nf, int n_atoms, int n_pad, cudaStream_t st)
+{
+    float* dst = dst_host + (size_t)f0 * n_atoms * 3;
+    if (n_pad == n_atoms) return cudaMemcpyAsync(dst, src, (size_t)nf * n_atoms * 12, cudaMemcpyDeviceToHost, st);
+    return cudaMemcpy2DAsync(dst, (size_t)n_atoms * 12, src, (size_t)n_pad * 12, (size_t)n_atoms * 12, (size_t)nf,
+                             cudaMemcpyDeviceToHost, st);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int b200rmsd_rmsd_host(const float* target, int64_t n_frames, int n_atoms_target, const float* ref_frame,
+                       int n_atoms_ref, const int32_t* idx, const int32_t* ref_idx, int n_sel, int superpose,
+                       int precentered, const float* traces, float ref_trace, float* out, int device)
+{
+    if (!target || !ref_frame || !out || n_frames < 0 || n_atoms_target <= 0 || n_atoms_ref <= 0)
+        return fail(B200RMSD_EINVAL, "rmsd_host: bad arguments");
+    if ((idx == nullptr) != (ref_idx == nullptr)) return fail(B200RMSD_EINVAL, "rmsd_host: idx and ref_idx must both be given or both NULL");
+    if (!idx && n_atoms_target != n_atoms_ref) return fail(B200RMSD_EINVAL, "rmsd_host: atom counts differ and no index lists given");
+    if (idx && n_sel <= 0) return fail(B200RMSD_EINVAL, "rmsd_host: empty selection");
+    if (precentered && (!traces || idx)) return fail(B200RMSD_EINVAL, "rmsd_host: precentered needs traces and no index lists");
+    if (device < 0 || device >= 64) return fail(B200RMSD_EINVAL, "rmsd_host: device %d", device);
+    if (n_frames == 0) return 0;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(B200RMSD_ENODEVICE, "rmsd_host: cannot select CUDA device %d", device);
+    int sm = 0;
+    if (int rc = current_sm_count(&sm)) return rc;
+
+    Workspace& w = g_ws[device];
+    std::lock_guard<std::mutex> lk(w.mu);
+    const int n_pad = (n_atoms_target + 3) / 4 * 4;
+    const int64_t fpc = frames_per_chunk(n_frames, n_pad);
+    const int n_use = idx ? n_sel : n_atoms_target;
+    if (int rc = ws_prepare(w, (size_t)fpc * n_pad * 12, (size_t)fpc, b200rmsd_scratch_bytes(fpc, n_atoms_target),
+                            (size_t)std::max(n_atoms_ref, n_use), idx ? (size_t)n_sel : 0))
+        return rc;
+
+    cudaStream_t s0 = w.stream[0];
+    CU(cudaMemcpyAsync(w.ref_raw, ref_frame, (size_t)n_atoms_ref * 12, cudaMemcpyHostToDevice, s0));
+    if (idx) {
+        CU(cudaMemcpyAsync(w.idx, idx, (size_t)n_sel * 4, cudaMemcpyHostToDevice, s0));
+        CU(cudaMemcpyAsync(w.ref_idx, ref_idx, (size_t)n_sel * 4, cudaMemcpyHostToDevice, s0));
+    }
+    // superpose: centred packed reference; no-superpose: packed raw reference (do_center = 0)
+    CU(launch_prepare_ref(w.ref_raw, idx ? w.ref_idx : nullptr, n_use, (superpose && !precentered) ? 1 : 0, ref_trace,
+                          w.ref_sel, w.stats, s0));
+    CU(cudaEventRecord(w.ref_ready, s0));
+    CU(cudaStreamWaitEvent(w.stream[1], w.ref_ready, 0));
+
+    int slot = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += fpc, slot ^= 1) {
+        const int64_t nf = std::min(fpc, n_frames - f0);
+        cudaStream_t st = w.stream[slot];
+        CU(upload_chunk(w.xyz[slot], target, f0, nf, n_atoms_target, n_pad, st));
+        int rc;
+        if (superpose) {
+            if (precentered) CU(cudaMemcpyAsync(w.trc[slot], traces + f0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+            rc = b200rmsd_rmsd_dev(w.xyz[slot], nf, n_atoms_target, (int64_t)n_pad * 3, idx ? w.idx : nullptr, n_sel,
+                                   w.ref_sel, w.stats, precentered ? w.trc[slot] : nullptr,
+                                   precentered ? B200RMSD_PRECENTERED : 0u, w.out[slot], nullptr, nullptr, nullptr,
+                                   w.scratch[slot], w.scratch_bytes, st);
+        } else {
+            rc = b200rmsd_rmsd_nosuperpose_dev(w.xyz[slot], nf, n_atoms_target, (int64_t)n_pad * 3,
+                                               idx ? w.idx : nullptr, n_sel, w.ref_sel, w.out[slot], st);
+        }
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(out + f0, w.out[slot], (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(w.stream[0]));
+    CU(cudaStreamSynchronize(w.stream[1]));
+    return 0;
+}
+
+int b200rmsd_superpose_host(float* xyz, int64_t n_frames, int n_atoms, const float* ref_frame, int n_atoms_ref,
+                            const int32_t* idx, const int32_t* ref_idx, int n_sel, float* out_rot, float* out_rmsd,
+                            unsigned* n_degenerate, int device)
+{
+    if (!xyz || !ref_frame || n_frames < 0 || n_atoms <= 0 || n_atoms_ref <= 0) return fail(B200RMSD_EINVAL, "superpose_host: bad arguments");
+    if ((idx == nullptr) != (ref_idx == nullptr)) return fail(B200RMSD_EINVAL, "superpose_host: idx and ref_idx must both be given or both NULL");
+    if (!idx && n_atoms != n_atoms_ref) return fail(B200RMSD_EINVAL, "superpose_host: atom counts differ and no index lists given");
+    if (idx && n_sel <= 0) return fail(B200RMSD_EINVAL, "superpose_host: empty selection");
+    if (device < 0 || device >= 64) return fail(B200RMSD_EINVAL, "superpose_host: device %d", device);
+    if (n_degenerate) *n_degenerate = 0;
+    if (n_frames == 0) return 0;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(B200RMSD_ENODEVICE, "superpose_host: cannot select CUDA device %d", device);
+    int sm = 0;
+    if (int rc = current_sm_count(&sm)) return rc;
+
+    Workspace& w = g_ws[device];
+    std::lock_guard<std::mutex> lk(w.mu);
+    const int n_pad = (n_atoms + 3) / 4 * 4;
+    const int64_t fpc = frames_per_chunk(n_frames, n_pad);
+    const int n_use = idx ? n_sel : n_atoms;
+    if (int rc = ws_prepare(w, (size_t)fpc * n_pad * 12, (size_t)fpc, b200rmsd_scratch_bytes(fpc, n_atoms),
+                            (size_t)std::max(n_atoms_ref, n_use), idx ? (size_t)n_sel : 0))
+        return rc;
+
+    cudaStream_t s0 = w.stream[0];
+    CU(cudaMemsetAsync(w.degen, 0, sizeof(unsigned), s0));
+    CU(cudaMemcpyAsync(w.ref_raw, ref_frame, (size_t)n_atoms_ref * 12, cudaMemcpyHostToDevice, s0));
+    if (idx) {
+        CU(cudaMemcpyAsync(w.idx, idx, (size_t)n_sel * 4, cudaMemcpyHostToDevice, s0));
+        CU(cudaMemcpyAsync(w.ref_idx, ref_idx, (size_t)n_sel * 4, cudaMemcpyHostToDevice, s0));
+    }
+    CU(launch_prepare_ref(w.ref_raw, idx ? w.ref_idx : nullptr, n_use, 1, 0.f, w.ref_sel, w.stats, s0));
+    CU(cudaEventRecord(w.ref_ready, s0));
+    CU(cudaStreamWaitEvent(w.stream[1], w.ref_ready, 0));
+
+    int slot = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += fpc, slot ^= 1) {
+        const int64_t nf = std::min(fpc, n_frames - f0);
+        cudaStream_t st = w.stream[slot];
+        CU(upload_chunk(w.xyz[slot], xyz, f0, nf, n_atoms, n_pad, st));
+        int rc = b200rmsd_superpose_dev(w.xyz[slot], nf, n_atoms, (int64_t)n_pad * 3, idx ? w.idx : nullptr, n_sel,
+                                        w.ref_sel, w.stats, w.out[slot], w.rot[slot], w.degen, w.scratch[slot],
+                                        w.scratch_bytes, st);
+        if (rc) return rc;
+        CU(download_chunk(xyz, w.xyz[slot], f0, nf, n_atoms, n_pad, st));
+        if (out_rot) CU(cudaMemcpyAsync(out_rot + f0 * 9, w.rot[slot], (size_t)nf * 36, cudaMemcpyDeviceToHost, st));
+        if (out_rmsd) CU(cudaMemcpyAsync(out_rmsd + f0, w.out[slot], (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(w.stream[0]));
+    CU(cudaStreamSynchronize(w.stream[1]));
+    if (n_degenerate) CU(cudaMemcpy(n_degenerate, w.degen, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int b200rmsd_center_host(float* xyz, int64_t n_frames, int n_atoms, float* traces, int device)
+{
+    if (!xyz || n_frames < 0 || n_atoms <= 0) return fail(B200RMSD_EINVAL, "center_host: bad arguments");
+    if (device < 0 || device >= 64) return fail(B200RMSD_EINVAL, "center_host: device %d", device);
+    if (n_frames == 0) return 0;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(B200RMSD_ENODEVICE, "center_host: cannot select CUDA device %d", device);
+    int sm = 0;
+    if (int rc = current_sm_count(&sm)) return rc;
+    Workspace& w = g_ws[device];
+    std::lock_guard<std::mutex> lk(w.mu);
+    const int n_pad = (n_atoms + 3) / 4 * 4;
+    const int64_t fpc = frames_per_chunk(n_frames, n_pad);
+    if (int rc = ws_prepare(w, (size_t)fpc * n_pad * 12, (size_t)fpc, 256, 4, 0)) return rc;
+    int slot = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += fpc, slot ^= 1) {
+        const int64_t nf = std::min(fpc, n_frames - f0);
+        cudaStream_t st = w.stream[slot];
+        CU(upload_chunk(w.xyz[slot], xyz, f0, nf, n_atoms, n_pad, st));
+        CU(launch_center_trace(w.xyz[slot], nf, n_atoms, (int64_t)n_pad * 3, w.trc[slot], sm, st));
+        CU(download_chunk(xyz, w.xyz[slot], f0, nf, n_atoms, n_pad, st));
+        if (traces) CU(cudaMemcpyAsync(traces + f0, w.trc[slot], (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(w.stream[0]));
+    CU(cudaStreamSynchronize(w.stream[1]));
+    return 0;
+}
+
+void b200rmsd_release_workspaces(void)
+{
+    for (int d = 0; d < 64; ++d) {
+        Workspace& w = g_ws[d];
+        std::lock_guard<std::mutex> lk(w.mu);
+        if (!w.init) continue;
+        int prev = -1;
+        cudaGetDevice(&prev);
+        if (cudaSetDevice(d) == cudaSuccess) {
+            for (int i = 0; i < 2; ++i) {
+                cudaFree(w.xyz[i]); cudaFree(w.out[i]); cudaFree(w.rot[i]); cudaFree(w.trc[i]); cudaFree(w.scratch[i]);
+                w.xyz[i] = w.out[i] = w.rot[i] = w.trc[i] = nullptr; w.scratch[i] = nullptr;
+                cudaStreamDestroy(w.stream[i]);
+            }
+            cudaFree(w.ref_raw); cudaFree(w.ref_sel); cudaFree(w.idx); cudaFree(w.ref_idx); cudaFree(w.stats); cudaFree(w.degen);
+            cudaEventDestroy(w.ref_ready);
+        }
+        if (prev >= 0) cudaSetDevice(prev);
+        w.reset();
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// common.cuh -- sm_100a PTX wrappers shared by the RMSD kernels.
+//
+// mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP / SYNCS), cache-hinted
+// vector loads/stores, and the 16-value warp reduce-scatter used by every
+// streaming kernel.  No library dependencies.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier -------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    // make the inits visible to the async proxy before any bulk copy targets them
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// generic-proxy accesses before this point are ordered before later async-proxy
+// (bulk copy) accesses to the same shared memory
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- 1-D bulk copies (TMA engine, no tensor map needed) ---------------------
+// global -> shared, completion counted in bytes on an mbarrier.  src/dst 16-byte
+// aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// same, with an L2 eviction-priority policy (streamed-once data: evict_first)
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// shared -> global
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---- streaming vector global access -----------------------------------------
+__device__ __forceinline__ float4 ldg_stream(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+// ---- 16-value warp reduce-scatter -------------------------------------------
+// Every lane holds v[0..15]; on return v[0] of lane L is sum over all 32 lanes of
+// value index (L >> 1).  16 shuffles instead of 80 for 16 separate all-reduces.
+__device__ __forceinline__ void warp_reduce_scatter16(float (&v)[16], int lane)
+{
+    const unsigned full = 0xffffffffu;
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float send = up ? v[j] : v[j + 8];
+            const float keep = up ? v[j + 8] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float send = up ? v[j] : v[j + 4];
+            const float keep = up ? v[j + 4] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float send = up ? v[j] : v[j + 2];
+            const float keep = up ? v[j + 2] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, 4);
+        }
+    }
+    {
+        const bool up = lane & 2;
+        const float send = up ? v[0] : v[1];
+        const float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(full, send, 2);
+    }
+    v[0] += __shfl_xor_sync(full, v[0], 1);
+}
+
+__device__ __forceinline__ double warp_sum(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ float warp_sum(float x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+}  // namespace b200

@@ -1,0 +1,68 @@
+// kernels.cuh -- launch-parameter structs and launcher prototypes (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kWarpsPerCta = 16;               // streaming kernels: 512 threads, 1 CTA / SM
+constexpr int kThreadsPerCta = kWarpsPerCta * 32;
+constexpr int kBatch = 16;                     // frames solved together (one lane each) per warp
+constexpr int kSumStride = 17;                 // padded stride of a 16-value sum record in smem
+constexpr int kUnitFloats = 12;                // one "unit" = 4 atoms = 48 bytes = 3 x float4
+constexpr int kMaxSegUnits = 1024;             // reference segment resident in smem: <= 4096 atoms (48 KB)
+
+// reference-frame statistics written by prepare_ref_kernel (device memory)
+struct RefStats {
+    double G;       // trace of the centred reference selection
+    double sum[3];  // residual sum of the float32-centred reference (~0)
+    double mean[3]; // centroid that was removed (float64)
+};
+
+struct OvmParams {
+    const float* xyz;       // (F, frame_stride) floats, atom-major, padded to a multiple of 4 atoms
+    int64_t n_frames;
+    int64_t frame_stride;   // floats between consecutive frames (multiple of 4)
+    int n_atoms;            // real atoms taking part (== n_sel when idx != nullptr)
+    const int* idx;         // optional atom selection (gather path), length n_atoms
+    const float* ref;       // centred reference selection, (n_pad,3) floats, zero padded
+    const RefStats* ref_stats;
+    const float* traces;    // precentered mode: per-frame traces, else nullptr
+    float* out_rmsd;        // (F)
+    float* out_rot;         // (F,9) or nullptr
+    double* out_centroid;   // (F,3) or nullptr
+    unsigned int* degenerate;  // counter of identity-fallback rotations, or nullptr
+    // tiling of the TMA path
+    int n_seg;              // atom segments (1 => fused epilogue)
+    int seg_units;          // units per segment (last may be shorter)
+    int total_units;        // ceil(n_atoms/4)
+    int chunk_units;        // units per bulk copy
+    int stages;             // ring depth per warp
+    float* partials;        // (F, n_seg, 16) when n_seg > 1
+};
+
+struct ApplyParams {
+    float* xyz;             // in/out (F, frame_stride)
+    int64_t n_frames;
+    int64_t frame_stride;
+    int n_atoms;
+    const float* rot;       // (F,9)
+    const double* centroid; // (F,3) removed before rotation
+    const RefStats* ref_stats;  // mean[] added after rotation
+};
+
+cudaError_t launch_ovm_tma(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st);
+cudaError_t launch_ovm_gather(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st);
+cudaError_t launch_prepare_ref(const float* frame, const int* idx, int n_sel, int do_center, float given_trace,
+                               float* ref_out, RefStats* stats, cudaStream_t st);
+cudaError_t launch_center_trace(float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, float* traces,
+                                int sm_count, cudaStream_t st);
+cudaError_t launch_nosuperpose(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const int* idx,
+                               const float* ref_raw, float* out, int sm_count, cudaStream_t st);
+cudaError_t launch_apply_transform(const ApplyParams& p, int sm_count, cudaStream_t st);
+size_t ovm_tma_smem_bytes(const OvmParams& p);
+
+// records a thread-local message for b200rmsd_last_error() and returns `code` (defined in capi.cu)
+int set_error(int code, const char* fmt, ...);
+
+}  // namespace b200

@@ -1,0 +1,375 @@
+// one_vs_many.cu -- the HBM-bound streaming kernels of the RMSD hot path (sm_100a).
+//
+//   ovm_tma_kernel      every frame of a padded atom-major trajectory against ONE
+//                       reference frame: centroid + trace G + 3x3 inner product M in
+//                       a single pass over HBM, then the QCP solve in registers.
+//                       Replaces the three-pass CPU sequence
+//                         inplace_center_and_trace_atom_major   center_sse.h:3-112
+//                         msd_atom_major                        theobald_rmsd_sse.h:184-335
+//                         msdFromMandG                          theobald_rmsd.cpp:217-334
+//                       driven by the prange loop at _rmsd.pyx:217-224.
+//   ovm_gather_kernel   same maths for an atom_indices selection (replaces the
+//                       fancy-index copy at _rmsd.pyx:197 + the loop above).
+//   ovm_finish_kernel   combines per-segment partial sums when a frame is split.
+//
+// Design:
+//   * persistent grid, one 512-thread CTA per SM, static contiguous frame ranges
+//     per warp (output stays coalesced, imbalance < 1 frame per warp);
+//   * each warp owns a ring of shared-memory stages filled by 1-D bulk async copies
+//     (cp.async.bulk -> UBLKCP) that complete on mbarriers; lane 0 is the producer,
+//     all 32 lanes consume with conflict-free 128-bit shared loads (48-byte lane
+//     stride = 4 whole atoms per lane);
+//   * the centred reference (<= 4096 atoms per segment) is resident in shared memory
+//     for the whole kernel; longer frames are split into atom segments across CTAs
+//     and finished by ovm_finish_kernel;
+//   * single pass: sums are taken about a per-frame pivot (the frame's first atom),
+//     so  G = sum|x-p|^2 - N|mu-p|^2  loses one bit instead of log2(|offset|^2/Rg^2);
+//     since the reference frame is centred, M needs no centring of the target;
+//   * float32 lane partials (<= a few dozen terms each), one 16-value reduce-scatter
+//     per frame (16 shuffles), then everything -- recentring, polynomial, Newton,
+//     the G_a+G_b-2*lambda cancellation, quaternion -- in float64 on one lane per
+//     frame, kBatch frames at a time.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "qcp.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------
+// per-frame epilogue: 16 float32 sums -> rmsd (+ rotation, centroid)
+//   rec[0..2]  = sum (x - p)          rec[3] = sum |x - p|^2
+//   rec[4..12] = sum (x - p)_i y_j    rec[13..15] = pivot p
+// ---------------------------------------------------------------------------
+template <bool PRE>
+__device__ __forceinline__ void finish_frame(const double rec[16], int64_t f, const OvmParams& p)
+{
+    const RefStats rs = *p.ref_stats;
+    QcpInput q;
+    q.n_atoms = p.n_atoms;
+    q.Gb = rs.G;
+    const double invn = 1.0 / (double)p.n_atoms;
+    double cx = 0, cy = 0, cz = 0;
+    if (PRE) {
+        q.Ga = (double)p.traces[f];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) q.M[i] = rec[4 + i];
+    } else {
+        const double mx = rec[0] * invn, my = rec[1] * invn, mz = rec[2] * invn;  // mean relative to pivot
+        double ga = rec[3] - (rec[0] * mx + rec[1] * my + rec[2] * mz);
+        q.Ga = ga > 0.0 ? ga : 0.0;
+        // M_c = M' - N mu' (mu_y)^T ; mu_y is the float32 residual of the centred reference
+        q.M[0] = rec[4] - mx * rs.sum[0];  q.M[1] = rec[5] - mx * rs.sum[1];  q.M[2] = rec[6] - mx * rs.sum[2];
+        q.M[3] = rec[7] - my * rs.sum[0];  q.M[4] = rec[8] - my * rs.sum[1];  q.M[5] = rec[9] - my * rs.sum[2];
+        q.M[6] = rec[10] - mz * rs.sum[0]; q.M[7] = rec[11] - mz * rs.sum[1]; q.M[8] = rec[12] - mz * rs.sum[2];
+        cx = rec[13] + mx; cy = rec[14] + my; cz = rec[15] + mz;
+    }
+    float R[9];
+    bool degen = false;
+    const double msd = qcp_solve(q, p.out_rot ? R : nullptr, &degen);
+    p.out_rmsd[f] = (float)sqrt(msd);
+    if (p.out_rot) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) p.out_rot[f * 9 + i] = R[i];
+        if (degen && p.degenerate) atomicAdd(p.degenerate, 1u);
+    }
+    if (p.out_centroid) {
+        p.out_centroid[f * 3 + 0] = cx;
+        p.out_centroid[f * 3 + 1] = cy;
+        p.out_centroid[f * 3 + 2] = cz;
+    }
+}
+
+// accumulate one atom
+template <bool PRE>
+__device__ __forceinline__ void acc_atom(float (&v)[16], float ax, float ay, float az, float bx, float by, float bz,
+                                         float px, float py, float pz)
+{
+    if (!PRE) {
+        ax -= px; ay -= py; az -= pz;
+        v[0] += ax; v[1] += ay; v[2] += az;
+        v[3] = fmaf(ax, ax, v[3]); v[3] = fmaf(ay, ay, v[3]); v[3] = fmaf(az, az, v[3]);
+    }
+    v[4] = fmaf(ax, bx, v[4]);   v[5] = fmaf(ax, by, v[5]);   v[6] = fmaf(ax, bz, v[6]);
+    v[7] = fmaf(ay, bx, v[7]);   v[8] = fmaf(ay, by, v[8]);   v[9] = fmaf(ay, bz, v[9]);
+    v[10] = fmaf(az, bx, v[10]); v[11] = fmaf(az, by, v[11]); v[12] = fmaf(az, bz, v[12]);
+}
+
+// one unit = 4 atoms held in 3 float4 (x0 y0 z0 x1 | y1 z1 x2 y2 | z2 x3 y3 z3)
+template <bool PRE>
+__device__ __forceinline__ void acc_unit(float (&v)[16], const float4& a0, const float4& a1, const float4& a2,
+                                         const float4& b0, const float4& b1, const float4& b2, float px, float py,
+                                         float pz, int nvalid)
+{
+    acc_atom<PRE>(v, a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, px, py, pz);
+    if (nvalid >= 4) {
+        acc_atom<PRE>(v, a0.w, a1.x, a1.y, b0.w, b1.x, b1.y, px, py, pz);
+        acc_atom<PRE>(v, a1.z, a1.w, a2.x, b1.z, b1.w, b2.x, px, py, pz);
+        acc_atom<PRE>(v, a2.y, a2.z, a2.w, b2.y, b2.z, b2.w, px, py, pz);
+    } else {  // ragged last unit of the frame: padding atoms must not see the pivot
+        if (nvalid > 1) acc_atom<PRE>(v, a0.w, a1.x, a1.y, b0.w, b1.x, b1.y, px, py, pz);
+        if (nvalid > 2) acc_atom<PRE>(v, a1.z, a1.w, a2.x, b1.z, b1.w, b2.x, px, py, pz);
+    }
+}
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct OvmSmemLayout {
+    size_t ref_off, ring_off, sums_off, bar_off, total;
+    size_t stage_bytes;
+};
+__host__ __device__ inline OvmSmemLayout ovm_layout(int seg_units, int chunk_units, int stages)
+{
+    OvmSmemLayout L;
+    L.stage_bytes = (size_t)chunk_units * 48;
+    L.ref_off = 0;
+    L.ring_off = align_up((size_t)seg_units * 48, 128);
+    L.sums_off = L.ring_off + (size_t)kWarpsPerCta * stages * L.stage_bytes;
+    L.bar_off = align_up(L.sums_off + (size_t)kWarpsPerCta * kBatch * kSumStride * sizeof(float), 8);
+    L.total = L.bar_off + ((size_t)kWarpsPerCta * stages + 1) * sizeof(uint64_t);
+    return L;
+}
+size_t ovm_tma_smem_bytes(const OvmParams& p) { return ovm_layout(p.seg_units, p.chunk_units, p.stages).total; }
+
+// ---------------------------------------------------------------------------
+// the streaming kernel
+// grid = n_seg * ctas_per_seg ; CTA b works on segment (b % n_seg)
+// ---------------------------------------------------------------------------
+template <bool PRE>
+__global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const OvmSmemLayout L = ovm_layout(p.seg_units, p.chunk_units, p.stages);
+    const float4* ref_s = reinterpret_cast<const float4*>(smem + L.ref_off);
+    float* sums_all = reinterpret_cast<float*>(smem + L.sums_off);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = blockIdx.x % p.n_seg;
+    const int cta_in_seg = blockIdx.x / p.n_seg;
+    const int ctas_per_seg = gridDim.x / p.n_seg;
+    const int seg_unit0 = seg * p.seg_units;
+    const int upf = min(p.seg_units, p.total_units - seg_unit0);  // units of this segment per frame
+
+    unsigned char* ring = smem + L.ring_off + (size_t)warp * p.stages * L.stage_bytes;
+    uint64_t* my_bars = bars + warp * p.stages;
+    uint64_t* ref_bar = bars + kWarpsPerCta * p.stages;
+    float* sums = sums_all + warp * kBatch * kSumStride;
+
+    if (lane == 0)
+        for (int s = 0; s < p.stages; ++s) mbar_init(&my_bars[s], 1);
+    if (threadIdx.x == 0) mbar_init(ref_bar, 1);
+    fence_mbar_init();
+    __syncthreads();
+
+    if (threadIdx.x == 0) {  // reference segment: loaded once, stays resident
+        const uint32_t bytes = (uint32_t)upf * 48u;
+        mbar_arrive_expect_tx(ref_bar, bytes);
+        bulk_g2s(smem + L.ref_off, p.ref + (size_t)seg_unit0 * kUnitFloats, bytes, ref_bar);
+    }
+
+    // static contiguous frame range of this warp
+    const int64_t W = (int64_t)ctas_per_seg * kWarpsPerCta;
+    const int64_t gw = (int64_t)cta_in_seg * kWarpsPerCta + warp;
+    const int64_t f_begin = p.n_frames * gw / W, f_end = p.n_frames * (gw + 1) / W;
+    const int cpf = (upf + p.chunk_units - 1) / p.chunk_units;  // bulk copies per frame
+    const int64_t total_chunks = (f_end - f_begin) * cpf;
+
+    // producer cursor (meaningful on lane 0 only)
+    int64_t pf = f_begin, issued = 0;
+    int pc = 0;
+    const uint64_t pol = l2_policy_evict_first();
+    auto issue = [&](int stage) {
+        const int units = min(p.chunk_units, upf - pc * p.chunk_units);
+        const uint32_t bytes = (uint32_t)units * 48u;
+        const float* src = p.xyz + pf * p.frame_stride + (size_t)(seg_unit0 + pc * p.chunk_units) * kUnitFloats;
+        mbar_arrive_expect_tx(&my_bars[stage], bytes);
+        bulk_g2s_hint(ring + (size_t)stage * L.stage_bytes, src, bytes, &my_bars[stage], pol);
+        if (++pc == cpf) { pc = 0; ++pf; }
+        ++issued;
+    };
+    if (lane == 0)
+        for (int s = 0; s < p.stages && issued < total_chunks; ++s) issue(s);
+
+    mbar_wait(ref_bar, 0);
+
+    int stage = 0;
+    uint32_t phase = 0;
+    int slot = 0;
+    int64_t batch_f0 = f_begin;
+    float npx = 0.f, npy = 0.f, npz = 0.f;
+    if (!PRE && f_begin < f_end) {
+        const float* fp = p.xyz + f_begin * p.frame_stride;
+        npx = __ldg(fp); npy = __ldg(fp + 1); npz = __ldg(fp + 2);
+    }
+
+#pragma unroll 1
+    for (int64_t f = f_begin; f < f_end; ++f) {
+        const float px = npx, py = npy, pz = npz;
+        if (!PRE && f + 1 < f_end) {  // prefetch next frame's pivot
+            const float* fp = p.xyz + (f + 1) * p.frame_stride;
+            npx = __ldg(fp); npy = __ldg(fp + 1); npz = __ldg(fp + 2);
+        }
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+
+#pragma unroll 1
+        for (int c = 0; c < cpf; ++c) {
+            const int unit0 = c * p.chunk_units;
+            const int units = min(p.chunk_units, upf - unit0);
+            mbar_wait(&my_bars[stage], phase);
+            const float4* xs = reinterpret_cast<const float4*>(ring + (size_t)stage * L.stage_bytes);
+            const float4* ys = ref_s + (size_t)unit0 * 3;
+            const int atom0 = (seg_unit0 + unit0) * 4;
+#pragma unroll 2
+            for (int u = lane; u < units; u += 32) {
+                const float4 a0 = xs[3 * u], a1 = xs[3 * u + 1], a2 = xs[3 * u + 2];
+                const float4 b0 = ys[3 * u], b1 = ys[3 * u + 1], b2 = ys[3 * u + 2];
+                acc_unit<PRE>(v, a0, a1, a2, b0, b1, b2, px, py, pz, p.n_atoms - (atom0 + 4 * u));
+            }
+            __syncwarp();
+            if (lane == 0 && issued < total_chunks) {
+                fence_proxy_async_smem();
+                issue(stage);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+
+        if (lane == 0) { v[13] = px; v[14] = py; v[15] = pz; }
+        warp_reduce_scatter16(v, lane);
+
+        if (p.n_seg > 1) {
+            if (!(lane & 1)) p.partials[((size_t)f * p.n_seg + seg) * 16 + (lane >> 1)] = v[0];
+        } else {
+            if (!(lane & 1)) sums[slot * kSumStride + (lane >> 1)] = v[0];
+            ++slot;
+            if (slot == kBatch || f + 1 == f_end) {
+                __syncwarp();
+                if (lane < slot) {
+                    double rec[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) rec[i] = (double)sums[lane * kSumStride + i];
+                    finish_frame<PRE>(rec, batch_f0 + lane, p);
+                }
+                __syncwarp();
+                slot = 0;
+                batch_f0 = f + 1;
+            }
+        }
+    }
+}
+
+// combine segment partials (float64) and solve; one thread per frame
+template <bool PRE>
+__global__ void ovm_finish_kernel(const OvmParams p)
+{
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= p.n_frames) return;
+    double rec[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) rec[i] = 0.0;
+    for (int s = 0; s < p.n_seg; ++s) {
+        const float4* src = reinterpret_cast<const float4*>(p.partials + ((size_t)f * p.n_seg + s) * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 t = src[i];
+            rec[4 * i] += t.x; rec[4 * i + 1] += t.y; rec[4 * i + 2] += t.z; rec[4 * i + 3] += t.w;
+        }
+    }
+    // every segment carried the same pivot in slots 13..15
+    const double inv = 1.0 / p.n_seg;
+    rec[13] *= inv; rec[14] *= inv; rec[15] *= inv;
+    finish_frame<PRE>(rec, f, p);
+}
+
+// ---------------------------------------------------------------------------
+// atom_indices path: gather 12-byte atoms by index straight from the full frame.
+// One warp per frame at a time, grid-stride over contiguous frame ranges.
+// ---------------------------------------------------------------------------
+template <bool PRE>
+__global__ void __launch_bounds__(256) ovm_gather_kernel(const OvmParams p)
+{
+    __shared__ float sums_all[8 * kBatch * kSumStride];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sums = sums_all + warp * kBatch * kSumStride;
+    const int64_t W = (int64_t)gridDim.x * 8;
+    const int64_t gw = (int64_t)blockIdx.x * 8 + warp;
+    const int64_t f_begin = p.n_frames * gw / W, f_end = p.n_frames * (gw + 1) / W;
+    const int n = p.n_atoms;
+    const int piv = p.idx ? __ldg(p.idx) : 0;
+    int slot = 0;
+    int64_t batch_f0 = f_begin;
+
+#pragma unroll 1
+    for (int64_t f = f_begin; f < f_end; ++f) {
+        const float* fr = p.xyz + f * p.frame_stride;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (!PRE) { px = __ldg(fr + 3 * piv); py = __ldg(fr + 3 * piv + 1); pz = __ldg(fr + 3 * piv + 2); }
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+#pragma unroll 4
+        for (int k = lane; k < n; k += 32) {
+            const int a = p.idx ? __ldg(p.idx + k) : k;
+            const float ax = __ldg(fr + 3 * a), ay = __ldg(fr + 3 * a + 1), az = __ldg(fr + 3 * a + 2);
+            const float bx = __ldg(p.ref + 3 * k), by = __ldg(p.ref + 3 * k + 1), bz = __ldg(p.ref + 3 * k + 2);
+            acc_atom<PRE>(v, ax, ay, az, bx, by, bz, px, py, pz);
+        }
+        if (lane == 0) { v[13] = px; v[14] = py; v[15] = pz; }
+        warp_reduce_scatter16(v, lane);
+        if (!(lane & 1)) sums[slot * kSumStride + (lane >> 1)] = v[0];
+        ++slot;
+        if (slot == kBatch || f + 1 == f_end) {
+            __syncwarp();
+            if (lane < slot) {
+                double rec[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) rec[i] = (double)sums[lane * kSumStride + i];
+                finish_frame<PRE>(rec, batch_f0 + lane, p);
+            }
+            __syncwarp();
+            slot = 0;
+            batch_f0 = f + 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+cudaError_t launch_ovm_tma(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st)
+{
+    if (p.n_frames <= 0) return cudaSuccess;
+    const size_t smem = ovm_tma_smem_bytes(p);
+    auto kern = precentered ? ovm_tma_kernel<true> : ovm_tma_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int ctas_per_seg = sm_count / p.n_seg;
+    if (ctas_per_seg < 1) ctas_per_seg = 1;
+    // do not launch more warps than frames
+    const int64_t need = (p.n_frames + kWarpsPerCta - 1) / kWarpsPerCta;
+    if ((int64_t)ctas_per_seg > need) ctas_per_seg = (int)need;
+    kern<<<p.n_seg * ctas_per_seg, kThreadsPerCta, smem, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (p.n_seg > 1) {
+        auto fin = precentered ? ovm_finish_kernel<true> : ovm_finish_kernel<false>;
+        const int threads = 128;
+        fin<<<(unsigned)((p.n_frames + threads - 1) / threads), threads, 0, st>>>(p);
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+cudaError_t launch_ovm_gather(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st)
+{
+    if (p.n_frames <= 0) return cudaSuccess;
+    auto kern = precentered ? ovm_gather_kernel<true> : ovm_gather_kernel<false>;
+    int64_t ctas = (int64_t)sm_count * 8;  // 8 x 256 threads = full occupancy
+    const int64_t need = (p.n_frames + 7) / 8;
+    if (ctas > need) ctas = need;
+    kern<<<(unsigned)ctas, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -1,0 +1,106 @@
+// qcp.cuh -- per-frame QCP solve in registers (double), shared by every kernel.
+//
+// Replaces msdFromMandG + DirectSolve (mdtraj/rmsd/src/theobald_rmsd.cpp:217-334,
+// :183-193).  Same polynomial, same root, same quaternion-from-cofactors rotation
+// and the same identity fallback; what differs is by design:
+//   * the reference forms K, C2, C1, C0 in float32 and the final G_a+G_b-2*lambda
+//     cancellation in float32 (:275); here everything after the streamed float32
+//     partial sums is double, so the result sits closer to the float64 truth than
+//     the reference does;
+//   * the root comes from Newton-Raphson on the quartic from lambda0 = (G_a+G_b)/2
+//     (monotone from above, the largest root), not from the closed-form Ferrari
+//     route -- no acos/cos/pow on the device.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+struct QcpInput {
+    double M[9];  // M[3*i+j] = sum_k a_k[i] * b_k[j], both frames centred
+    double Ga, Gb;
+    int n_atoms;
+};
+
+// largest root of  t^4 + C2 t^2 + C1 t + C0
+__device__ __forceinline__ double qcp_newton(double C2, double C1, double C0, double lam0)
+{
+    double lam = lam0;
+#pragma unroll 1
+    for (int it = 0; it < 64; ++it) {
+        const double l2 = lam * lam;
+        const double b = (l2 + C2) * lam;
+        const double a = b + C1;
+        const double den = 2.0 * l2 * lam + b + a;
+        if (den == 0.0) break;
+        const double delta = (a * lam + C0) / den;
+        lam -= delta;
+        if (fabs(delta) <= 1e-15 * fabs(lam)) break;
+    }
+    return lam;
+}
+
+// Returns the clamped msd.  If rot != nullptr also writes the row-major rotation
+// (applied as row-vector * R, rotation_generic.h:40-42) and returns whether the
+// reference's degenerate-quaternion branch (theobald_rmsd.cpp:299-302) was taken.
+__device__ __forceinline__ double qcp_solve(const QcpInput& in, float* rot, bool* degenerate)
+{
+    const double Sxx = in.M[0], Sxy = in.M[1], Sxz = in.M[2];
+    const double Syx = in.M[3], Syy = in.M[4], Syz = in.M[5];
+    const double Szx = in.M[6], Szy = in.M[7], Szz = in.M[8];
+
+    double k00 = Sxx + Syy + Szz;
+    const double k01 = Szy - Syz, k02 = Sxz - Szx, k03 = Syx - Sxy;
+    double k11 = Sxx - Syy - Szz;
+    const double k12 = Syx + Sxy, k13 = Sxz + Szx;
+    double k22 = -Sxx + Syy - Szz;
+    const double k23 = Szy + Syz;
+    double k33 = -Sxx - Syy + Szz;
+
+    double ss = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ss += in.M[i] * in.M[i];
+    const double C2 = -2.0 * ss;
+    const double detM = Sxx * (Syy * Szz - Syz * Szy) + Syx * (Szy * Sxz - Szz * Sxy) + Szx * (Sxy * Syz - Sxz * Syy);
+    const double C1 = -8.0 * detM;
+
+    // det(K) by 2x2 minors of the (rows 0,1) x (rows 2,3) Laplace expansion
+    const double a01 = k00 * k11 - k01 * k01, a02 = k00 * k12 - k02 * k01, a03 = k00 * k13 - k03 * k01;
+    const double a12 = k01 * k12 - k02 * k11, a13 = k01 * k13 - k03 * k11, a23 = k02 * k13 - k03 * k12;
+    const double b01 = k02 * k13 - k12 * k03, b02 = k02 * k23 - k22 * k03, b03 = k02 * k33 - k23 * k03;
+    const double b12 = k12 * k23 - k22 * k13, b13 = k12 * k33 - k23 * k13, b23 = k22 * k33 - k23 * k23;
+    const double C0 = a01 * b23 - a02 * b13 + a03 * b12 + a12 * b03 - a13 * b02 + a23 * b01;
+
+    const double lam = qcp_newton(C2, C1, C0, 0.5 * (in.Ga + in.Gb));
+    double msd = (in.Ga + in.Gb - 2.0 * lam) / in.n_atoms;
+    if (!(msd > 0.0)) msd = 0.0;
+
+    if (rot != nullptr) {
+        k00 -= lam; k11 -= lam; k22 -= lam; k33 -= lam;
+        const double m2233 = k22 * k33 - k23 * k23, m1233 = k12 * k33 - k13 * k23, m1223 = k12 * k23 - k13 * k22;
+        const double m0223 = k02 * k23 - k03 * k22, m0233 = k02 * k33 - k03 * k23, m0213 = k02 * k13 - k03 * k12;
+        double qa = k11 * m2233 - k12 * m1233 + k13 * m1223;
+        double qx = -k01 * m2233 + k12 * m0233 - k13 * m0223;
+        double qy = k01 * m1233 - k11 * m0233 + k13 * m0213;
+        double qz = -k01 * m1223 + k11 * m0223 - k12 * m0213;
+        const double n2 = qa * qa + qx * qx + qy * qy + qz * qz;
+        const bool degen = n2 < 1e-11;  // same absolute threshold as the reference
+        if (degenerate) *degenerate = degen;
+        if (degen) {
+            rot[0] = rot[4] = rot[8] = 1.0f;
+            rot[1] = rot[2] = rot[3] = rot[5] = rot[6] = rot[7] = 0.0f;
+        } else {
+            const double inv = rsqrt(n2);
+            qa *= inv; qx *= inv; qy *= inv; qz *= inv;
+            const double aa = qa * qa, xx = qx * qx, yy = qy * qy, zz = qz * qz;
+            const double xy = qx * qy, az = qa * qz, zx = qz * qx, ay = qa * qy, yz = qy * qz, ax = qa * qx;
+            rot[0] = (float)(aa + xx - yy - zz); rot[1] = (float)(2.0 * (xy - az)); rot[2] = (float)(2.0 * (zx + ay));
+            rot[3] = (float)(2.0 * (xy + az)); rot[4] = (float)(aa - xx + yy - zz); rot[5] = (float)(2.0 * (yz - ax));
+            rot[6] = (float)(2.0 * (zx - ay)); rot[7] = (float)(2.0 * (yz + ax)); rot[8] = (float)(aa - xx - yy + zz);
+        }
+    } else if (degenerate) {
+        *degenerate = false;
+    }
+    return msd;
+}
+
+}  // namespace b200

@@ -1,0 +1,312 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against
+  (1) golden vectors produced by the real reference (tests/golden/make_golden.py),
+  (2) the CPU oracle (oracle/, C restatement + compiled reference when shipped),
+  (3) float64 Kabsch truth,
+on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): RMSD 1e-5 nm absolute or 1e-4 relative; rotation-matrix
+elements 1e-5; superposed coordinates 1e-5 nm (float32 coordinates of magnitude <= ~10 nm carry
+~5e-7 nm of rounding each way); atom selection / frame order exact.
+Mirrors the reference's tests/test_rmsd.py where noted.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ATOL, RTOL = 1e-5, 1e-4
+SYNTH = [("iid", 64, 100, 11), ("iid", 33, 22, 12), ("iid", 16, 1000, 13), ("md", 40, 303, 14), ("iid", 5, 4100, 15)]
+
+
+def close(a, b, atol=ATOL, rtol=RTOL):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return bool(np.all(np.abs(a - b) <= np.maximum(atol, rtol * np.abs(b))))
+
+
+def assert_close(a, b, atol=ATOL, rtol=RTOL, what=""):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    err = np.abs(a - b)
+    ok = err <= np.maximum(atol, rtol * np.abs(b))
+    assert ok.all(), f"{what}: max abs err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+def gen(O, kind, F, N, seed):
+    return (O.synth_iid if kind == "iid" else O.synth_md)(F, N, seed=seed)
+
+
+# ------------------------------------------------------------------ C1: ala2 golden
+def test_ala2_rmsd_matches_reference(mdb, golden, ala2):
+    t = mdb.Trajectory(ala2.copy())
+    d = mdb.rmsd(t, t, 0)
+    assert d.dtype == np.float32 and d.shape == (100,)
+    assert d[0] == 0.0
+    assert_close(d, golden["ala2_rmsd_frame0"], what="ala2 rmsd vs reference")
+    assert abs(float(d.max()) - 0.16302569) < 1e-5
+
+
+def test_ala2_device_path_and_precentered(mdb, golden, ala2):
+    dt = mdb.DeviceTrajectory.from_host(ala2)
+    d = mdb.rmsd(dt, dt, 0)
+    assert_close(d, golden["ala2_rmsd_frame0"], what="device path")
+    dt.center_coordinates()
+    assert_close(dt.xyz, golden["ala2_centered_xyz"], atol=2e-7, rtol=0, what="centred coordinates")
+    assert_close(dt._rmsd_traces.cpu().numpy(), golden["ala2_traces"], atol=0, rtol=1e-6, what="traces")
+    d5 = mdb.rmsd(dt, dt, 5, precentered=True)
+    assert_close(d5, golden["ala2_rmsd_frame5_precentered"], what="precentered")
+    # host precentered path
+    t = mdb.Trajectory(ala2.copy())
+    t.center_coordinates()
+    assert_close(t.xyz, golden["ala2_centered_xyz"], atol=2e-7, rtol=0, what="host centred coordinates")
+    assert_close(mdb.rmsd(t, t, 5, precentered=True), golden["ala2_rmsd_frame5_precentered"], what="host precentered")
+
+
+def test_ala2_nosuperpose(mdb, golden, ala2):
+    t = mdb.Trajectory(ala2.copy())
+    assert_close(mdb.rmsd(t, t, 3, superpose=False), golden["ala2_rmsd_frame3_nosuperpose"], what="superpose=False")
+
+
+def test_ala2_allpairs_known_answers(mdb, golden, ala2):
+    """examples/clustering.ipynb:73 (0.188493) and examples/centroids.ipynb:111 (83)."""
+    t = mdb.Trajectory(ala2.copy())
+    D = mdb.rmsd_matrix(t)
+    assert D.shape == (100, 100) and D.dtype == np.float32
+    assert_close(D, golden["ala2_allpairs"], what="all-pairs vs reference loop")
+    assert "%f" % D.max() == "0.188493"
+    assert np.all(np.diag(D) == 0)
+    assert np.abs(D - D.T).max() < 1e-6  # clustering.ipynb cell 8
+    heavy = golden["ala2_heavy_idx"]
+    Dh = mdb.rmsd_matrix(t, atom_indices=heavy)
+    off = ~np.eye(100, dtype=bool)  # with an index list the reference's diagonal is float32 noise, not 0
+    assert_close(Dh[off], golden["ala2_allpairs_heavy"][off], what="heavy-atom all-pairs")
+    index = np.exp(-1 * Dh / Dh.std()).sum(axis=1).argmax()
+    assert index == 83 == int(golden["ala2_centroid_index"])
+
+
+def test_ala2_rows_equal_one_vs_many(mdb, ala2):
+    dt = mdb.DeviceTrajectory.from_host(ala2)
+    D = mdb.rmsd_matrix(dt)
+    for i in (0, 17, 99):
+        assert_close(D[i], mdb.rmsd(dt, dt, i), atol=2e-6, what=f"row {i}")
+
+
+def test_ala2_superpose(mdb, golden, ala2):
+    t = mdb.Trajectory(ala2.copy()); r = mdb.Trajectory(ala2.copy())
+    ret = t.superpose(r, 7)
+    assert ret is t and t._rmsd_traces is None
+    assert np.array_equal(r.xyz, ala2)  # reference never mutated (tests/test_rmsd.py:131-140)
+    assert_close(t.xyz, golden["ala2_superposed_frame7"], what="superpose all atoms")
+    t = mdb.Trajectory(ala2.copy())
+    t.superpose(r, 2, atom_indices=golden["ala2_heavy_idx"])
+    assert_close(t.xyz, golden["ala2_superposed_frame2_heavy"], what="superpose heavy atoms")
+
+
+# ------------------------------------------------------------------ seeded synthetic golden
+@pytest.mark.parametrize("kind,F,N,seed", SYNTH)
+def test_synthetic_golden(mdb, golden, oracle_mod, kind, F, N, seed):
+    O = oracle_mod
+    X = gen(O, kind, F, N, seed)
+    key = f"{kind}_{F}x{N}_s{seed}"
+    idx = np.arange(0, N, 3)
+    t = mdb.Trajectory(X.copy())
+    d = mdb.rmsd(t, t, 1)
+    assert np.array_equal(t.xyz, X)  # host arrays untouched by default (documented deviation)
+    assert_close(d, golden[key + "_rmsd_f1"], what="rmsd")
+    # three-way report against float64 truth
+    truth = O.truth_rmsd(X, X, 1)
+    e_gpu, e_ref = np.abs(d - truth).max(), np.abs(golden[key + "_rmsd_f1"] - truth)[np.arange(F) != 1].max()
+    assert e_gpu <= max(ATOL, 2 * e_ref), (e_gpu, e_ref)
+    assert_close(mdb.rmsd(t, t, 2, atom_indices=idx), golden[key + "_rmsd_f2_idx3"], what="atom_indices")
+    assert_close(mdb.rmsd(t, t, 0, atom_indices=idx, ref_atom_indices=idx[::-1].copy()),
+                 golden[key + "_rmsd_f0_idx3_refrev"], what="ref_atom_indices")
+    assert_close(mdb.rmsd(t, t, 1, superpose=False), golden[key + "_rmsd_f1_nosup"], what="superpose=False")
+    # device-resident path gives the same numbers as the host-streamed path
+    dt = mdb.DeviceTrajectory.from_host(X)
+    assert np.array_equal(mdb.rmsd(dt, dt, 1), d)
+    assert np.array_equal(mdb.rmsd(dt, dt, 2, atom_indices=idx), mdb.rmsd(t, t, 2, atom_indices=idx))
+    # superpose
+    a = mdb.Trajectory(X.copy()); r = mdb.Trajectory(X.copy())
+    a.superpose(r, 1, atom_indices=idx)
+    assert_close(a.xyz, golden[key + "_superposed_f1_idx3"], what="superpose idx")
+    b = mdb.Trajectory(X.copy())
+    b.superpose(r, 0)
+    assert_close(b.xyz, golden[key + "_superposed_f0"], what="superpose all")
+    dt.superpose(dt, 0)
+    assert_close(dt.xyz, golden[key + "_superposed_f0"], what="device superpose")
+    # centring
+    c = mdb.Trajectory(X.copy())
+    c.center_coordinates()
+    assert_close(c._rmsd_traces, golden[key + "_traces"], atol=0, rtol=1e-6, what="traces")
+    assert np.abs(c.xyz.mean(1)).max() < 1e-6  # tests/test_trajectory.py:316-344
+    assert_close(mdb.rmsd(c, c, 1, precentered=True), golden[key + "_rmsd_f1"], what="precentered == on the fly")
+
+
+# ------------------------------------------------------------------ oracle on fresh inputs
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 7, 31, 32, 33, 127, 128, 255, 1000, 4096, 4100, 9000])
+def test_rmsd_vs_oracle_ragged_sizes(mdb, oracle_mod, N):
+    """Every padding remainder, sub-warp frames, the segment boundary (4096) and multi-segment frames."""
+    O = oracle_mod
+    F = 37 if N < 2000 else 9
+    X = O.synth_iid(F, N, seed=100 + N) + np.float32(3.0)  # off-origin on purpose
+    impl = "reference" if O.ref_available() else "port"
+    want = O.rmsd(X, X, 2, impl=impl)
+    truth = O.truth_rmsd(X, X, 2)
+    for target in (mdb.Trajectory(X.copy()), mdb.DeviceTrajectory.from_host(X)):
+        got = mdb.rmsd(target, target, 2)
+        m = np.arange(F) != 2
+        if N >= 3:
+            assert_close(got[m], want[m], what=f"N={N} vs oracle({impl})")
+        assert_close(got[m], truth[m], what=f"N={N} vs float64 truth")
+        assert got[2] == 0.0
+
+
+def test_rotation_parity_md(mdb, oracle_mod):
+    """Rotation matrices on well-conditioned (MD-like) data: 1e-5 per element vs reference and truth."""
+    O = oracle_mod
+    X = O.synth_md(48, 1000, seed=5, rg=1.5, sigma=0.1)
+    idx = np.arange(0, 1000, 5)
+    impl = "reference" if O.ref_available() else "port"
+    want_xyz, want_R = O.superpose(X, X, 0, idx, impl=impl, return_rot=True)
+    truth_xyz, truth_R = O.truth_superpose(X, X, 0, idx)
+    dt = mdb.DeviceTrajectory.from_host(X)
+    _, R = dt.superpose(dt, 0, atom_indices=idx, return_rotations=True)
+    R = R.cpu().numpy()
+    assert np.abs(R - truth_R).max() < 1e-5
+    assert np.abs(R - want_R).max() < 1e-5
+    assert_close(dt.xyz, want_xyz, what="superposed coordinates vs oracle")
+    assert_close(dt.xyz, truth_xyz, what="superposed coordinates vs truth")
+    assert np.abs(np.linalg.det(R.astype(np.float64)) - 1).max() < 1e-5
+    # after superposition the plain RMSD equals the QCP RMSD (tests/test_rmsd.py:98-108)
+    ref = mdb.Trajectory(X.copy())
+    plain = mdb.rmsd(dt, ref, 0, atom_indices=idx, superpose=False)
+    qcp = mdb.rmsd(mdb.Trajectory(X.copy()), ref, 0, atom_indices=idx)
+    assert_close(plain[1:], qcp[1:], atol=2e-5, what="superpose then plain rmsd")
+
+
+def test_superpose_semantics(mdb):
+    """tests/test_rmsd.py:111-171, 319-334 restated on the new API."""
+    rng = np.random.RandomState(52)
+    t1 = mdb.Trajectory(rng.randn(10, 100, 3).astype(np.float32))
+    t2 = mdb.Trajectory(rng.randn(10, 100, 3).astype(np.float32) + 100)
+    t2_copy = t2.xyz.copy()
+    t1.superpose(t2)
+    t1.superpose(t2, atom_indices=[1, 2, 3, 4, 5, 6, 7])
+    assert np.array_equal(t2.xyz, t2_copy)
+    assert 99 < t1.xyz.mean() < 101  # translated onto the reference centroid
+    # ref_atom_indices: swapping halves of the reference makes the superposition a no-op
+    n = 20
+    half = rng.randn(1, n // 2, 3).astype(np.float32)
+    other = rng.randn(1, n // 2, 3).astype(np.float32)
+    a = mdb.Trajectory(np.concatenate([half, other], axis=1))
+    b = mdb.Trajectory(np.concatenate([other * 3 + 1, half], axis=1))
+    before = a.xyz.copy()
+    a.superpose(b, 0, atom_indices=np.arange(n // 2), ref_atom_indices=np.arange(n // 2, n))
+    assert np.abs(a.xyz - before).max() < 2e-6
+    with pytest.raises(ValueError):
+        a.superpose(b, 0, atom_indices=[])
+    one = mdb.Trajectory(rng.randn(3, 10, 3).astype(np.float32))
+    one.superpose(one, 0, atom_indices=[4])
+    assert np.isfinite(one.xyz).all()
+
+
+def test_different_atom_counts_with_index_lists(mdb, oracle_mod):
+    """tests/test_rmsd.py:291-316."""
+    O = oracle_mod
+    A = O.synth_iid(12, 40, seed=1); B = O.synth_iid(3, 55, seed=2)
+    ia = np.array([3, 1, 9, 30, 30, 7]); ib = np.array([50, 2, 2, 11, 54, 0])  # unsorted + repeated
+    got = mdb.rmsd(mdb.Trajectory(A.copy()), mdb.Trajectory(B.copy()), 2, atom_indices=ia, ref_atom_indices=ib)
+    want = O.truth_rmsd(A, B, 2, ia, ib)
+    assert_close(got, want, what="index lists on different atom counts")
+    with pytest.raises(ValueError):
+        mdb.rmsd(mdb.Trajectory(A.copy()), mdb.Trajectory(B.copy()), 0)
+
+
+def test_warnings_and_readonly(mdb, golden, oracle_mod):
+    X = oracle_mod.synth_iid(5, 10, 1)
+    t = mdb.Trajectory(X.copy())
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        mdb.rmsd(t, t, 0, precentered=True)
+    assert f"{w[-1].category.__name__}: {w[-1].message}" == str(golden["msg_warn_precentered_no_traces"])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        mdb.rmsd(t, t, 0, precentered=True, superpose=False)
+    assert f"{w[-1].category.__name__}: {w[-1].message}" == str(golden["msg_warn_precentered_nosuperpose"])
+    ro = X.copy(); ro.setflags(write=False)
+
+    class Duck:
+        xyz = ro
+        _rmsd_traces = None
+    with pytest.raises(ValueError, match="read-only"):
+        mdb.rmsd(Duck(), Duck(), 0)
+    assert mdb.rmsd(Duck(), Duck(), 0, atom_indices=[0, 1, 2, 3]).shape == (5,)  # copy path works
+    assert mdb.rmsd(t, t, -1).shape == (5,)  # negative frame is python indexing
+
+
+def test_inplace_centering_compat(mdb, oracle_mod):
+    X = oracle_mod.synth_iid(6, 30, 3) + np.float32(2.0)
+    t = mdb.Trajectory(X.copy())
+    mdb.set_inplace_centering(True)
+    try:
+        mdb.rmsd(t, t, 0)
+    finally:
+        mdb.set_inplace_centering(False)
+    assert np.abs(t.xyz.mean(1)).max() < 1e-6
+
+
+def test_empty_and_single_frame(mdb, oracle_mod):
+    X = oracle_mod.synth_iid(1, 17, 4)
+    t = mdb.Trajectory(X.copy())
+    assert mdb.rmsd(t, t, 0).tolist() == [0.0]
+    e = mdb.Trajectory(np.zeros((0, 17, 3), np.float32))
+    assert mdb.rmsd(e, t, 0).shape == (0,)
+
+
+# ------------------------------------------------------------------ large sizes: size-independent properties
+def test_large_properties(mdb):
+    """At BASELINE-like sizes: (a) rigid motions leave RMSD unchanged; (b) RMSD to a noisy copy equals the
+    injected noise level; (c) frame order is preserved; (d) sharded == unsharded bit for bit."""
+    import torch
+    F, N = 20000, 1000
+    dt = mdb.DeviceTrajectory.synthetic_iid(F, N, seed=7)
+    same = mdb.rmsd_device(dt, dt, 0, as_numpy=False)
+    assert same[0].item() == 0.0 and torch.isfinite(same).all()
+    ref = mdb.DeviceTrajectory(dt.xyz_dev[:1].clone(), N)
+    base = mdb.rmsd_device(dt, ref, 0, as_numpy=False)
+    assert torch.equal(base[1:], same[1:])
+    # (a) rotate + translate every frame by its own rigid motion
+    g = torch.Generator(device=dt.device); g.manual_seed(1)
+    q = torch.randn((F, 4), generator=g, device=dt.device, dtype=torch.float64)
+    q = q / q.norm(dim=1, keepdim=True)
+    a, b, c, d = q.unbind(1)
+    R = torch.stack([a*a+b*b-c*c-d*d, 2*(b*c-a*d), 2*(b*d+a*c), 2*(b*c+a*d), a*a-b*b+c*c-d*d, 2*(c*d-a*b),
+                     2*(b*d-a*c), 2*(c*d+a*b), a*a-b*b-c*c+d*d], dim=1).view(F, 3, 3)
+    moved = torch.bmm(dt.xyz_dev.double(), R) + torch.rand((F, 1, 3), generator=g, device=dt.device, dtype=torch.float64) * 10 - 5
+    dm = mdb.DeviceTrajectory(moved.float().contiguous(), N)
+    moved_r = mdb.rmsd_device(dm, ref, 0, as_numpy=False)
+    assert (moved_r[1:] - base[1:]).abs().max().item() < 1e-5
+    # (c) order: permute frames, results permute identically
+    perm = torch.randperm(F, generator=torch.Generator().manual_seed(3)).to(dt.device)
+    dp = mdb.DeviceTrajectory(dt.xyz_dev[perm].contiguous(), N)
+    pr = mdb.rmsd_device(dp, ref, 0, as_numpy=False)
+    assert torch.equal(pr, base[perm])
+    # (d) two halves computed separately == one call
+    h1 = mdb.rmsd_device(dt[: F // 2], ref, 0, as_numpy=False); h2 = mdb.rmsd_device(dt[F // 2:], ref, 0, as_numpy=False)
+    assert torch.equal(torch.cat([h1, h2]), base)
+    # (b) known noise level
+    noisy = dt.xyz_dev[:1] + 0.05 * torch.randn((2000, N, 3), generator=g, device=dt.device)
+    dn = mdb.DeviceTrajectory(noisy.contiguous(), N)
+    r = mdb.rmsd_device(dn, ref, 0, as_numpy=False)
+    assert abs(r.mean().item() - 0.05 * (3 ** 0.5)) < 2e-3
+
+
+def test_allpairs_vs_truth_random(mdb, oracle_mod):
+    O = oracle_mod
+    X = O.synth_md(70, 300, seed=9, rg=1.0, sigma=0.15)
+    D = mdb.rmsd_matrix(mdb.Trajectory(X.copy()))
+    for i in (0, 33, 69):
+        truth = O.truth_rmsd(X, X, i)
+        m = np.arange(70) != i
+        assert_close(D[i][m], truth[m], what=f"all-pairs row {i} vs truth")
+    assert np.abs(D - D.T).max() < 1e-6
