@@ -32,6 +32,16 @@ def assert_close(a, b, atol=ATOL, rtol=RTOL, what=""):
     assert ok.all(), f"{what}: max abs err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
 
 
+def assert_three_way(got, ref, truth, what="", atol=ATOL):
+    """Parity where the reference itself is float32-noisy (ill-conditioned rotations on
+    iid data, low-RMSD MD-like data at large N): pass when we match the reference within tolerance, or when
+    we are at least as close to the float64 truth as the reference is."""
+    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64); truth = np.asarray(truth, np.float64)
+    e_ref = np.abs(got - ref).max(); e_truth = np.abs(got - truth).max(); ref_truth = np.abs(ref - truth).max()
+    assert e_ref <= atol or e_truth <= max(atol, 1.5 * ref_truth), \
+        f"{what}: |gpu-ref|={e_ref:.3e} |gpu-truth|={e_truth:.3e} |ref-truth|={ref_truth:.3e}"
+
+
 def gen(O, kind, F, N, seed):
     return (O.synth_iid if kind == "iid" else O.synth_md)(F, N, seed=seed)
 
@@ -117,7 +127,12 @@ def test_synthetic_golden(mdb, golden, oracle_mod, kind, F, N, seed):
     truth = O.truth_rmsd(X, X, 1)
     e_gpu, e_ref = np.abs(d - truth).max(), np.abs(golden[key + "_rmsd_f1"] - truth)[np.arange(F) != 1].max()
     assert e_gpu <= max(ATOL, 2 * e_ref), (e_gpu, e_ref)
-    assert_close(mdb.rmsd(t, t, 2, atom_indices=idx), golden[key + "_rmsd_f2_idx3"], what="atom_indices")
+    # with an index list the reference's frame-vs-itself value is float32 noise (up to ~1e-3 nm, Appendix B #15:
+    # the pointer shortcut cannot fire on the fancy-index copy); the truth is 0, so that entry is checked against 0
+    not2 = np.arange(F) != 2
+    d_idx = mdb.rmsd(t, t, 2, atom_indices=idx)
+    assert_close(d_idx[not2], golden[key + "_rmsd_f2_idx3"][not2], what="atom_indices")
+    assert d_idx[2] <= max(1e-5, float(golden[key + "_rmsd_f2_idx3"][2]))
     assert_close(mdb.rmsd(t, t, 0, atom_indices=idx, ref_atom_indices=idx[::-1].copy()),
                  golden[key + "_rmsd_f0_idx3_refrev"], what="ref_atom_indices")
     assert_close(mdb.rmsd(t, t, 1, superpose=False), golden[key + "_rmsd_f1_nosup"], what="superpose=False")
@@ -128,12 +143,13 @@ def test_synthetic_golden(mdb, golden, oracle_mod, kind, F, N, seed):
     # superpose
     a = mdb.Trajectory(X.copy()); r = mdb.Trajectory(X.copy())
     a.superpose(r, 1, atom_indices=idx)
-    assert_close(a.xyz, golden[key + "_superposed_f1_idx3"], what="superpose idx")
+    assert_three_way(a.xyz, golden[key + "_superposed_f1_idx3"], O.truth_superpose(X, X, 1, idx)[0], "superpose idx")
     b = mdb.Trajectory(X.copy())
     b.superpose(r, 0)
-    assert_close(b.xyz, golden[key + "_superposed_f0"], what="superpose all")
+    truth0 = O.truth_superpose(X, X, 0)[0]
+    assert_three_way(b.xyz, golden[key + "_superposed_f0"], truth0, "superpose all")
     dt.superpose(dt, 0)
-    assert_close(dt.xyz, golden[key + "_superposed_f0"], what="device superpose")
+    assert_three_way(dt.xyz, golden[key + "_superposed_f0"], truth0, "device superpose")
     # centring
     c = mdb.Trajectory(X.copy())
     c.center_coordinates()
@@ -156,8 +172,11 @@ def test_rmsd_vs_oracle_ragged_sizes(mdb, oracle_mod, N):
         got = mdb.rmsd(target, target, 2)
         m = np.arange(F) != 2
         if N >= 3:
-            assert_close(got[m], want[m], what=f"N={N} vs oracle({impl})")
-        assert_close(got[m], truth[m], what=f"N={N} vs float64 truth")
+            assert_three_way(got[m], want[m], truth[m], f"N={N} vs oracle({impl})")
+        # float32 products put a floor of ~eps32 * <r^2> / rmsd under any float32-input QCP
+        floor = 3e-7 * float((X.astype(np.float64) - X.mean(1, keepdims=True)).var() * 3) / np.maximum(truth[m], 1e-4)
+        err = np.abs(got[m].astype(np.float64) - truth[m])
+        assert np.all(err <= np.maximum(np.maximum(ATOL, RTOL * truth[m]), floor)), f"N={N} vs truth: {err.max():.3e}"
         assert got[2] == 0.0
 
 
@@ -173,8 +192,9 @@ def test_rotation_parity_md(mdb, oracle_mod):
     _, R = dt.superpose(dt, 0, atom_indices=idx, return_rotations=True)
     R = R.cpu().numpy()
     assert np.abs(R - truth_R).max() < 1e-5
-    assert np.abs(R - want_R).max() < 1e-5
-    assert_close(dt.xyz, want_xyz, what="superposed coordinates vs oracle")
+    # the reference's own float32 rotation is up to ~7e-5 from the truth on this input (three-way report)
+    assert_three_way(R, want_R, truth_R, "rotation elements")
+    assert_three_way(dt.xyz, want_xyz, truth_xyz, "superposed coordinates")
     assert_close(dt.xyz, truth_xyz, what="superposed coordinates vs truth")
     assert np.abs(np.linalg.det(R.astype(np.float64)) - 1).max() < 1e-5
     # after superposition the plain RMSD equals the QCP RMSD (tests/test_rmsd.py:98-108)
@@ -218,7 +238,9 @@ def test_different_atom_counts_with_index_lists(mdb, oracle_mod):
     got = mdb.rmsd(mdb.Trajectory(A.copy()), mdb.Trajectory(B.copy()), 2, atom_indices=ia, ref_atom_indices=ib)
     want = O.truth_rmsd(A, B, 2, ia, ib)
     assert_close(got, want, what="index lists on different atom counts")
-    with pytest.raises(ValueError):
+    # atom-count mismatch without index lists: the reference means to raise ValueError (_rmsd.pyx:178-181) but
+    # trips over len(slice) first (TypeError); we raise the same type it does.
+    with pytest.raises(TypeError):
         mdb.rmsd(mdb.Trajectory(A.copy()), mdb.Trajectory(B.copy()), 0)
 
 
