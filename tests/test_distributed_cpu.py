@@ -1,0 +1,57 @@
+"""CPU, world_size = 2 over gloo: the N>1 host path -- frame partition, ragged all-gather, shortcut
+placement.  The per-shard kernel is replaced by the CPU oracle (test infrastructure standing in for the GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, F, N, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import mdtraj_b200 as mdb
+        from mdtraj_b200 import distributed as D
+        from oracle import oracle as O
+        X = O.synth_iid(F, N, seed=5)
+        t = mdb.Trajectory(X.copy())
+
+        def shard_fn(sub, reference, frame, ai, rai, parallel, precentered, superpose):
+            # stand-in for mdtraj_b200.rmsd on this rank's GPU
+            return O.rmsd(sub.xyz, reference.xyz, frame, ai, rai, superpose=superpose, impl="port")
+        full = D.rmsd_sharded(t, t, 3, shard_fn=shard_fn)
+        a, b = D.shard_bounds(F, rank, world)
+        blk = D.gather_frames(np.full(b - a, float(rank), np.float32), F)
+        q.put((rank, full, blk))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("F", [7, 64])
+def test_rmsd_sharded_world2(F):
+    from oracle import oracle as O
+    N, world = 30, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, F, N, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    X = O.synth_iid(F, N, seed=5)
+    want = O.rmsd(X, X, 3, impl="port")
+    want[3] = 0.0
+    for rank, full, blk in res:
+        assert full.shape == (F,) and np.array_equal(full, want)  # identical to the unsharded result, bit for bit
+        assert np.array_equal(blk, np.concatenate([np.zeros(F // 2, np.float32), np.ones(F - F // 2, np.float32)]))

@@ -1,0 +1,107 @@
+"""CPU: host-side logic of the drop-in boundary -- validation, exceptions and messages identical to the
+reference's (captured verbatim from the real mdtraj by tests/golden/make_golden.py), Trajectory container
+semantics, frame sharding.  None of these reach the GPU."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import mdtraj_b200 as mdb
+from mdtraj_b200 import distributed as D
+
+
+def _t(F=5, N=10, seed=1):
+    rng = np.random.default_rng(seed)
+    return mdb.Trajectory(rng.standard_normal((F, N, 3)).astype(np.float32))
+
+
+def _msg(fn):
+    try:
+        fn()
+    except Exception as e:  # noqa: BLE001
+        return f"{type(e).__name__}: {e}"
+    return "NO ERROR"
+
+
+def test_error_messages_match_reference(golden):
+    t = _t()
+    assert _msg(lambda: mdb.rmsd(t, t, 0, atom_indices=[0, 10])) == str(golden["msg_bad_index"])
+    assert _msg(lambda: mdb.rmsd(t, t, 0, atom_indices=[0, 1], ref_atom_indices=[0])) == str(golden["msg_len_mismatch"])
+    assert _msg(lambda: mdb.rmsd(t, t, 5)) == str(golden["msg_bad_frame"])
+    assert _msg(lambda: mdb.rmsd(t, t, 0, ref_atom_indices=[0, 1])) == str(golden["msg_ref_only_indices"])
+    assert _msg(lambda: t.superpose(t, 0, atom_indices=[])) == str(golden["msg_empty_superpose"])
+    with pytest.raises(ValueError, match="valid positive indices"):
+        mdb.rmsd(t, t, 0, atom_indices=[-1, 2])
+    with pytest.raises(ValueError, match="ref_atom_indices must be valid"):
+        mdb.rmsd(t, t, 0, atom_indices=[1, 2], ref_atom_indices=[1, 99])
+
+
+def test_readonly_buffer_raises_before_any_work():
+    ro = np.zeros((3, 4, 3), np.float32); ro.setflags(write=False)
+
+    class Duck:
+        xyz = ro
+        _rmsd_traces = None
+    with pytest.raises(ValueError, match="buffer source array is read-only"):
+        mdb.rmsd(Duck(), Duck(), 0)
+    with pytest.raises(ValueError, match="read-only"):
+        mdb._center_inplace_atom_major(ro)
+
+
+def test_float_indices_warn_and_truncate():
+    t = _t()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with pytest.raises(ValueError):  # [0.5, 10.2] -> [0, 10]: 10 is out of range, after the cast warning
+            mdb.rmsd(t, t, 0, atom_indices=[0.5, 10.2])
+    assert any(issubclass(x.category, mdb.TypeCastPerformanceWarning) for x in w)
+
+
+def test_trajectory_container_semantics():
+    x = np.arange(2 * 3 * 3, dtype=np.float64).reshape(2, 3, 3)
+    t = mdb.Trajectory(x)
+    assert t.xyz.dtype == np.float32 and t.xyz.flags.c_contiguous and t.n_frames == 2 and t.n_atoms == 3
+    t._rmsd_traces = np.array([1.0, 2.0], np.float32)
+    t.xyz = x + 1
+    assert t._rmsd_traces is None  # the setter resets the cache (trajectory.py:1029)
+    one = mdb.Trajectory(np.zeros((4, 3)))
+    assert one.xyz.shape == (1, 4, 3)  # add_newaxis_on_deficient_ndim
+    with pytest.raises(ValueError):
+        mdb.Trajectory(np.zeros((2, 3, 4)))
+    t._rmsd_traces = np.array([5.0, 6.0], np.float32)
+    s = t[1]
+    assert s.n_frames == 1 and s._rmsd_traces.tolist() == [6.0]  # traces follow the slice (upstream bug fixed)
+    s.xyz[0, 0, 0] = 99
+    assert t.xyz[1, 0, 0] != 99  # slices copy
+
+
+def test_legacy_entry_validation():
+    a = np.zeros((2, 5, 3), np.float32); b = np.zeros((3, 6, 3), np.float32); g = np.zeros(3, np.float32)
+    with pytest.raises(ValueError, match="same number of atoms"):
+        mdb.getMultipleRMSDs_atom_major(a, b, g, g, 0)
+    with pytest.raises(ValueError, match="Cannot calculate RMSD of frame 2"):
+        mdb.getMultipleRMSDs_atom_major(a, a, g, g, 2)
+    with pytest.raises(ValueError, match="same number of frames"):
+        mdb.superpose_atom_major(a, a, g, g, np.zeros((3, 5, 3), np.float32), 0)
+    with pytest.raises(ValueError, match="4\\*n"):
+        mdb.getMultipleAlignDisplaceRMSDs_atom_major(a, a, g, g, a, a, 5, 5, 0)
+
+
+def test_shard_bounds_cover_exactly_once():
+    for n in (0, 1, 7, 100, 1_000_003):
+        for w in (1, 2, 3, 8):
+            b = D.all_shard_bounds(n, w)
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(y - x for x, y in b) - min(y - x for x, y in b) <= 1
+
+
+def test_h5min_reads_reference_fixture(ala2):
+    path = "/root/reference/examples/ala2.h5"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout absent on this box")
+    from mdtraj_b200 import h5min
+    xyz = h5min.load_coordinates(path)
+    assert xyz.shape == (100, 22, 3) and np.array_equal(xyz, ala2)
+    assert h5min.H5Min(path).keys() == ["coordinates", "time", "topology"]
