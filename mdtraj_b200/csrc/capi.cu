@@ -102,6 +102,13 @@ void configure_tma(OvmParams& p)
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+// development overrides of the frame-resident kernel geometry
+void apply_fused_env(FusedParams& p, int op)
+{
+    const int g = env_int("B200RMSD_FUSED_GROUPS", 0), n = env_int("B200RMSD_FUSED_NBUF", 0);
+    if (g > 0 || n > 0) fused_override(p, op, g, n);
+}
+
 }  // namespace
 
 extern "C" {
@@ -146,6 +153,19 @@ int b200rmsd_center_trace_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t
                                      "frame_stride %% 4 == 0, >= 3*n_pad)");
     int sm = 0;
     if (int rc = current_sm_count(&sm)) return rc;
+    FusedParams fp{};
+    fp.xyz = xyz;
+    fp.n_frames = n_frames;
+    fp.frame_stride = frame_stride;
+    fp.n_atoms = n_atoms;
+    fp.n_pad = (n_atoms + 3) / 4 * 4;
+    fp.n_sel = n_atoms;
+    fp.traces = traces;
+    if (!env_int("B200RMSD_NO_FUSED", 0) && fused_config(fp, OP_CENTER)) {
+        apply_fused_env(fp, OP_CENTER);
+        CU(launch_frame_resident(fp, OP_CENTER, sm, (cudaStream_t)stream));
+        return 0;
+    }
     CU(launch_center_trace(xyz, n_frames, n_atoms, frame_stride, traces, sm, (cudaStream_t)stream));
     return 0;
 }
@@ -240,6 +260,29 @@ int b200rmsd_superpose_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t fr
     // rmsd output is mandatory for the kernel; park it at the head of the centroid block's tail if not wanted
     float* rms = out_rmsd;
     if (!rms) return fail(B200RMSD_EINVAL, "superpose: out_rmsd must not be NULL in the device API");
+    {
+        // single-pass path: frames resident in shared memory between the rotation solve and the transform
+        int sm1 = 0;
+        if (int rc1 = current_sm_count(&sm1)) return rc1;
+        FusedParams fp{};
+        fp.xyz = xyz;
+        fp.n_frames = n_frames;
+        fp.frame_stride = frame_stride;
+        fp.n_atoms = n_atoms;
+        fp.n_pad = (n_atoms + 3) / 4 * 4;
+        fp.idx = idx;
+        fp.n_sel = idx ? n_sel : n_atoms;
+        fp.ref = ref;
+        fp.ref_stats = (const RefStats*)ref_stats;
+        fp.out_rmsd = out_rmsd;
+        fp.out_rot = out_rot;
+        fp.degenerate = n_degenerate;
+        if (!env_int("B200RMSD_NO_FUSED", 0) && aligned16(ref) && fused_config(fp, OP_SUPERPOSE)) {
+            apply_fused_env(fp, OP_SUPERPOSE);
+            CU(launch_frame_resident(fp, OP_SUPERPOSE, sm1, (cudaStream_t)stream));
+            return 0;
+        }
+    }
     int rc = b200rmsd_rmsd_dev(xyz, n_frames, n_atoms, frame_stride, idx, n_sel, ref, ref_stats, nullptr, 0u, rms, rot,
                                cen, n_degenerate, partial ? base : nullptr, partial, stream);
     if (rc) return rc;

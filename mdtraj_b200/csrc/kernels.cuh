@@ -51,6 +51,29 @@ struct ApplyParams {
     const RefStats* ref_stats;  // mean[] added after rotation
 };
 
+// frame-resident read-modify-write kernels (frame_resident.cu)
+enum { OP_SUPERPOSE = 0, OP_CENTER = 1 };
+struct FusedParams {
+    float* xyz;             // in/out, frames contiguous: frame_stride == 3*n_pad
+    int64_t n_frames;
+    int64_t frame_stride;
+    int n_atoms;
+    int n_pad;
+    const int* idx;         // align selection (OP_SUPERPOSE) or nullptr
+    int n_sel;              // == n_atoms when idx == nullptr
+    const float* ref;       // centred packed reference selection
+    const RefStats* ref_stats;
+    float* out_rmsd;        // may be nullptr
+    float* out_rot;         // may be nullptr
+    float* traces;          // OP_CENTER output, may be nullptr
+    unsigned int* degenerate;
+    int batch;              // G: frame groups computing concurrently (power of two <= 16)
+    int nbuf;               // whole-frame shared-memory buffers in the ring (>= G + 1)
+};
+bool fused_config(FusedParams& p, int op);
+bool fused_override(FusedParams& p, int op, int G, int nbuf);
+cudaError_t launch_frame_resident(const FusedParams& p, int op, int sm_count, cudaStream_t st);
+
 cudaError_t launch_ovm_tma(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st);
 cudaError_t launch_ovm_gather(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st);
 cudaError_t launch_prepare_ref(const float* frame, const int* idx, int n_sel, int do_center, float given_trace,

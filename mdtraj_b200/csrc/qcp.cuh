@@ -7,9 +7,9 @@
 //     cancellation in float32 (:275); here everything after the streamed float32
 //     partial sums is double, so the result sits closer to the float64 truth than
 //     the reference does;
-//   * the root comes from Newton-Raphson on the quartic from lambda0 = (G_a+G_b)/2
-//     (monotone from above, the largest root), not from the closed-form Ferrari
-//     route -- no acos/cos/pow on the device.
+//   * the root comes from Newton-Raphson on the quartic from an upper bound of the
+//     largest root (monotone from above), not from the closed-form Ferrari route --
+//     no acos/cos/pow on the device.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -21,22 +21,54 @@ struct QcpInput {
     int n_atoms;
 };
 
-// largest root of  t^4 + C2 t^2 + C1 t + C0
-__device__ __forceinline__ double qcp_newton(double C2, double C1, double C0, double lam0)
+// Largest root of  t^4 + C2 t^2 + C1 t + C0  (all four roots are real: K is symmetric).
+//
+// Start: lam0 = min((G_a+G_b)/2, sqrt(3)*||M||_F).  Both are upper bounds of lambda_max (the first is the
+// reference's own starting value, theobald_rmsd.cpp:245; the second follows from sum(lambda_i) = 0 and
+// lambda_max = s1 + s2 +- s3 <= sqrt(3)*||M||_F for the singular values s of M), and lambda_max >= s1 >=
+// ||M||_F/sqrt(3), so the start is never more than 3x above the root -- for dissimilar (e.g. iid random)
+// frames (G_a+G_b)/2 alone can be 10-30x above it and Newton would crawl down by 3/4 per step.  Newton from the right of the largest root of a real-rooted
+// polynomial is monotone, so the iteration cannot leave the basin.
+// The polynomial is normalised by lam0 (t = lambda/lam0 in (0,1]); the first iterations run in float32
+// (4-cycle FMA + MUFU reciprocal) and the last ones in float64 to full precision.
+__device__ __forceinline__ double qcp_newton(double C2, double C1, double C0, double lam_upper, double frob2)
 {
-    double lam = lam0;
+    double lam0 = sqrt(3.0 * frob2);
+    if (!(lam0 < lam_upper)) lam0 = lam_upper;
+    if (!(lam0 > 0.0)) return 0.0;
+    const double inv = 1.0 / lam0, inv2 = inv * inv;
+    const double c2 = C2 * inv2, c1 = C1 * inv2 * inv, c0 = C0 * inv2 * inv2;
+    // float32 phase
+    float t = 1.0f;
+    {
+        const float f2 = (float)c2, f1 = (float)c1, f0 = (float)c0;
 #pragma unroll 1
-    for (int it = 0; it < 64; ++it) {
-        const double l2 = lam * lam;
-        const double b = (l2 + C2) * lam;
-        const double a = b + C1;
-        const double den = 2.0 * l2 * lam + b + a;
-        if (den == 0.0) break;
-        const double delta = (a * lam + C0) / den;
-        lam -= delta;
-        if (fabs(delta) <= 1e-15 * fabs(lam)) break;
+        for (int it = 0; it < 24; ++it) {
+            const float t2 = t * t;
+            const float b = (t2 + f2) * t;
+            const float a = b + f1;
+            const float den = fmaf(2.0f * t2, t, b + a);
+            if (!(fabsf(den) > 1e-30f)) break;
+            const float delta = __fdividef(fmaf(a, t, f0), den);
+            t -= delta;
+            if (!(fabsf(delta) > 2e-6f * fabsf(t))) break;
+        }
+        if (!(t > 0.0f) || !(t <= 1.0f)) t = 1.0f;  // numerical accident: restart the float64 phase from the bound
     }
-    return lam;
+    // float64 polish (quadratic convergence from ~1e-6)
+    double x = (double)t;
+#pragma unroll 1
+    for (int it = 0; it < 48; ++it) {
+        const double x2 = x * x;
+        const double b = (x2 + c2) * x;
+        const double a = b + c1;
+        const double den = 2.0 * x2 * x + b + a;
+        if (den == 0.0) break;
+        const double delta = (a * x + c0) / den;
+        x -= delta;
+        if (fabs(delta) <= 1e-15 * fabs(x)) break;
+    }
+    return x * lam0;
 }
 
 // Returns the clamped msd.  If rot != nullptr also writes the row-major rotation
@@ -70,7 +102,7 @@ __device__ __forceinline__ double qcp_solve(const QcpInput& in, float* rot, bool
     const double b12 = k12 * k23 - k22 * k13, b13 = k12 * k33 - k23 * k13, b23 = k22 * k33 - k23 * k23;
     const double C0 = a01 * b23 - a02 * b13 + a03 * b12 + a12 * b03 - a13 * b02 + a23 * b01;
 
-    const double lam = qcp_newton(C2, C1, C0, 0.5 * (in.Ga + in.Gb));
+    const double lam = qcp_newton(C2, C1, C0, 0.5 * (in.Ga + in.Gb), ss);
     double msd = (in.Ga + in.Gb - 2.0 * lam) / in.n_atoms;
     if (!(msd > 0.0)) msd = 0.0;
 

@@ -63,6 +63,16 @@ def main():
     res["pre_ms"] = med; res["pre_GBs"] = res["bytes"] / med / 1e6
 
     rot = torch.empty((F, 9), dtype=torch.float32, device=dev)
+    stride5 = torch.arange(0, N, 5, dtype=torch.int32, device=dev)
+    prep5 = prepare_reference(dt.xyz_dev[0].clone(), stride5, int(stride5.numel()), True)
+
+    def sup5():
+        _capi.check(L.b200rmsd_superpose_dev(dt.xyz_dev.data_ptr(), F, N, dt.frame_stride, stride5.data_ptr(),
+                                             int(stride5.numel()), prep5.ref.data_ptr(), prep5.stats.data_ptr(),
+                                             out.data_ptr(), rot.data_ptr(), None, scratch.data_ptr(), scratch.numel(),
+                                             stream), "superpose idx")
+    med, best = time_fn(sup5, reps)
+    res["superpose_idx5_ms"] = med; res["superpose_idx5_GBs_24N"] = 2 * res["bytes"] / med / 1e6
 
     def sup():
         _capi.check(L.b200rmsd_superpose_dev(dt.xyz_dev.data_ptr(), F, N, dt.frame_stride, None, N, prep.ref.data_ptr(),
