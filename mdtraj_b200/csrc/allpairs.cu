@@ -16,26 +16,12 @@
 //                            for small problems and as the on-device accuracy check of the
 //                            tensor-core path (allpairs_tc.cu).
 #include "../../include/b200rmsd.h"
+#include "allpairs_layout.cuh"
 #include "common.cuh"
 #include "kernels.cuh"
 #include "qcp.cuh"
 
 namespace b200 {
-
-struct ApHeader {        // first 256 bytes of the workspace
-    uint64_t magic;
-    int64_t n_frames;
-    int32_t n_sel;
-    int32_t k_pad;       // atoms padded to a multiple of 32
-    int64_t traces_off;  // byte offsets from the workspace base
-    int64_t x_off;       // axis-major fp32 operand (F,3,k_pad)
-    int64_t hi_off;      // tf32 split operands for the tensor path (0 if absent)
-    int64_t lo_off;
-    int64_t rows_pad;    // rows of the split operands
-};
-constexpr uint64_t kApMagic = 0x42323030524d5344ull;  // "B200RMSD"
-
-__host__ __device__ inline int ap_kpad(int n_sel) { return (n_sel + 31) / 32 * 32; }
 
 // one warp per frame
 __global__ void __launch_bounds__(256) allpairs_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames,
@@ -169,15 +155,20 @@ using namespace b200;
 
 #define fail b200::set_error
 
+static int ap_sm_count()
+{
+    int dev = 0, sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    return sm;
+}
+
 extern "C" {
 
 size_t b200rmsd_allpairs_workspace_bytes(int64_t n_frames, int n_sel)
 {
     if (n_frames <= 0 || n_sel <= 0) return 256;
-    const size_t kp = (size_t)ap_kpad(n_sel);
-    const size_t tr = ((size_t)n_frames * 4 + 255) / 256 * 256;
-    const size_t x = ((size_t)n_frames * 3 * kp * 4 + 255) / 256 * 256;
-    return 256 + tr + x;
+    return ap_geometry(n_frames, n_sel).total;
 }
 
 int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride,
@@ -186,29 +177,24 @@ int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atom
     if (!xyz || !workspace || n_frames <= 0 || n_atoms <= 0) return fail(B200RMSD_EINVAL, "allpairs_prepare: bad arguments");
     const int ns = idx ? n_sel : n_atoms;
     if (ns <= 0) return fail(B200RMSD_EINVAL, "allpairs_prepare: empty selection");
-    if (workspace_bytes < b200rmsd_allpairs_workspace_bytes(n_frames, ns))
-        return fail(B200RMSD_EINVAL, "allpairs_prepare: workspace too small (need %zu bytes)", b200rmsd_allpairs_workspace_bytes(n_frames, ns));
+    const ApGeometry g = ap_geometry(n_frames, ns);
+    if (workspace_bytes < g.total) return fail(B200RMSD_EINVAL, "allpairs_prepare: workspace too small (need %zu bytes)", g.total);
     if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return fail(B200RMSD_EINVAL, "allpairs_prepare: workspace must be 256-byte aligned");
-    ApHeader h{};
-    h.magic = kApMagic;
-    h.n_frames = n_frames;
-    h.n_sel = ns;
-    h.k_pad = ap_kpad(ns);
-    h.traces_off = 256;
-    h.x_off = 256 + (int64_t)(((size_t)n_frames * 4 + 255) / 256 * 256);
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemcpyAsync(workspace, &h, sizeof(h), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return fail(B200RMSD_ECUDA, "allpairs_prepare: %s", cudaGetErrorString(e));
-    int dev = 0, sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
-    int64_t ctas = (int64_t)sm * 8;
-    const int64_t need = (n_frames + 7) / 8;
-    if (ctas > need) ctas = need;
     char* base = (char*)workspace;
-    allpairs_prepare_kernel<<<(unsigned)ctas, 256, 0, st>>>(xyz, n_frames, frame_stride, idx, ns, h.k_pad,
-                                                            (float*)(base + h.x_off), (float*)(base + h.traces_off));
-    e = cudaGetLastError();
+    const int sm = ap_sm_count();
+    cudaError_t e;
+    if (g.tc) {
+        e = launch_allpairs_tc_prepare(xyz, n_frames, frame_stride, idx, ns, g.k_pad, (float*)(base + g.hi_off),
+                                       (float*)(base + g.lo_off), (float*)(base + g.traces_off), g.rows_pad, sm, st);
+    } else {
+        int64_t ctas = (int64_t)sm * 8;
+        const int64_t need = (n_frames + 7) / 8;
+        if (ctas > need) ctas = need;
+        allpairs_prepare_kernel<<<(unsigned)ctas, 256, 0, st>>>(xyz, n_frames, frame_stride, idx, ns, g.k_pad,
+                                                                (float*)(base + g.x_off), (float*)(base + g.traces_off));
+        e = cudaGetLastError();
+    }
     return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "allpairs_prepare: %s", cudaGetErrorString(e));
 }
 
@@ -217,17 +203,19 @@ int b200rmsd_allpairs_rows_dev(const void* workspace, size_t workspace_bytes, in
 {
     if (!workspace || !out || n_frames <= 0 || n_sel <= 0 || row0 < 0 || row1 > n_frames || row0 > row1 || ld < n_frames)
         return fail(B200RMSD_EINVAL, "allpairs_rows: bad arguments");
-    if (workspace_bytes < b200rmsd_allpairs_workspace_bytes(n_frames, n_sel)) return fail(B200RMSD_EINVAL, "allpairs_rows: workspace too small");
+    const ApGeometry g = ap_geometry(n_frames, n_sel);
+    if (workspace_bytes < g.total) return fail(B200RMSD_EINVAL, "allpairs_rows: workspace too small");
     if (row0 == row1) return 0;
-    const int kp = ap_kpad(n_sel);
     const char* base = (const char*)workspace;
-    const int64_t traces_off = 256;
-    const int64_t x_off = 256 + (int64_t)(((size_t)n_frames * 4 + 255) / 256 * 256);
+    if (g.tc)
+        return launch_allpairs_tc_rows((const float*)(base + g.hi_off), (const float*)(base + g.lo_off),
+                                       (const float*)(base + g.traces_off), n_frames, n_sel, g.k_pad, g.rows_pad, row0,
+                                       row1, out, ld, flags, ap_sm_count(), (cudaStream_t)stream);
     dim3 grid((unsigned)((n_frames + kTile - 1) / kTile), (unsigned)((row1 - row0 + kTile - 1) / kTile));
     if (grid.y > 65535) return fail(B200RMSD_EINVAL, "allpairs_rows: at most 65535*32 rows per call");
-    allpairs_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)(base + x_off),
-                                                                 (const float*)(base + traces_off), n_frames, n_sel, kp,
-                                                                 row0, row1, out, ld, flags);
+    allpairs_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)(base + g.x_off),
+                                                                 (const float*)(base + g.traces_off), n_frames, n_sel,
+                                                                 g.k_pad, row0, row1, out, ld, flags);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "allpairs_rows: %s", cudaGetErrorString(e));
 }

@@ -1,0 +1,396 @@
+// allpairs_tc.cu -- all-pairs RMSD matrix on the 5th-generation tensor cores.
+//
+// D[i][j] = rmsd(frame j onto frame i) needs the 3x3 inner products M_ij = X_i X_j^T of the centred
+// frames: one dense contraction (3F x A).(A x 3F).  This kernel computes it as a tcgen05 GEMM:
+//
+//   operands   K-major fp32 rows (one row per frame component, K = atoms padded to 32), pre-split into
+//              tf32 "hi" and "lo" parts by allpairs_tc_prepare_kernel (hi = rna_tf32(x), lo = rna_tf32(x-hi));
+//              rows are grouped 10 frames (30 rows) + 2 zero rows per 32, so that the three rows of a frame
+//              always sit in one warp's TMEM lane quarter;
+//   loads      TMA tiled copies (cp.async.bulk.tensor.2d, SWIZZLE_128B, 128 rows x 32 floats per box) into a
+//              3-stage shared-memory ring, mbarrier full/empty pipeline;
+//   MMA        one elected thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8, three per
+//              K-step (lo.hi, hi.lo, hi.hi: "3xTF32", the dropped lo.lo term is ~2^-22 relative) accumulating
+//              fp32 in TMEM; tcgen05.commit releases smem stages and publishes finished accumulators;
+//   epilogue   4 warps read the accumulator with tcgen05.ld.32x32b (one TMEM lane = one row per thread),
+//              regroup 3x3 blocks with warp shuffles, run the QCP solve and write only the RMSD (4 bytes per
+//              pair); TMEM is double buffered so the epilogue of tile t overlaps the MMAs of tile t+1.
+//
+// The inner products never touch HBM.  Replaces the Python loop of F md.rmsd calls
+// (examples/clustering.ipynb:78-81); arithmetic of each pair == msdFromMandG (theobald_rmsd.cpp:217-334).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/b200rmsd.h"
+#include "allpairs_layout.cuh"
+#include "common.cuh"
+#include "kernels.cuh"
+#include "qcp.cuh"
+
+namespace b200 {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32, kStages = 3;
+constexpr int kFramesPerTile = 40;               // 4 warps x 10 frames
+constexpr int kOperandBytes = kBM * kBK * 4;     // 16 KB: one 128 x 32 fp32 box
+constexpr int kStageBytes = 4 * kOperandBytes;   // A_hi, A_lo, B_hi, B_lo
+constexpr int kTcThreads = 256;
+constexpr int kAccCols = kBN;                    // fp32 accumulator columns per stage
+constexpr uint32_t kTmemCols = 256;              // 2 accumulator stages
+
+// ---- tcgen05 / TMA PTX wrappers -------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64)
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(const void* smem_tile)
+{
+    const uint64_t addr = (smem_u32(smem_tile) >> 4) & 0x3FFFu;
+    return addr | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format=F32 [4,6) a/b_format=TF32 [7,10),[10,13)
+// a/b K-major [15],[16] = 0, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_tf32_idesc(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// prepare: centre every frame (center_generic.h:3-44 semantics), write tf32 hi/lo rows + traces.
+// one warp per frame.  Row of (frame f, component c) = 32*(f/10) + 3*(f%10) + c.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rna_tf32(float x)
+{
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256) allpairs_tc_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames,
+                                                                  int64_t frame_stride, const int* __restrict__ idx,
+                                                                  int n_sel, int k_pad, float* __restrict__ hi,
+                                                                  float* __restrict__ lo, float* __restrict__ traces)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    for (int64_t f = (int64_t)blockIdx.x * 8 + warp; f < n_frames; f += n_warps) {
+        const float* fr = xyz + f * frame_stride;
+        double sx = 0, sy = 0, sz = 0;
+        for (int k = lane; k < n_sel; k += 32) {
+            const int a = idx ? __ldg(idx + k) : k;
+            sx += (double)__ldg(fr + 3 * a); sy += (double)__ldg(fr + 3 * a + 1); sz += (double)__ldg(fr + 3 * a + 2);
+        }
+        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+        const float mx = (float)(sx / n_sel), my = (float)(sy / n_sel), mz = (float)(sz / n_sel);
+        const int64_t row = ap_tc_row(f, 0);
+        double tr = 0;
+        for (int k = lane; k < k_pad; k += 32) {
+            float v[3] = {0.f, 0.f, 0.f};
+            if (k < n_sel) {
+                const int a = idx ? __ldg(idx + k) : k;
+                v[0] = __ldg(fr + 3 * a) - mx; v[1] = __ldg(fr + 3 * a + 1) - my; v[2] = __ldg(fr + 3 * a + 2) - mz;
+                tr += (double)(v[0] * v[0]); tr += (double)(v[1] * v[1]); tr += (double)(v[2] * v[2]);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float h = rna_tf32(v[c]);
+                hi[(row + c) * k_pad + k] = h;
+                lo[(row + c) * k_pad + k] = rna_tf32(v[c] - h);
+            }
+        }
+        tr = warp_sum(tr);
+        if (lane == 0) traces[f] = (float)tr;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct TcParams {
+    const float* traces;
+    float* out;
+    int64_t ld;
+    int64_t n_frames;
+    int64_t row0, row1;      // output rows [row0, row1)
+    int n_sel;
+    int nk;                  // K blocks of 32
+    int tiles_i0;            // first i-tile (= row0 / 40)
+    int tiles_i, tiles_j;    // tile grid
+    unsigned flags;
+};
+
+__device__ __forceinline__ float sel3(int c, float a0, float a1, float a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TcParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is not guaranteed to have it
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* empty = full + kStages;
+    uint64_t* tfull = empty + kStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = (int64_t)p.tiles_i * p.tiles_j;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int ti = p.tiles_i0 + (int)(t / p.tiles_j), tj = (int)(t % p.tiles_j);
+                for (int kb = 0; kb < p.nk; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    unsigned char* st = smem + stage * kStageBytes;
+                    mbar_arrive_expect_tx(&full[stage], kStageBytes);
+                    tma_load_2d(st, &map_hi, &full[stage], kb * kBK, ti * kBM);
+                    tma_load_2d(st + kOperandBytes, &map_lo, &full[stage], kb * kBK, ti * kBM);
+                    tma_load_2d(st + 2 * kOperandBytes, &map_hi, &full[stage], kb * kBK, tj * kBN);
+                    tma_load_2d(st + 3 * kOperandBytes, &map_lo, &full[stage], kb * kBK, tj * kBN);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_tf32_idesc(kBM, kBN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+                for (int kb = 0; kb < p.nk; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    unsigned char* st = smem + stage * kStageBytes;
+                    const uint64_t a_hi = make_sw128_kmajor_desc(st), a_lo = make_sw128_kmajor_desc(st + kOperandBytes);
+                    const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * kOperandBytes),
+                                   b_lo = make_sw128_kmajor_desc(st + 3 * kOperandBytes);
+#pragma unroll
+                    for (int ks = 0; ks < kBK / 8; ++ks) {
+                        const uint64_t off = (uint64_t)(ks * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
+                        umma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, (kb | ks) != 0 ? 1u : 0u);
+                        umma_tf32(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
+                        umma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
+                    }
+                    umma_commit(&empty[stage]);  // frees this smem stage when the MMAs above have read it
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull[acc]);        // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue (TMEM -> QCP -> HBM)
+        const int ew = warp - 4;                 // TMEM lane quarter
+        const int c = lane % 3, tq = lane / 3;   // component row and frame slot of this lane
+        const bool row_valid = lane < 30;
+        const int src1 = lane - c + (c + 1) % 3, src2 = lane - c + (c + 2) % 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int ti = p.tiles_i0 + (int)(t / p.tiles_j), tj = (int)(t % p.tiles_j);
+            const int64_t fi = (int64_t)ti * kFramesPerTile + ew * 10 + tq;  // row frame of this lane
+            const bool i_ok = row_valid && fi >= p.row0 && fi < p.row1;
+            const double Gi = i_ok ? (double)__ldg(p.traces + fi) : 0.0;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int chunk = 0; chunk < 4; ++chunk) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kAccCols + chunk * 32), r);
+#pragma unroll
+                for (int jg = 0; jg < 4; ++jg) {
+                    // columns of the three j-frames of this group (the last group holds one frame only)
+                    float own[3], r1[3], r2[3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const float m0 = __uint_as_float(r[(jg < 3 ? 9 * jg : 27) + q]);
+                        const float m1 = __uint_as_float(r[(jg < 3 ? 9 * jg + 3 : 27) + q]);
+                        const float m2 = __uint_as_float(r[(jg < 3 ? 9 * jg + 6 : 27) + q]);
+                        own[q] = sel3(c, m0, m1, m2);
+                        // what the reader one row below / two rows below needs from this lane
+                        const float send1 = sel3(c, m2, m0, m1);  // reader has comp (c+2)%3
+                        const float send2 = sel3(c, m1, m2, m0);  // reader has comp (c+1)%3
+                        r1[q] = __shfl_sync(0xffffffffu, send1, src1);
+                        r2[q] = __shfl_sync(0xffffffffu, send2, src2);
+                    }
+                    const int jl = 3 * jg + c;  // j-frame slot inside the chunk
+                    const int64_t fj = (int64_t)tj * kFramesPerTile + chunk * 10 + jl;
+                    if (i_ok && jl < 10 && fj < p.n_frames) {
+                        float res;
+                        if (fi == fj && (p.flags & B200RMSD_DIAG_ZERO)) {
+                            res = 0.f;
+                        } else {
+                            QcpInput q;
+                            q.n_atoms = p.n_sel;
+                            q.Ga = (double)__ldg(p.traces + fj);
+                            q.Gb = Gi;
+                            // rows (c, c+1, c+2) mod 3: a cyclic permutation of x,y,z = a proper rotation of frame i,
+                            // which leaves the RMSD unchanged
+                            q.M[0] = own[0]; q.M[1] = own[1]; q.M[2] = own[2];
+                            q.M[3] = r1[0];  q.M[4] = r1[1];  q.M[5] = r1[2];
+                            q.M[6] = r2[0];  q.M[7] = r2[1];  q.M[8] = r2[2];
+                            res = (float)sqrt(qcp_solve(q, nullptr, nullptr));
+                        }
+                        p.out[(size_t)(fi - p.row0) * p.ld + fj] = res;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static bool make_operand_map(CUtensorMap* map, const float* base, int64_t rows, int k_pad)
+{
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)k_pad * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t launch_allpairs_tc_prepare(const float* xyz, int64_t n_frames, int64_t frame_stride, const int* idx, int n_sel,
+                                       int k_pad, float* hi, float* lo, float* traces, int64_t rows_pad, int sm_count,
+                                       cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(hi, 0, (size_t)rows_pad * k_pad * 4, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(lo, 0, (size_t)rows_pad * k_pad * 4, st);
+    if (e != cudaSuccess) return e;
+    int64_t ctas = (int64_t)sm_count * 8;
+    const int64_t need = (n_frames + 7) / 8;
+    if (ctas > need) ctas = need;
+    allpairs_tc_prepare_kernel<<<(unsigned)ctas, 256, 0, st>>>(xyz, n_frames, frame_stride, idx, n_sel, k_pad, hi, lo, traces);
+    return cudaGetLastError();
+}
+
+int launch_allpairs_tc_rows(const float* hi, const float* lo, const float* traces, int64_t n_frames, int n_sel, int k_pad,
+                            int64_t rows_pad, int64_t row0, int64_t row1, float* out, int64_t ld, unsigned flags,
+                            int sm_count, cudaStream_t st)
+{
+    CUtensorMap map_hi, map_lo;
+    if (!make_operand_map(&map_hi, hi, rows_pad, k_pad) || !make_operand_map(&map_lo, lo, rows_pad, k_pad))
+        return set_error(B200RMSD_ECUDA, "allpairs: cuTensorMapEncodeTiled failed");
+    TcParams p{};
+    p.traces = traces;
+    p.out = out;
+    p.ld = ld;
+    p.n_frames = n_frames;
+    p.row0 = row0;
+    p.row1 = row1;
+    p.n_sel = n_sel;
+    p.nk = k_pad / kBK;
+    p.tiles_i0 = (int)(row0 / kFramesPerTile);
+    p.tiles_i = (int)((row1 + kFramesPerTile - 1) / kFramesPerTile) - p.tiles_i0;
+    p.tiles_j = (int)((n_frames + kFramesPerTile - 1) / kFramesPerTile);
+    p.flags = flags;
+    const size_t smem = (size_t)kStages * kStageBytes + 1024 + 256;
+    cudaError_t e = cudaFuncSetAttribute(allpairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(B200RMSD_ECUDA, "allpairs: %s", cudaGetErrorString(e));
+    int64_t ctas = sm_count;
+    const int64_t n_tiles = (int64_t)p.tiles_i * p.tiles_j;
+    if (ctas > n_tiles) ctas = n_tiles;
+    allpairs_tc_kernel<<<(unsigned)ctas, kTcThreads, smem, st>>>(map_hi, map_lo, p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error(B200RMSD_ECUDA, "allpairs: %s", cudaGetErrorString(e));
+}
+
+}  // namespace b200

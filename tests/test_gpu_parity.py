@@ -332,3 +332,31 @@ def test_allpairs_vs_truth_random(mdb, oracle_mod):
         m = np.arange(70) != i
         assert_close(D[i][m], truth[m], what=f"all-pairs row {i} vs truth")
     assert np.abs(D - D.T).max() < 1e-6
+
+
+# ------------------------------------------------------------------ tensor-core all-pairs path
+@pytest.mark.parametrize("F,N", [(600, 300), (1001, 97), (520, 22)])
+def test_allpairs_tensor_core_vs_simt_and_truth(mdb, oracle_mod, monkeypatch, F, N):
+    """The tcgen05 3xTF32 kernel (F >= 512) against the exact-fp32 SIMT kernel and float64 truth."""
+    O = oracle_mod
+    X = O.synth_md(F, N, seed=21, rg=1.0, sigma=0.15)
+    dt = mdb.DeviceTrajectory.from_host(X)
+    monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
+    D_tc = mdb.rmsd_matrix(dt)
+    monkeypatch.setenv("B200RMSD_ALLPAIRS", "simt")
+    D_simt = mdb.rmsd_matrix(dt)
+    monkeypatch.delenv("B200RMSD_ALLPAIRS")
+    assert D_tc.shape == (F, F) and np.isfinite(D_tc).all()
+    assert np.all(np.diag(D_tc) == 0)
+    assert_close(D_tc, D_simt, atol=5e-6, what="tcgen05 vs SIMT all-pairs")
+    assert np.abs(D_tc - D_tc.T).max() < 2e-6
+    for i in (0, F // 2, F - 1):
+        truth = O.truth_rmsd(X, X, i)
+        m = np.arange(F) != i
+        assert_close(D_tc[i][m], truth[m], what=f"tcgen05 row {i} vs truth")
+    # a row block, as a rank of a sharded run computes it
+    from mdtraj_b200 import allpairs as AP
+    monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
+    prep = AP.prepare(dt)
+    blk = AP.rows(prep, 37, 123).cpu().numpy()
+    assert np.array_equal(blk, D_tc[37:123])
