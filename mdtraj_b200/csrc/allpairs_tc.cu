@@ -12,7 +12,7 @@
 //   MMA        one elected thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8, three per
 //              K-step (lo.hi, hi.lo, hi.hi: "3xTF32", the dropped lo.lo term is ~2^-22 relative) accumulating
 //              fp32 in TMEM; tcgen05.commit releases smem stages and publishes finished accumulators;
-//   epilogue   4 warps read the accumulator with tcgen05.ld.32x32b (one TMEM lane = one row per thread),
+//   epilogue   8 warps read the accumulator with tcgen05.ld.32x32b (one TMEM lane = one row per thread),
 //              regroup 3x3 blocks with warp shuffles, run the QCP solve and write only the RMSD (4 bytes per
 //              pair); TMEM is double buffered so the epilogue of tile t overlaps the MMAs of tile t+1.
 //
@@ -20,6 +20,9 @@
 // (examples/clustering.ipynb:78-81); arithmetic of each pair == msdFromMandG (theobald_rmsd.cpp:217-334).
 #include <cuda.h>
 #include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
 
 #include "../../include/b200rmsd.h"
 #include "allpairs_layout.cuh"
@@ -33,7 +36,6 @@ constexpr int kBM = 128, kBN = 128, kBK = 32, kStages = 3;
 constexpr int kFramesPerTile = 40;               // 4 warps x 10 frames
 constexpr int kOperandBytes = kBM * kBK * 4;     // 16 KB: one 128 x 32 fp32 box
 constexpr int kStageBytes = 4 * kOperandBytes;   // A_hi, A_lo, B_hi, B_lo
-constexpr int kTcThreads = 256;
 constexpr int kAccCols = kBN;                    // fp32 accumulator columns per stage
 constexpr uint32_t kTmemCols = 256;              // 2 accumulator stages
 
@@ -164,7 +166,10 @@ struct TcParams {
 
 __device__ __forceinline__ float sel3(int c, float a0, float a1, float a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+// EPI_WARPS in {4, 8, 16}: epilogue warps (each TMEM lane quarter is served by EPI_WARPS/4 warps that split the
+// four 32-column chunks of the accumulator); NP in {1, 2}: independent solves interleaved per lane.
+template <int EPI_WARPS, int NP>
+__global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TcParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -181,7 +186,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -229,7 +234,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                     const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * kOperandBytes),
                                    b_lo = make_sw128_kmajor_desc(st + 3 * kOperandBytes);
 #pragma unroll
-                    for (int ks = 0; ks < kBK / 8; ++ks) {
+                    for (int ks = 0; ks < ((p.flags & 0x200u) ? 0 : kBK / 8); ++ks) {  // 0x200: development, skip MMAs
                         const uint64_t off = (uint64_t)(ks * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
                         umma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, (kb | ks) != 0 ? 1u : 0u);
                         umma_tf32(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
@@ -243,60 +248,67 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        // ===================================================== epilogue (TMEM -> QCP -> HBM)
-        const int ew = warp - 4;                 // TMEM lane quarter
+        // ===================================================== epilogue (TMEM -> QCP -> HBM), 8 warps
+        const int ew = warp & 3;                 // TMEM lane quarter this warp may read (warp_id % 4)
+        constexpr int kChunksPerWarp = 16 / EPI_WARPS;  // 4, 2 or 1 of the four 32-column chunks
+        const int part = (warp - 4) >> 2;        // which share of the chunks
         const int c = lane % 3, tq = lane / 3;   // component row and frame slot of this lane
         const bool row_valid = lane < 30;
         const int src1 = lane - c + (c + 1) % 3, src2 = lane - c + (c + 2) % 3;
+        const float inv_n = 1.0f / (float)p.n_sel;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int ti = p.tiles_i0 + (int)(t / p.tiles_j), tj = (int)(t % p.tiles_j);
             const int64_t fi = (int64_t)ti * kFramesPerTile + ew * 10 + tq;  // row frame of this lane
             const bool i_ok = row_valid && fi >= p.row0 && fi < p.row1;
-            const double Gi = i_ok ? (double)__ldg(p.traces + fi) : 0.0;
+            const float Gi = i_ok ? __ldg(p.traces + fi) : 1.0f;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
-            for (int chunk = 0; chunk < 4; ++chunk) {
+            for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+                const int chunk = part * kChunksPerWarp + cc;
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kAccCols + chunk * 32), r);
 #pragma unroll
-                for (int jg = 0; jg < 4; ++jg) {
-                    // columns of the three j-frames of this group (the last group holds one frame only)
-                    float own[3], r1[3], r2[3];
+                for (int jp = 0; jp < 4 / NP; ++jp) {
+                    // NP j-frame groups per pass so that NP independent solves interleave
+                    float M[NP][9], Ga[NP], Gb[NP], res[NP];
+                    int64_t fj[NP];
+                    bool ok[NP];
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const float m0 = __uint_as_float(r[(jg < 3 ? 9 * jg : 27) + q]);
-                        const float m1 = __uint_as_float(r[(jg < 3 ? 9 * jg + 3 : 27) + q]);
-                        const float m2 = __uint_as_float(r[(jg < 3 ? 9 * jg + 6 : 27) + q]);
-                        own[q] = sel3(c, m0, m1, m2);
-                        // what the reader one row below / two rows below needs from this lane
-                        const float send1 = sel3(c, m2, m0, m1);  // reader has comp (c+2)%3
-                        const float send2 = sel3(c, m1, m2, m0);  // reader has comp (c+1)%3
-                        r1[q] = __shfl_sync(0xffffffffu, send1, src1);
-                        r2[q] = __shfl_sync(0xffffffffu, send2, src2);
-                    }
-                    const int jl = 3 * jg + c;  // j-frame slot inside the chunk
-                    const int64_t fj = (int64_t)tj * kFramesPerTile + chunk * 10 + jl;
-                    if (i_ok && jl < 10 && fj < p.n_frames) {
-                        float res;
-                        if (fi == fj && (p.flags & B200RMSD_DIAG_ZERO)) {
-                            res = 0.f;
-                        } else {
-                            QcpInput q;
-                            q.n_atoms = p.n_sel;
-                            q.Ga = (double)__ldg(p.traces + fj);
-                            q.Gb = Gi;
+                    for (int u = 0; u < NP; ++u) {
+                        const int jg = NP * jp + u;  // group of three j-frames (the last group holds one frame only)
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const float m0 = __uint_as_float(r[(jg < 3 ? 9 * jg : 27) + q]);
+                            const float m1 = __uint_as_float(r[(jg < 3 ? 9 * jg + 3 : 27) + q]);
+                            const float m2 = __uint_as_float(r[(jg < 3 ? 9 * jg + 6 : 27) + q]);
                             // rows (c, c+1, c+2) mod 3: a cyclic permutation of x,y,z = a proper rotation of frame i,
                             // which leaves the RMSD unchanged
-                            q.M[0] = own[0]; q.M[1] = own[1]; q.M[2] = own[2];
-                            q.M[3] = r1[0];  q.M[4] = r1[1];  q.M[5] = r1[2];
-                            q.M[6] = r2[0];  q.M[7] = r2[1];  q.M[8] = r2[2];
-                            res = (float)sqrt(qcp_solve(q, nullptr, nullptr));
+                            M[u][q] = sel3(c, m0, m1, m2);
+                            const float send1 = sel3(c, m2, m0, m1);  // for the reader whose component is (c+2)%3
+                            const float send2 = sel3(c, m1, m2, m0);  // for the reader whose component is (c+1)%3
+                            M[u][3 + q] = __shfl_sync(0xffffffffu, send1, src1);
+                            M[u][6 + q] = __shfl_sync(0xffffffffu, send2, src2);
                         }
-                        p.out[(size_t)(fi - p.row0) * p.ld + fj] = res;
+                        const int jl = 3 * jg + c;  // j-frame slot inside the chunk
+                        fj[u] = (int64_t)tj * kFramesPerTile + chunk * 10 + jl;
+                        ok[u] = i_ok && jl < 10 && fj[u] < p.n_frames;
+                        Ga[u] = ok[u] ? __ldg(p.traces + fj[u]) : 1.0f;
+                        Gb[u] = Gi;
                     }
+                    if (p.flags & 0x100u) {  // development: skip the solve to time the GEMM main loop alone
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) res[u] = M[u][0];
+                    } else {
+                        qcp_msd_fast<NP>(M, Ga, Gb, inv_n, res);
+                    }
+#pragma unroll
+                    for (int u = 0; u < NP; ++u)
+                        if (ok[u])
+                            p.out[(size_t)(fi - p.row0) * p.ld + fj[u]] =
+                                (fi == fj[u] && (p.flags & B200RMSD_DIAG_ZERO)) ? 0.f : res[u];
                 }
             }
             tc_fence_before();
@@ -382,13 +394,27 @@ int launch_allpairs_tc_rows(const float* hi, const float* lo, const float* trace
     p.tiles_i = (int)((row1 + kFramesPerTile - 1) / kFramesPerTile) - p.tiles_i0;
     p.tiles_j = (int)((n_frames + kFramesPerTile - 1) / kFramesPerTile);
     p.flags = flags;
+    if (const char* dbg = getenv("B200RMSD_TC_DEBUG")) p.flags |= (unsigned)strtoul(dbg, nullptr, 0) & 0xff00u;
     const size_t smem = (size_t)kStages * kStageBytes + 1024 + 256;
-    cudaError_t e = cudaFuncSetAttribute(allpairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(B200RMSD_ECUDA, "allpairs: %s", cudaGetErrorString(e));
     int64_t ctas = sm_count;
     const int64_t n_tiles = (int64_t)p.tiles_i * p.tiles_j;
     if (ctas > n_tiles) ctas = n_tiles;
-    allpairs_tc_kernel<<<(unsigned)ctas, kTcThreads, smem, st>>>(map_hi, map_lo, p);
+    const char* cfg = getenv("B200RMSD_TC_EPILOGUE");  // development: "<warps>x<np>", e.g. 16x1
+    int ew = 16, np = 2;  // measured best on B200 (16x2 > 16x1 > 8x2 > 8x1)
+    if (cfg) sscanf(cfg, "%dx%d", &ew, &np);
+    cudaError_t e = cudaSuccess;
+#define B200_LAUNCH_TC(EW, NP)                                                                                         \
+    do {                                                                                                               \
+        e = cudaFuncSetAttribute(allpairs_tc_kernel<EW, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) allpairs_tc_kernel<EW, NP><<<(unsigned)ctas, 128 + 32 * EW, smem, st>>>(map_hi, map_lo, p); \
+    } while (0)
+    if (ew == 4 && np == 2) B200_LAUNCH_TC(4, 2);
+    else if (ew == 8 && np == 1) B200_LAUNCH_TC(8, 1);
+    else if (ew == 8 && np == 2) B200_LAUNCH_TC(8, 2);
+    else if (ew == 16 && np == 1) B200_LAUNCH_TC(16, 1);
+    else B200_LAUNCH_TC(16, 2);
+#undef B200_LAUNCH_TC
+    if (e != cudaSuccess) return set_error(B200RMSD_ECUDA, "allpairs: %s", cudaGetErrorString(e));
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error(B200RMSD_ECUDA, "allpairs: %s", cudaGetErrorString(e));
 }

@@ -135,4 +135,88 @@ __device__ __forceinline__ double qcp_solve(const QcpInput& in, float* rot, bool
     return msd;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Throughput variant for the all-pairs epilogue (no rotation): branch-free so that two independent
+// solves interleave in one instruction stream.  Same polynomial and root as qcp_solve:
+//   * coefficients C2, C1, C0 in float64 (the Laplace minors have plenty of ILP);
+//   * scaling by an exact power of two instead of a division;
+//   * a fixed number of float32 Newton steps from the upper bound, then two float64 steps whose
+//     divisions are a float32 reciprocal refined by one Newton step (3 DFMA instead of a DDIV chain);
+//   * float32 square root of the float64 msd.
+// ---------------------------------------------------------------------------------------------
+template <int NP>
+__device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const float (&Ga)[NP], const float (&Gb)[NP],
+                                             float inv_n, float (&rmsd)[NP])
+{
+    double c2[NP], c1[NP], c0[NP], e0[NP], scale_back[NP];
+    float t[NP], f2[NP], f1[NP], f0[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const double Sxx = M[p][0], Sxy = M[p][1], Sxz = M[p][2];
+        const double Syx = M[p][3], Syy = M[p][4], Syz = M[p][5];
+        const double Szx = M[p][6], Szy = M[p][7], Szz = M[p][8];
+        const double k00 = Sxx + Syy + Szz, k11 = Sxx - Syy - Szz, k22 = -Sxx + Syy - Szz, k33 = -Sxx - Syy + Szz;
+        const double k01 = Szy - Syz, k02 = Sxz - Szx, k03 = Syx - Sxy;
+        const double k12 = Syx + Sxy, k13 = Sxz + Szx, k23 = Szy + Syz;
+        const double ss = Sxx * Sxx + Sxy * Sxy + Sxz * Sxz + Syx * Syx + Syy * Syy + Syz * Syz + Szx * Szx + Szy * Szy +
+                          Szz * Szz;
+        const double detM = Sxx * (Syy * Szz - Syz * Szy) + Syx * (Szy * Sxz - Szz * Sxy) + Szx * (Sxy * Syz - Sxz * Syy);
+        const double a01 = k00 * k11 - k01 * k01, a02 = k00 * k12 - k02 * k01, a03 = k00 * k13 - k03 * k01;
+        const double a12 = k01 * k12 - k02 * k11, a13 = k01 * k13 - k03 * k11, a23 = k02 * k13 - k03 * k12;
+        const double b01 = k02 * k13 - k12 * k03, b02 = k02 * k23 - k22 * k03, b03 = k02 * k33 - k23 * k03;
+        const double b12 = k12 * k23 - k22 * k13, b13 = k12 * k33 - k23 * k13, b23 = k22 * k33 - k23 * k23;
+        const double C0 = a01 * b23 - a02 * b13 + a03 * b12 + a12 * b03 - a13 * b02 + a23 * b01;
+        const double C2 = -2.0 * ss, C1 = -8.0 * detM;
+        e0[p] = 0.5 * ((double)Ga[p] + (double)Gb[p]);
+        // upper bound of the largest root, float32 is enough (nudged up so rounding cannot undershoot)
+        float ub = fminf(sqrtf(3.0f * (float)ss) * 1.000001f, (float)e0[p] * 1.000001f);
+        ub = fmaxf(ub, 1e-30f);
+        // exact power-of-two scale s = 2^-e with ub*s in [1,2)
+        const int e = ((__float_as_int(ub) >> 23) & 0xff) - 127;
+        const double s1 = __longlong_as_double((long long)(1023 - e) << 52);
+        const double s2 = s1 * s1;
+        scale_back[p] = __longlong_as_double((long long)(1023 + e) << 52);
+        c2[p] = C2 * s2; c1[p] = C1 * s2 * s1; c0[p] = C0 * s2 * s2;
+        f2[p] = (float)c2[p]; f1[p] = (float)c1[p]; f0[p] = (float)c0[p];
+        t[p] = ub * (float)s1;
+    }
+#pragma unroll 1
+    for (int it = 0; it < 16; ++it) {
+        bool conv = true;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const float t2 = t[p] * t[p];
+            const float b = (t2 + f2[p]) * t[p];
+            const float a = b + f1[p];
+            const float den = fmaf(2.0f * t2, t[p], b + a);
+            const float num = fmaf(a, t[p], f0[p]);
+            const float d = (fabsf(den) > 1e-30f) ? __fdividef(num, den) : 0.0f;
+            t[p] -= d;
+            conv = conv && (fabsf(d) <= 4e-6f * t[p]);
+        }
+        if (__all_sync(0xffffffffu, conv)) break;  // warp-uniform exit: no divergence inside the loop
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        double x = (double)t[p];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const double x2 = x * x;
+            const double b = (x2 + c2[p]) * x;
+            const double a = b + c1[p];
+            const double den = 2.0 * x2 * x + b + a;
+            const double num = a * x + c0[p];
+            double r = (double)__frcp_rn((float)den);
+            r = r * (2.0 - den * r);
+            const double d = num * r;
+            x -= (fabs(den) > 1e-300 && d == d) ? d : 0.0;
+        }
+        const double lam = x * scale_back[p];
+        double msd = 2.0 * (e0[p] - lam) * (double)inv_n;
+        msd = msd > 0.0 ? msd : 0.0;
+        rmsd[p] = sqrtf((float)msd);
+    }
+}
+
 }  // namespace b200
