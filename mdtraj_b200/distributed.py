@@ -40,6 +40,8 @@ def gather_frames(local: "np.ndarray | object", n_total: int, group=None, device
     bounds = all_shard_bounds(n_total, world)
     is_tensor = isinstance(local, torch.Tensor)
     t = local if is_tensor else torch.from_numpy(np.ascontiguousarray(local, dtype=np.float32))
+    if device is None and not t.is_cuda and dist.get_backend(group) == "nccl":
+        device = torch.device("cuda", torch.cuda.current_device())  # NCCL moves device memory only
     if device is not None:
         t = t.to(device)
     assert t.numel() == bounds[rank][1] - bounds[rank][0], "local block does not match this rank's shard"
