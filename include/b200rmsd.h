@@ -128,7 +128,10 @@ int b200rmsd_rotate_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t frame
  * b200rmsd_allpairs_workspace_bytes(n_frames, n_sel) bytes; opaque contents (centred
  * K-major operands, traces).  With multiple GPUs every rank prepares (or receives by
  * broadcast) the same workspace and computes its own row block. */
-#define B200RMSD_DIAG_ZERO 1u /* D[i][i] = 0 exactly, like the reference's same-pointer shortcut */
+#define B200RMSD_DIAG_ZERO 1u  /* D[i][i] = 0 exactly, like the reference's same-pointer shortcut */
+#define B200RMSD_FAST_SOLVE 2u /* all-float32 QCP solve in the tensor-core epilogue: the precision class of the
+                                * reference's own msdFromMandG (float32 polynomial + float32 G_a+G_b-2*lambda,
+                                * theobald_rmsd.cpp:249-277) instead of the default float64 polynomial */
 
 size_t b200rmsd_allpairs_workspace_bytes(int64_t n_frames, int n_sel);
 

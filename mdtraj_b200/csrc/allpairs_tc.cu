@@ -164,12 +164,32 @@ struct TcParams {
     unsigned flags;
 };
 
+// Tile rasterisation: super-blocks of kSuper x kSuper tiles, row-major inside a block and across blocks, so that the
+// ~150 CTAs in flight share a working set of 2*kSuper operand tiles (10 MB at K=320) that stays L2-resident,
+// instead of sweeping the whole operand (hundreds of MB) once per tile row.
+constexpr int kSuper = 16;
+__device__ __forceinline__ void tile_coords(int64_t t, const TcParams& p, int& ti, int& tj)
+{
+    const int bj_count = (p.tiles_j + kSuper - 1) / kSuper;
+    const int64_t full_row = (int64_t)kSuper * p.tiles_j;          // tiles in one full block row
+    const int bi = (int)(t / full_row);
+    const int rows_here = min(kSuper, p.tiles_i - bi * kSuper);
+    int64_t r = t - (int64_t)bi * full_row;                        // index inside this block row
+    const int64_t per_block = (int64_t)rows_here * kSuper;
+    int bj = (int)(r / per_block);
+    if (bj >= bj_count) bj = bj_count - 1;
+    r -= (int64_t)bj * per_block;
+    const int cols_here = min(kSuper, p.tiles_j - bj * kSuper);
+    ti = p.tiles_i0 + bi * kSuper + (int)(r / cols_here);
+    tj = bj * kSuper + (int)(r % cols_here);
+}
+
 __device__ __forceinline__ float sel3(int c, float a0, float a1, float a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
 
 // EPI_WARPS in {4, 8, 16}: epilogue warps (each TMEM lane quarter is served by EPI_WARPS/4 warps that split the
 // four 32-column chunks of the accumulator); NP in {1, 2}: independent solves interleaved per lane.
 template <int EPI_WARPS, int NP>
-__global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TcParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -189,19 +209,23 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == EPI_WARPS) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    // Warp roles: warps [0, EPI_WARPS) epilogue, warp EPI_WARPS = TMA producer, warp EPI_WARPS+1 = MMA issuer.
+    // The two single-thread roles get the highest warp ids: the SMSP arbiter favours higher warp ids, and a late
+    // TMA or MMA issue stalls the whole pipeline while a late epilogue instruction does not.
+    if (warp == EPI_WARPS) {
         // ===================================================== TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int ti = p.tiles_i0 + (int)(t / p.tiles_j), tj = (int)(t % p.tiles_j);
+                int ti, tj;
+                tile_coords(t, p, ti, tj);
                 for (int kb = 0; kb < p.nk; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     unsigned char* st = smem + stage * kStageBytes;
@@ -214,7 +238,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == EPI_WARPS + 1) {
         // ===================================================== MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = make_tf32_idesc(kBM, kBN);
@@ -247,11 +271,11 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else if (warp >= 4) {
-        // ===================================================== epilogue (TMEM -> QCP -> HBM), 8 warps
+    } else {
+        // ===================================================== epilogue (TMEM -> QCP -> HBM)
         const int ew = warp & 3;                 // TMEM lane quarter this warp may read (warp_id % 4)
         constexpr int kChunksPerWarp = 16 / EPI_WARPS;  // 4, 2 or 1 of the four 32-column chunks
-        const int part = (warp - 4) >> 2;        // which share of the chunks
+        const int part = warp >> 2;              // which share of the chunks
         const int c = lane % 3, tq = lane / 3;   // component row and frame slot of this lane
         const bool row_valid = lane < 30;
         const int src1 = lane - c + (c + 1) % 3, src2 = lane - c + (c + 2) % 3;
@@ -259,7 +283,8 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int ti = p.tiles_i0 + (int)(t / p.tiles_j), tj = (int)(t % p.tiles_j);
+            int ti, tj;
+            tile_coords(t, p, ti, tj);
             const int64_t fi = (int64_t)ti * kFramesPerTile + ew * 10 + tq;  // row frame of this lane
             const bool i_ok = row_valid && fi >= p.row0 && fi < p.row1;
             const float Gi = i_ok ? __ldg(p.traces + fi) : 1.0f;
@@ -301,8 +326,10 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                     if (p.flags & 0x100u) {  // development: skip the solve to time the GEMM main loop alone
 #pragma unroll
                         for (int u = 0; u < NP; ++u) res[u] = M[u][0];
+                    } else if (p.flags & B200RMSD_FAST_SOLVE) {  // all-float32 solve (reference-class precision)
+                        qcp_msd_f32<NP>(M, Ga, Gb, ok, inv_n, res);
                     } else {
-                        qcp_msd_fast<NP>(M, Ga, Gb, inv_n, res);
+                        qcp_msd_fast<NP>(M, Ga, Gb, ok, inv_n, res);
                     }
 #pragma unroll
                     for (int u = 0; u < NP; ++u)
@@ -320,7 +347,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == EPI_WARPS) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
@@ -394,7 +421,7 @@ int launch_allpairs_tc_rows(const float* hi, const float* lo, const float* trace
     p.tiles_i = (int)((row1 + kFramesPerTile - 1) / kFramesPerTile) - p.tiles_i0;
     p.tiles_j = (int)((n_frames + kFramesPerTile - 1) / kFramesPerTile);
     p.flags = flags;
-    if (const char* dbg = getenv("B200RMSD_TC_DEBUG")) p.flags |= (unsigned)strtoul(dbg, nullptr, 0) & 0xff00u;
+    if (const char* dbg = getenv("B200RMSD_TC_DEBUG")) p.flags |= (unsigned)strtoul(dbg, nullptr, 0) & 0xff02u;
     const size_t smem = (size_t)kStages * kStageBytes + 1024 + 256;
     int64_t ctas = sm_count;
     const int64_t n_tiles = (int64_t)p.tiles_i * p.tiles_j;
@@ -406,7 +433,7 @@ int launch_allpairs_tc_rows(const float* hi, const float* lo, const float* trace
 #define B200_LAUNCH_TC(EW, NP)                                                                                         \
     do {                                                                                                               \
         e = cudaFuncSetAttribute(allpairs_tc_kernel<EW, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) allpairs_tc_kernel<EW, NP><<<(unsigned)ctas, 128 + 32 * EW, smem, st>>>(map_hi, map_lo, p); \
+        if (e == cudaSuccess) allpairs_tc_kernel<EW, NP><<<(unsigned)ctas, 64 + 32 * EW, smem, st>>>(map_hi, map_lo, p); \
     } while (0)
     if (ew == 4 && np == 2) B200_LAUNCH_TC(4, 2);
     else if (ew == 8 && np == 1) B200_LAUNCH_TC(8, 1);

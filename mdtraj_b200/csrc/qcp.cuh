@@ -147,7 +147,7 @@ __device__ __forceinline__ double qcp_solve(const QcpInput& in, float* rot, bool
 // ---------------------------------------------------------------------------------------------
 template <int NP>
 __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const float (&Ga)[NP], const float (&Gb)[NP],
-                                             float inv_n, float (&rmsd)[NP])
+                                             const bool (&active)[NP], float inv_n, float (&rmsd)[NP])
 {
     double c2[NP], c1[NP], c0[NP], e0[NP], scale_back[NP];
     float t[NP], f2[NP], f1[NP], f0[NP];
@@ -193,7 +193,7 @@ __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const floa
             const float num = fmaf(a, t[p], f0[p]);
             const float d = (fabsf(den) > 1e-30f) ? __fdividef(num, den) : 0.0f;
             t[p] -= d;
-            conv = conv && (fabsf(d) <= 4e-6f * t[p]);
+            conv = conv && (!active[p] || fabsf(d) <= 4e-6f * t[p]);  // idle lanes must not hold the warp back
         }
         if (__all_sync(0xffffffffu, conv)) break;  // warp-uniform exit: no divergence inside the loop
     }
@@ -216,6 +216,63 @@ __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const floa
         double msd = 2.0 * (e0[p] - lam) * (double)inv_n;
         msd = msd > 0.0 ? msd : 0.0;
         rmsd[p] = sqrtf((float)msd);
+    }
+}
+
+// All-float32 variant (development / comparison): coefficients, Newton and the final cancellation in float32,
+// i.e. the precision class of the reference's own msdFromMandG (theobald_rmsd.cpp:217-277).
+template <int NP>
+__device__ __forceinline__ void qcp_msd_f32(const float (&M)[NP][9], const float (&Ga)[NP], const float (&Gb)[NP],
+                                            const bool (&active)[NP], float inv_n, float (&rmsd)[NP])
+{
+    float c2[NP], c1[NP], c0[NP], e0[NP], t[NP], sc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        e0[p] = 0.5f * (Ga[p] + Gb[p]);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ss = fmaf(M[p][i], M[p][i], ss);
+        float ub = fminf(sqrtf(3.0f * ss) * 1.000001f, e0[p] * 1.000001f);
+        ub = fmaxf(ub, 1e-30f);
+        const int e = ((__float_as_int(ub) >> 23) & 0xff) - 127;
+        const float s1 = __int_as_float((127 - e) << 23);
+        sc[p] = __int_as_float((127 + e) << 23);
+        float m[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) m[i] = M[p][i] * s1;  // exact scaling: work with M/2^e
+        const float Sxx = m[0], Sxy = m[1], Sxz = m[2], Syx = m[3], Syy = m[4], Syz = m[5], Szx = m[6], Szy = m[7], Szz = m[8];
+        const float k00 = Sxx + Syy + Szz, k11 = Sxx - Syy - Szz, k22 = -Sxx + Syy - Szz, k33 = -Sxx - Syy + Szz;
+        const float k01 = Szy - Syz, k02 = Sxz - Szx, k03 = Syx - Sxy, k12 = Syx + Sxy, k13 = Sxz + Szx, k23 = Szy + Syz;
+        const float detM = Sxx * (Syy * Szz - Syz * Szy) + Syx * (Szy * Sxz - Szz * Sxy) + Szx * (Sxy * Syz - Sxz * Syy);
+        const float a01 = k00 * k11 - k01 * k01, a02 = k00 * k12 - k02 * k01, a03 = k00 * k13 - k03 * k01;
+        const float a12 = k01 * k12 - k02 * k11, a13 = k01 * k13 - k03 * k11, a23 = k02 * k13 - k03 * k12;
+        const float b01 = k02 * k13 - k12 * k03, b02 = k02 * k23 - k22 * k03, b03 = k02 * k33 - k23 * k03;
+        const float b12 = k12 * k23 - k22 * k13, b13 = k12 * k33 - k23 * k13, b23 = k22 * k33 - k23 * k23;
+        c0[p] = a01 * b23 - a02 * b13 + a03 * b12 + a12 * b03 - a13 * b02 + a23 * b01;
+        c2[p] = -2.0f * ss * s1 * s1;
+        c1[p] = -8.0f * detM;
+        t[p] = ub * s1;
+    }
+#pragma unroll 1
+    for (int it = 0; it < 20; ++it) {
+        bool conv = true;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const float t2 = t[p] * t[p];
+            const float b = (t2 + c2[p]) * t[p];
+            const float a = b + c1[p];
+            const float den = fmaf(2.0f * t2, t[p], b + a);
+            const float num = fmaf(a, t[p], c0[p]);
+            const float d = (fabsf(den) > 1e-30f) ? __fdividef(num, den) : 0.0f;
+            t[p] -= d;
+            conv = conv && (!active[p] || fabsf(d) <= 2e-7f * t[p]);
+        }
+        if (__all_sync(0xffffffffu, conv)) break;
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const float msd = 2.0f * (e0[p] - t[p] * sc[p]) * inv_n;
+        rmsd[p] = sqrtf(fmaxf(msd, 0.f));
     }
 }
 

@@ -354,6 +354,10 @@ def test_allpairs_tensor_core_vs_simt_and_truth(mdb, oracle_mod, monkeypatch, F,
         truth = O.truth_rmsd(X, X, i)
         m = np.arange(F) != i
         assert_close(D_tc[i][m], truth[m], what=f"tcgen05 row {i} vs truth")
+    # all-float32 solve: reference-class precision, still inside the parity tolerance on this data
+    monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
+    D_fast = mdb.rmsd_matrix(dt, precise=False)
+    assert_close(D_fast, D_simt, what="tcgen05 float32 solve vs SIMT")
     # a row block, as a rank of a sharded run computes it
     from mdtraj_b200 import allpairs as AP
     monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
