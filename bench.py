@@ -383,11 +383,16 @@ def main():
         tpeak, tsrc = tf32_peak()
         kpad = (N + 31) // 32 * 32
         pairs_per_s = units_per_step / (kern_ms * 1e-3)
-        issued = pairs_per_s * 3 * 18 * kpad / 1e12  # three tf32 MMAs per product term, K padded to 32
+        # flops actually issued: 128x128 tiles (40x40 frames), three tf32 MMAs per K-step, K padded to 32; a
+        # single-rank full matrix computes the upper triangle of tiles only and mirrors it
+        T = -(-F // 40)
+        tiles = T * (T + 1) // 2 if world == 1 else -(-(r1 - r0) // 40) * T
+        issued = tiles * 128 * 128 * kpad * 2 * 3 / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": dominant, "achieved": issued, "peak": tpeak, "unit": "TFLOP/s",
                     "frac": issued / tpeak, "traffic": None, "peak_source": tsrc, "kernel_ms": kern_ms,
                     "useful_tflops": pairs_per_s * 18 * N / 1e12,
-                    "note": "achieved = issued 3xTF32 flops (3 * 18 * K_pad per pair); useful = 18 * A per pair"}
+                    "note": "achieved = tensor flops actually issued (3 tf32 MMAs per K-step over the computed 128x128 "
+                            "tiles; symmetric tiles computed once); useful = 18 * A flops per reported pair"}
 
     cpu = None
     if not args.no_cpu and args.gpus == 1:

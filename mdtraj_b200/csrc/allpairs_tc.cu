@@ -161,6 +161,8 @@ struct TcParams {
     int nk;                  // K blocks of 32
     int tiles_i0;            // first i-tile (= row0 / 40)
     int tiles_i, tiles_j;    // tile grid
+    int symmetric;           // full square matrix: compute tiles tj >= ti only and mirror them
+    int n_super;             // super-blocks per side (symmetric mode)
     unsigned flags;
 };
 
@@ -168,8 +170,23 @@ struct TcParams {
 // ~150 CTAs in flight share a working set of 2*kSuper operand tiles (10 MB at K=320) that stays L2-resident,
 // instead of sweeping the whole operand (hundreds of MB) once per tile row.
 constexpr int kSuper = 16;
-__device__ __forceinline__ void tile_coords(int64_t t, const TcParams& p, int& ti, int& tj)
+__device__ __forceinline__ bool tile_coords(int64_t t, const TcParams& p, int& ti, int& tj)
 {
+    if (p.symmetric) {
+        // slots: (super-block pair bi <= bj) x (kSuper x kSuper tiles); slots outside the matrix or below the
+        // diagonal are skipped (identically by all three warp roles)
+        const int64_t blk = t / (kSuper * kSuper);
+        const int in = (int)(t % (kSuper * kSuper));
+        const double nb2 = 2.0 * p.n_super + 1.0;
+        int bi = (int)((nb2 - sqrt(nb2 * nb2 - 8.0 * (double)blk)) * 0.5);
+        // first slot of block row bi is bi*n_super - bi*(bi-1)/2; fix rounding of the square root
+        while (bi > 0 && (int64_t)bi * p.n_super - (int64_t)bi * (bi - 1) / 2 > blk) --bi;
+        while ((int64_t)(bi + 1) * p.n_super - (int64_t)(bi + 1) * bi / 2 <= blk) ++bi;
+        const int bj = bi + (int)(blk - ((int64_t)bi * p.n_super - (int64_t)bi * (bi - 1) / 2));
+        ti = bi * kSuper + in / kSuper;
+        tj = bj * kSuper + in % kSuper;
+        return ti < p.tiles_i && tj < p.tiles_j && tj >= ti;
+    }
     const int bj_count = (p.tiles_j + kSuper - 1) / kSuper;
     const int64_t full_row = (int64_t)kSuper * p.tiles_j;          // tiles in one full block row
     const int bi = (int)(t / full_row);
@@ -182,6 +199,7 @@ __device__ __forceinline__ void tile_coords(int64_t t, const TcParams& p, int& t
     const int cols_here = min(kSuper, p.tiles_j - bj * kSuper);
     ti = p.tiles_i0 + bi * kSuper + (int)(r / cols_here);
     tj = bj * kSuper + (int)(r % cols_here);
+    return true;
 }
 
 __device__ __forceinline__ float sel3(int c, float a0, float a1, float a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
@@ -202,7 +220,8 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_tiles = (int64_t)p.tiles_i * p.tiles_j;
+    const int64_t n_tiles = p.symmetric ? (int64_t)p.n_super * (p.n_super + 1) / 2 * (kSuper * kSuper)
+                                        : (int64_t)p.tiles_i * p.tiles_j;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -225,7 +244,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             uint32_t phase = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 int ti, tj;
-                tile_coords(t, p, ti, tj);
+                if (!tile_coords(t, p, ti, tj)) continue;
                 for (int kb = 0; kb < p.nk; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     unsigned char* st = smem + stage * kStageBytes;
@@ -247,6 +266,8 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                int ti_unused, tj_unused;
+                if (!tile_coords(t, p, ti_unused, tj_unused)) continue;
                 mbar_wait(&tempty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
@@ -284,7 +305,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         uint32_t acc_phase = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             int ti, tj;
-            tile_coords(t, p, ti, tj);
+            if (!tile_coords(t, p, ti, tj)) continue;
             const int64_t fi = (int64_t)ti * kFramesPerTile + ew * 10 + tq;  // row frame of this lane
             const bool i_ok = row_valid && fi >= p.row0 && fi < p.row1;
             const float Gi = i_ok ? __ldg(p.traces + fi) : 1.0f;
@@ -333,9 +354,15 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                     }
 #pragma unroll
                     for (int u = 0; u < NP; ++u)
-                        if (ok[u])
-                            p.out[(size_t)(fi - p.row0) * p.ld + fj[u]] =
-                                (fi == fj[u] && (p.flags & B200RMSD_DIAG_ZERO)) ? 0.f : res[u];
+                        if (ok[u]) {
+                            const float v = (fi == fj[u] && (p.flags & B200RMSD_DIAG_ZERO)) ? 0.f : res[u];
+                            if (!p.symmetric) {
+                                p.out[(size_t)(fi - p.row0) * p.ld + fj[u]] = v;
+                            } else if (fj[u] >= fi) {  // each unordered pair once, mirrored: D is exactly symmetric
+                                p.out[(size_t)fi * p.ld + fj[u]] = v;
+                                if (fj[u] != fi) p.out[(size_t)fj[u] * p.ld + fi] = v;
+                            }
+                        }
                 }
             }
             tc_fence_before();
@@ -421,10 +448,12 @@ int launch_allpairs_tc_rows(const float* hi, const float* lo, const float* trace
     p.tiles_i = (int)((row1 + kFramesPerTile - 1) / kFramesPerTile) - p.tiles_i0;
     p.tiles_j = (int)((n_frames + kFramesPerTile - 1) / kFramesPerTile);
     p.flags = flags;
+    p.symmetric = (row0 == 0 && row1 == n_frames && !getenv("B200RMSD_NO_SYMMETRIC")) ? 1 : 0;
+    p.n_super = (p.tiles_j + kSuper - 1) / kSuper;
     if (const char* dbg = getenv("B200RMSD_TC_DEBUG")) p.flags |= (unsigned)strtoul(dbg, nullptr, 0) & 0xff02u;
     const size_t smem = (size_t)kStages * kStageBytes + 1024 + 256;
     int64_t ctas = sm_count;
-    const int64_t n_tiles = (int64_t)p.tiles_i * p.tiles_j;
+    const int64_t n_tiles = p.symmetric ? ((int64_t)p.tiles_j * (p.tiles_j + 1)) / 2 : (int64_t)p.tiles_i * p.tiles_j;
     if (ctas > n_tiles) ctas = n_tiles;
     const char* cfg = getenv("B200RMSD_TC_EPILOGUE");  // development: "<warps>x<np>", e.g. 16x1
     int ew = 16, np = 2;  // measured best on B200 (16x2 > 16x1 > 8x2 > 8x1)

@@ -363,4 +363,11 @@ def test_allpairs_tensor_core_vs_simt_and_truth(mdb, oracle_mod, monkeypatch, F,
     monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
     prep = AP.prepare(dt)
     blk = AP.rows(prep, 37, 123).cpu().numpy()
-    assert np.array_equal(blk, D_tc[37:123])
+    # full-matrix calls compute each unordered pair once and mirror it (exactly symmetric); row blocks compute
+    # every entry: identical to the unmirrored full matrix bit for bit, and to the mirrored one within float32 noise
+    assert np.array_equal(D_tc, D_tc.T)
+    monkeypatch.setenv("B200RMSD_NO_SYMMETRIC", "1")
+    D_full = mdb.rmsd_matrix(dt)
+    monkeypatch.delenv("B200RMSD_NO_SYMMETRIC")
+    assert np.array_equal(blk, D_full[37:123])
+    assert_close(blk, D_tc[37:123], atol=2e-6, what="row block vs mirrored full matrix")
