@@ -75,6 +75,7 @@ bool fused_override(FusedParams& p, int op, int G, int nbuf);
 cudaError_t launch_frame_resident(const FusedParams& p, int op, int sm_count, cudaStream_t st);
 
 cudaError_t launch_ovm_tma(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st);
+bool launch_ovm_group(OvmParams& p, bool precentered, int sm_count, cudaStream_t st, cudaError_t* err);
 cudaError_t launch_ovm_gather(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st);
 cudaError_t launch_prepare_ref(const float* frame, const int* idx, int n_sel, int do_center, float given_trace,
                                float* ref_out, RefStats* stats, cudaStream_t st);

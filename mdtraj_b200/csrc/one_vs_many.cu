@@ -29,6 +29,8 @@
 //     per frame (16 shuffles), then everything -- recentring, polynomial, Newton,
 //     the G_a+G_b-2*lambda cancellation, quaternion -- in float64 on one lane per
 //     frame, kBatch frames at a time.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "qcp.cuh"
@@ -259,6 +261,152 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
     }
 }
 
+// ---------------------------------------------------------------------------
+// Short frames (<= 256 atoms): L lanes per frame, 32/L frames per warp iteration.
+// A whole-warp pass over a 22- or 100-atom frame leaves most lanes idle and pays the reduction, the mbarrier
+// round trip and the copy issue once per frame; here one bulk copy brings 32/L consecutive frames, each lane group
+// reduces over log2(L) shuffle stages only, and the float64 solve runs on full 32-frame batches.
+// ---------------------------------------------------------------------------
+constexpr int kGroupBatch = 32;  // frames per solve batch (one per lane)
+
+template <int L>
+__device__ __forceinline__ int group_reduce_scatter16(float (&v)[16], int lane)
+{
+    // after the call v[0 .. 16/L) of this lane hold the group sums of value indices base .. base + 16/L - 1
+    int base = 0;
+    int cnt = 8;
+#pragma unroll
+    for (int h = L / 2; h >= 1; h >>= 1) {
+        const bool up = lane & h;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < cnt) {
+                const float send = up ? v[j] : v[j + cnt];
+                const float keep = up ? v[j + cnt] : v[j];
+                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+            }
+        }
+        base += up ? cnt : 0;
+        cnt >>= 1;
+    }
+    return base;
+}
+
+struct OvmGroupLayout {
+    size_t ref_off, ring_off, sums_off, bar_off, total, stage_bytes;
+};
+__host__ __device__ inline OvmGroupLayout ovm_group_layout(int units, int fpi, int stages)
+{
+    OvmGroupLayout G;
+    G.stage_bytes = (size_t)fpi * units * 48;
+    G.ref_off = 0;
+    G.ring_off = align_up((size_t)units * 48, 128);
+    G.sums_off = G.ring_off + (size_t)kWarpsPerCta * stages * G.stage_bytes;
+    G.bar_off = align_up(G.sums_off + (size_t)kWarpsPerCta * kGroupBatch * kSumStride * sizeof(float), 8);
+    G.total = G.bar_off + ((size_t)kWarpsPerCta * stages + 1) * sizeof(uint64_t);
+    return G;
+}
+
+template <int L, bool PRE>
+__global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_group_kernel(const OvmParams p)
+{
+    constexpr int FPI = 32 / L;  // frames per warp iteration
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int units = p.total_units;
+    const OvmGroupLayout G = ovm_group_layout(units, FPI, p.stages);
+    const float4* ref_s = reinterpret_cast<const float4*>(smem + G.ref_off);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.bar_off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / L, j = lane % L;
+    unsigned char* ring = smem + G.ring_off + (size_t)warp * p.stages * G.stage_bytes;
+    uint64_t* my_bars = bars + warp * p.stages;
+    uint64_t* ref_bar = bars + kWarpsPerCta * p.stages;
+    float* sums = reinterpret_cast<float*>(smem + G.sums_off) + warp * kGroupBatch * kSumStride;
+    const uint32_t frame_bytes = (uint32_t)units * 48u;
+
+    if (lane == 0)
+        for (int s = 0; s < p.stages; ++s) mbar_init(&my_bars[s], 1);
+    if (threadIdx.x == 0) mbar_init(ref_bar, 1);
+    fence_mbar_init();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(ref_bar, frame_bytes);
+        bulk_g2s(smem + G.ref_off, p.ref, frame_bytes, ref_bar);
+    }
+
+    const int64_t W = (int64_t)gridDim.x * kWarpsPerCta;
+    const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t f_begin = p.n_frames * gw / W, f_end = p.n_frames * (gw + 1) / W;
+    const int64_t n_iter = (f_end - f_begin + FPI - 1) / FPI;
+    const uint64_t pol = l2_policy_evict_first();
+
+    int64_t issued = 0;
+    auto issue = [&](int stage) {  // lane 0: one bulk copy = FPI consecutive frames (contiguous in HBM)
+        const int64_t fb = f_begin + issued * FPI;
+        const int nfr = (int)min((int64_t)FPI, f_end - fb);
+        const uint32_t bytes = (uint32_t)nfr * frame_bytes;
+        mbar_arrive_expect_tx(&my_bars[stage], bytes);
+        bulk_g2s_hint(ring + (size_t)stage * G.stage_bytes, p.xyz + fb * p.frame_stride, bytes, &my_bars[stage], pol);
+        ++issued;
+    };
+    if (lane == 0)
+        for (int s = 0; s < p.stages && issued < n_iter; ++s) issue(s);
+    mbar_wait(ref_bar, 0);
+
+    int stage = 0;
+    uint32_t phase = 0;
+    int slot = 0;
+    int64_t batch_f0 = f_begin;
+#pragma unroll 1
+    for (int64_t it = 0; it < n_iter; ++it) {
+        const int64_t fb = f_begin + it * FPI;
+        const bool active = fb + g < f_end;
+        mbar_wait(&my_bars[stage], phase);
+        const float4* xs = reinterpret_cast<const float4*>(ring + (size_t)stage * G.stage_bytes + (size_t)g * frame_bytes);
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (active) {
+            if (!PRE) {
+                const float4 first = xs[0];
+                px = first.x; py = first.y; pz = first.z;
+            }
+#pragma unroll 2
+            for (int u = j; u < units; u += L) {
+                const float4 a0 = xs[3 * u], a1 = xs[3 * u + 1], a2 = xs[3 * u + 2];
+                const float4 b0 = ref_s[3 * u], b1 = ref_s[3 * u + 1], b2 = ref_s[3 * u + 2];
+                acc_unit<PRE>(v, a0, a1, a2, b0, b1, b2, px, py, pz, p.n_atoms - 4 * u);
+            }
+            if (j == 0) { v[13] = px; v[14] = py; v[15] = pz; }
+        }
+        __syncwarp();
+        if (lane == 0 && issued < n_iter) {
+            fence_proxy_async_smem();
+            issue(stage);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+
+        const int base = group_reduce_scatter16<L>(v, lane);
+#pragma unroll
+        for (int k = 0; k < 16 / L; ++k) sums[(slot + g) * kSumStride + base + k] = v[k];
+        slot += FPI;
+        if (slot == kGroupBatch || it + 1 == n_iter) {
+            __syncwarp();
+            const int64_t f = batch_f0 + lane;
+            if (lane < slot && f < f_end) {
+                double rec[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) rec[i] = (double)sums[lane * kSumStride + i];
+                finish_frame<PRE>(rec, f, p);
+            }
+            __syncwarp();
+            slot = 0;
+            batch_f0 = fb + FPI;
+        }
+    }
+}
+
 // combine segment partials (float64) and solve; one thread per frame
 template <bool PRE>
 __global__ void ovm_finish_kernel(const OvmParams p)
@@ -359,6 +507,54 @@ cudaError_t launch_ovm_tma(const OvmParams& p, bool precentered, int sm_count, c
         e = cudaGetLastError();
     }
     return e;
+}
+
+template <int L>
+static cudaError_t launch_group_L(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st)
+{
+    const OvmGroupLayout G = ovm_group_layout(p.total_units, 32 / L, p.stages);
+    auto kern = precentered ? ovm_group_kernel<L, true> : ovm_group_kernel<L, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
+    if (e != cudaSuccess) return e;
+    int64_t ctas = sm_count;
+    const int64_t need = (p.n_frames + kWarpsPerCta * (32 / L) - 1) / (kWarpsPerCta * (32 / L));
+    if (ctas > need) ctas = need;
+    kern<<<(unsigned)ctas, kThreadsPerCta, G.total, st>>>(p);
+    return cudaGetLastError();
+}
+
+// Short-frame path.  Returns false (and launches nothing) when the shape is not eligible.
+bool launch_ovm_group(OvmParams& p, bool precentered, int sm_count, cudaStream_t st, cudaError_t* err)
+{
+    p.total_units = (p.n_atoms + 3) / 4;
+    const size_t frame_bytes = (size_t)p.total_units * 48;
+    if (p.frame_stride != (int64_t)p.total_units * 12 || frame_bytes > 3072 || p.n_seg > 1) return false;
+    const size_t budget = 232448;
+    const size_t fixed = align_up(frame_bytes, 128) + (size_t)kWarpsPerCta * kGroupBatch * kSumStride * sizeof(float) + 1024;
+    const size_t per_warp = (budget - fixed) / kWarpsPerCta;
+    // fewest lanes per frame (= most frames per bulk copy and per reduction) whose ring still holds >= 2 stages
+    int Lsel = 0, stages = 0;
+    for (int L = 2; L <= 16; L <<= 1) {
+        const size_t stage_bytes = (size_t)(32 / L) * frame_bytes;
+        const int st_n = (int)(per_warp / stage_bytes);
+        if (st_n >= 2) { Lsel = L; stages = st_n > 4 ? 4 : st_n; break; }
+    }
+    if (const char* force = getenv("B200RMSD_GROUP_LANES")) {  // development override
+        const int L = atoi(force);
+        if (L == 2 || L == 4 || L == 8 || L == 16) {
+            const int st_n = (int)(per_warp / ((size_t)(32 / L) * frame_bytes));
+            if (st_n >= 2) { Lsel = L; stages = st_n > 4 ? 4 : st_n; }
+        }
+    }
+    if (Lsel == 0) return false;
+    p.stages = stages;
+    switch (Lsel) {
+        case 2: *err = launch_group_L<2>(p, precentered, sm_count, st); break;
+        case 4: *err = launch_group_L<4>(p, precentered, sm_count, st); break;
+        case 8: *err = launch_group_L<8>(p, precentered, sm_count, st); break;
+        default: *err = launch_group_L<16>(p, precentered, sm_count, st); break;
+    }
+    return true;
 }
 
 cudaError_t launch_ovm_gather(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st)
