@@ -118,6 +118,26 @@ int b200rmsd_superpose_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t fr
 int b200rmsd_rotate_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const float* rot,
                         void* scratch, size_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------- "next" rows: rmsf, align/displace */
+
+/* Per-atom root-mean-square fluctuation over frames of  y = (x - c_f) . R_f  for the listed atoms
+ * (idx int32 or NULL = all n_atoms).  rot (F,9) and centroid (F,3 doubles) come from b200rmsd_rmsd_dev
+ * (out_rot / out_centroid); either may be NULL (no rotation: reference=None "prealigned" mode,
+ * _rmsd.pyx:328-330,410; no centring: the index-list path, where the reference rotates the uncentred copy,
+ * _rmsd.pyx:408).  scratch: b200rmsd_rmsf_scratch_bytes().  out_rmsf: n_sel floats.
+ * Replaces: the rotate + two per-atom reduction loops of rmsf(), _rmsd.pyx:410-444. */
+size_t b200rmsd_rmsf_scratch_bytes(int64_t n_frames, int n_sel);
+int b200rmsd_rmsf_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const int32_t* idx,
+                      int n_sel, const float* rot, const double* centroid, void* scratch, size_t scratch_bytes,
+                      float* out_rmsf, void* stream);
+
+/* out[i] = sqrt(mean_k |b_i[k] - a[k] . R_i|^2) with R_i = rot[i] (transpose != 0: its transpose); when rot_out is
+ * not NULL the rotation actually used is also written there.
+ * Replaces: rot_msd_atom_major, rotation.h:10 (loop body of getMultipleAlignDisplaceRMSDs_atom_major,
+ * _rmsd.pyx:746-749). */
+int b200rmsd_rot_msd_dev(const float* a_frame, const float* b_xyz, int64_t n_frames, int n_atoms, int64_t frame_stride,
+                         const float* rot, int transpose, float* rot_out, float* out_rmsd, void* stream);
+
 /* ------------------------------------------------------------ all-pairs matrix */
 
 /* The reference has no all-pairs function; clustering code loops md.rmsd(traj, traj, i)

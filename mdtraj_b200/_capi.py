@@ -31,6 +31,9 @@ SIGNATURES = {
     "b200rmsd_rmsd_nosuperpose_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _vp]),
     "b200rmsd_superpose_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200rmsd_rotate_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _sz, _vp]),
+    "b200rmsd_rmsf_scratch_bytes": (_sz, [_i64, _i32]),
+    "b200rmsd_rmsf_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "b200rmsd_rot_msd_dev": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _vp]),
     "b200rmsd_rmsd_host": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _f32, _vp, _i32]),
     "b200rmsd_superpose_host": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, C.POINTER(_u32), _i32]),
     "b200rmsd_center_host": (_i32, [_vp, _i64, _i32, _vp, _i32]),

@@ -245,4 +245,116 @@ cudaError_t launch_apply_transform(const ApplyParams& p, int sm_count, cudaStrea
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// md.rmsf per-atom statistics (_rmsd.pyx:411-444): y = (x - c) . R per frame, then over frames
+// mean(y) and sqrt(mean |y - mean(y)|^2).  One pass: float64 sums of y and |y|^2 per atom over a
+// chunk of frames; rmsf_finalize_kernel combines the chunks (the reference accumulates both in
+// float32 over all frames, two passes).
+// grid = (ceil(n_sel/128), n_chunks)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rmsf_stats_kernel(const float* __restrict__ xyz, int64_t n_frames,
+                                                         int64_t frame_stride, const int* __restrict__ idx, int n_sel,
+                                                         const float* __restrict__ rot, const double* __restrict__ centroid,
+                                                         int64_t frames_per_chunk, double* __restrict__ partials)
+{
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    const int64_t f0 = (int64_t)blockIdx.y * frames_per_chunk;
+    const int64_t f1 = min(n_frames, f0 + frames_per_chunk);
+    if (k >= n_sel) return;
+    const int a = idx ? __ldg(idx + k) : k;
+    double sx = 0, sy = 0, sz = 0, s2 = 0;
+    for (int64_t f = f0; f < f1; ++f) {
+        const float* fr = xyz + f * frame_stride + 3 * (int64_t)a;
+        float x = __ldg(fr), y = __ldg(fr + 1), z = __ldg(fr + 2);
+        if (centroid) {
+            x -= (float)centroid[f * 3]; y -= (float)centroid[f * 3 + 1]; z -= (float)centroid[f * 3 + 2];
+        }
+        float rx = x, ry = y, rz = z;
+        if (rot) {
+            const float* R = rot + f * 9;
+            rx = x * __ldg(R + 0) + y * __ldg(R + 3) + z * __ldg(R + 6);
+            ry = x * __ldg(R + 1) + y * __ldg(R + 4) + z * __ldg(R + 7);
+            rz = x * __ldg(R + 2) + y * __ldg(R + 5) + z * __ldg(R + 8);
+        }
+        sx += (double)rx; sy += (double)ry; sz += (double)rz;
+        s2 += (double)rx * rx + (double)ry * ry + (double)rz * rz;
+    }
+    double* out = partials + ((size_t)blockIdx.y * n_sel + k) * 4;
+    out[0] = sx; out[1] = sy; out[2] = sz; out[3] = s2;
+}
+
+__global__ void __launch_bounds__(128) rmsf_finalize_kernel(const double* __restrict__ partials, int n_chunks, int n_sel,
+                                                            int64_t n_frames, float* __restrict__ out)
+{
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    if (k >= n_sel) return;
+    double sx = 0, sy = 0, sz = 0, s2 = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const double* p = partials + ((size_t)c * n_sel + k) * 4;
+        sx += p[0]; sy += p[1]; sz += p[2]; s2 += p[3];
+    }
+    const double inv = 1.0 / (double)n_frames;
+    const double mx = sx * inv, my = sy * inv, mz = sz * inv;
+    double var = s2 * inv - (mx * mx + my * my + mz * mz);
+    out[k] = (float)sqrt(var > 0.0 ? var : 0.0);
+}
+
+int rmsf_chunks(int64_t n_frames) { return (int)((n_frames + 255) / 256 < 592 ? (n_frames + 255) / 256 : 592); }
+
+cudaError_t launch_rmsf(const float* xyz, int64_t n_frames, int64_t frame_stride, const int* idx, int n_sel,
+                        const float* rot, const double* centroid, double* partials, float* out, cudaStream_t st)
+{
+    if (n_frames <= 0 || n_sel <= 0) return cudaSuccess;
+    const int n_chunks = rmsf_chunks(n_frames);
+    const int64_t fpc = (n_frames + n_chunks - 1) / n_chunks;
+    dim3 grid((unsigned)((n_sel + 127) / 128), (unsigned)n_chunks);
+    rmsf_stats_kernel<<<grid, 128, 0, st>>>(xyz, n_frames, frame_stride, idx, n_sel, rot, centroid, fpc, partials);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    rmsf_finalize_kernel<<<(unsigned)((n_sel + 127) / 128), 128, 0, st>>>(partials, n_chunks, n_sel, n_frames, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// rot_msd_atom_major over frames (rotation_generic.h:47-102, loop body _rmsd.pyx:746-749):
+// out[i] = sqrt( mean_k | b_i[k] - a[k] . R_i |^2 ), R_i = rot[i] (or its transpose), float32 terms summed in
+// float64 like the reference.  One warp per frame.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rot_msd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                      int64_t n_frames, int n_atoms, int64_t frame_stride,
+                                                      const float* __restrict__ rot, int transpose,
+                                                      float* __restrict__ rot_out, float* __restrict__ out)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    for (int64_t f = (int64_t)blockIdx.x * 8 + warp; f < n_frames; f += n_warps) {
+        float R[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = __ldg(rot + f * 9 + (transpose ? (i % 3) * 3 + i / 3 : i));
+        if (rot_out && lane < 9) rot_out[f * 9 + lane] = __ldg(rot + f * 9 + (transpose ? (lane % 3) * 3 + lane / 3 : lane));
+        const float* bf = b + f * frame_stride;
+        double acc = 0.0;
+        for (int k = lane; k < n_atoms; k += 32) {
+            const float ax = __ldg(a + 3 * k), ay = __ldg(a + 3 * k + 1), az = __ldg(a + 3 * k + 2);
+            const float dx = __ldg(bf + 3 * k) - (ax * R[0] + ay * R[3] + az * R[6]);
+            const float dy = __ldg(bf + 3 * k + 1) - (ax * R[1] + ay * R[4] + az * R[7]);
+            const float dz = __ldg(bf + 3 * k + 2) - (ax * R[2] + ay * R[5] + az * R[8]);
+            acc += (double)(dx * dx + dy * dy + dz * dz);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[f] = sqrtf((float)(acc / (double)n_atoms));
+    }
+}
+
+cudaError_t launch_rot_msd(const float* a, const float* b, int64_t n_frames, int n_atoms, int64_t frame_stride,
+                           const float* rot, int transpose, float* rot_out, float* out, int sm_count, cudaStream_t st)
+{
+    if (n_frames <= 0) return cudaSuccess;
+    int64_t ctas = (int64_t)sm_count * 8;
+    const int64_t need = (n_frames + 7) / 8;
+    if (ctas > need) ctas = need;
+    rot_msd_kernel<<<(unsigned)ctas, 256, 0, st>>>(a, b, n_frames, n_atoms, frame_stride, rot, transpose, rot_out, out);
+    return cudaGetLastError();
+}
+
 }  // namespace b200

@@ -329,6 +329,35 @@ int b200rmsd_rotate_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t frame
     return 0;
 }
 
+size_t b200rmsd_rmsf_scratch_bytes(int64_t n_frames, int n_sel)
+{
+    if (n_frames <= 0 || n_sel <= 0) return 256;
+    return (size_t)rmsf_chunks(n_frames) * (size_t)n_sel * 4 * sizeof(double) + 256;
+}
+
+int b200rmsd_rmsf_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const int32_t* idx,
+                      int n_sel, const float* rot, const double* centroid, void* scratch, size_t scratch_bytes,
+                      float* out_rmsf, void* stream)
+{
+    if (!xyz || !out_rmsf || n_frames <= 0 || n_atoms <= 0) return fail(B200RMSD_EINVAL, "rmsf: bad arguments");
+    const int ns = idx ? n_sel : n_atoms;
+    if (ns <= 0) return fail(B200RMSD_EINVAL, "rmsf: empty selection");
+    if (!scratch || scratch_bytes < b200rmsd_rmsf_scratch_bytes(n_frames, ns) || (reinterpret_cast<uintptr_t>(scratch) & 7u))
+        return fail(B200RMSD_EINVAL, "rmsf: needs %zu bytes of 8-byte aligned scratch", b200rmsd_rmsf_scratch_bytes(n_frames, ns));
+    CU(launch_rmsf(xyz, n_frames, frame_stride, idx, ns, rot, centroid, (double*)scratch, out_rmsf, (cudaStream_t)stream));
+    return 0;
+}
+
+int b200rmsd_rot_msd_dev(const float* a_frame, const float* b_xyz, int64_t n_frames, int n_atoms, int64_t frame_stride,
+                         const float* rot, int transpose, float* rot_out, float* out_rmsd, void* stream)
+{
+    if (!a_frame || !b_xyz || !rot || !out_rmsd || n_frames < 0 || n_atoms <= 0) return fail(B200RMSD_EINVAL, "rot_msd: bad arguments");
+    int sm = 0;
+    if (int rc = current_sm_count(&sm)) return rc;
+    CU(launch_rot_msd(a_frame, b_xyz, n_frames, n_atoms, frame_stride, rot, transpose, rot_out, out_rmsd, sm, (cudaStream_t)stream));
+    return 0;
+}
+
 }  // extern "C"
 
 // ===========================================================================

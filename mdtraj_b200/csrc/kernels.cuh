@@ -85,6 +85,11 @@ cudaError_t launch_nosuperpose(const float* xyz, int64_t n_frames, int n_atoms, 
                                const float* ref_raw, float* out, int sm_count, cudaStream_t st);
 cudaError_t launch_apply_transform(const ApplyParams& p, int sm_count, cudaStream_t st);
 size_t ovm_tma_smem_bytes(const OvmParams& p);
+int rmsf_chunks(int64_t n_frames);
+cudaError_t launch_rmsf(const float* xyz, int64_t n_frames, int64_t frame_stride, const int* idx, int n_sel,
+                        const float* rot, const double* centroid, double* partials, float* out, cudaStream_t st);
+cudaError_t launch_rot_msd(const float* a, const float* b, int64_t n_frames, int n_atoms, int64_t frame_stride,
+                           const float* rot, int transpose, float* rot_out, float* out, int sm_count, cudaStream_t st);
 
 // records a thread-local message for b200rmsd_last_error() and returns `code` (defined in capi.cu)
 int set_error(int code, const char* fmt, ...);

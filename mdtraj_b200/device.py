@@ -359,7 +359,39 @@ def superpose_raw_arrays(align_target_frame, align_mobile, g_target, g_mobile, d
     return rot.cpu().numpy().reshape(F, 3, 3)
 
 
-def align_displace_raw_arrays(*args, **kwargs):
-    raise NotImplementedError(
-        "getMultipleAlignDisplaceRMSDs_atom_major (align-on-A / RMSD-on-B, _rmsd.pyx:679-759) is listed as a "
-        "'next' row in SURVEY.md section 8(f) and is not built yet; there is deliberately no CPU fallback.")
+def align_displace_raw_arrays(align1_frame, align2, g1, g2, displ1_frame, displ2, n_align, n_displ):
+    """Body of ``getMultipleAlignDisplaceRMSDs_atom_major`` (_rmsd.pyx:736-759) for host arrays.
+
+    The reference aligns a = ``xyz_align1[frame]`` onto b = ``xyz_align2[i]`` (rotation R_i), then measures
+    ``displ1[frame] . R_i`` against ``displ2[i]``.  The streaming kernel produces the rotation of frame i onto the
+    single frame, i.e. R_i^T; ``b200rmsd_rot_msd_dev(transpose=1)`` undoes that and does the measuring.
+    Returns (rmsds (F,), rotations (F,3,3)).
+    """
+    torch = _torch()
+    from ._rmsd import current_device
+    dev = torch.device("cuda", current_device())
+    F, na_pad = align2.shape[0], align2.shape[1]
+    nd_pad = displ2.shape[1]
+    L = _capi.lib()
+    a2 = torch.from_numpy(np.ascontiguousarray(align2, dtype=np.float32)).to(dev)
+    d2 = torch.from_numpy(np.ascontiguousarray(displ2, dtype=np.float32)).to(dev)
+    a1 = torch.from_numpy(np.ascontiguousarray(align1_frame, dtype=np.float32)).to(dev)
+    d1 = torch.from_numpy(np.ascontiguousarray(displ1_frame, dtype=np.float32)).to(dev)
+    tr2 = torch.from_numpy(np.ascontiguousarray(g2, dtype=np.float32)).to(dev)
+    out = torch.zeros(F, dtype=torch.float32, device=dev)
+    rot = torch.zeros((F, 9), dtype=torch.float32, device=dev)
+    rot_t = torch.zeros((F, 9), dtype=torch.float32, device=dev)
+    if F == 0:
+        return out.cpu().numpy(), rot.cpu().numpy().reshape(0, 3, 3)
+    prep = prepare_reference(a1, None, int(n_align), False, float(g1))
+    scratch = _Scratch.get(torch, dev, L.b200rmsd_scratch_bytes(F, int(n_align)))
+    with torch.cuda.device(dev):
+        stream = _stream_ptr(torch, dev)
+        rc = L.b200rmsd_rmsd_dev(a2.data_ptr(), F, int(n_align), na_pad * 3, None, int(n_align), prep.ref.data_ptr(),
+                                 prep.stats.data_ptr(), tr2.data_ptr(), _capi.PRECENTERED, out.data_ptr(),
+                                 rot_t.data_ptr(), None, None, scratch.data_ptr(), scratch.numel(), stream)
+        _capi.check(rc, "b200rmsd_rmsd_dev")
+        rc = L.b200rmsd_rot_msd_dev(d1.data_ptr(), d2.data_ptr(), F, int(n_displ), nd_pad * 3, rot_t.data_ptr(), 1,
+                                    rot.data_ptr(), out.data_ptr(), stream)
+        _capi.check(rc, "b200rmsd_rot_msd_dev")
+    return out.cpu().numpy(), rot.cpu().numpy().reshape(F, 3, 3)

@@ -105,6 +105,27 @@ def main():
         out[key + "_traces"] = np.asarray(t._rmsd_traces).copy()
         out[key + "_centered_max_abs_mean"] = np.float64(np.abs(t.xyz.mean(1)).max())
 
+    # ---- "next" rows: rmsf and the align/displace entry point ---------------------------------------
+    from mdtraj import _rmsd as ref_rmsd
+    for kind, F, N, seed in (("md", 40, 303, 14), ("iid", 64, 100, 11)):
+        gen = O.synth_iid if kind == "iid" else O.synth_md
+        X = gen(F, N, seed=seed)
+        key = f"{kind}_{F}x{N}_s{seed}"
+        out[key + "_rmsf_f1"] = md.rmsf(traj(X), traj(X), 1)
+        idx = np.arange(0, N, 3)
+        out[key + "_rmsf_f2_idx3"] = md.rmsf(traj(X), traj(X), 2, atom_indices=idx)
+        out[key + "_rmsf_prealigned"] = md.rmsf(traj(X), None)
+        t = traj(X); t.center_coordinates()
+        out[key + "_rmsf_f0_precentered"] = md.rmsf(t, t, 0, precentered=True)
+        # getMultipleAlignDisplaceRMSDs_atom_major: align on the first 60 atoms, measure on the last 40
+        n_al, n_di = 60, 40
+        A = np.zeros((F, 60, 3), np.float32); D = np.zeros((F, 40, 3), np.float32)
+        A[:] = X[:, :n_al]; D[:] = X[:, N - n_di:]
+        A -= A.mean(1, keepdims=True)
+        gA = np.einsum("ijk,ijk->i", A, A).astype(np.float32)
+        r, rot = ref_rmsd.getMultipleAlignDisplaceRMSDs_atom_major(A, A, gA, gA, D, D, n_al, n_di, 3)
+        out[key + "_aligndispl_rmsd"] = np.asarray(r).copy(); out[key + "_aligndispl_rot"] = np.asarray(rot).copy()
+
     # ---- error/warning behaviour captured verbatim (Appendix B #12) ---------------------------
     msgs = {}
     t = traj(O.synth_iid(5, 10, 1))

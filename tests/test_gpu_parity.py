@@ -371,3 +371,74 @@ def test_allpairs_tensor_core_vs_simt_and_truth(mdb, oracle_mod, monkeypatch, F,
     monkeypatch.delenv("B200RMSD_NO_SYMMETRIC")
     assert np.array_equal(blk, D_full[37:123])
     assert_close(blk, D_tc[37:123], atol=2e-6, what="row block vs mirrored full matrix")
+
+
+# ------------------------------------------------------------------ "next" rows: rmsf, align/displace
+@pytest.mark.parametrize("kind,F,N,seed", [("md", 40, 303, 14), ("iid", 64, 100, 11)])
+def test_rmsf_and_align_displace_golden(mdb, golden, oracle_mod, kind, F, N, seed):
+    """md.rmsf (_rmsd.pyx:247-484) and getMultipleAlignDisplaceRMSDs_atom_major (:679-759) vs the real reference.
+    The reference's own tests use decimal=3 for rmsf (tests/test_rmsd.py:251); we hold 2e-5."""
+    O = oracle_mod
+    X = gen(O, kind, F, N, seed)
+    key = f"{kind}_{F}x{N}_s{seed}"
+    idx = np.arange(0, N, 3)
+    t = mdb.Trajectory(X.copy())
+    assert_close(mdb.rmsf(t, t, 1), golden[key + "_rmsf_f1"], atol=2e-5, what="rmsf")
+    # index list + reference: upstream passes a non-contiguous copy to rot_atom_major (_rmsd.pyx:408,415) and
+    # returns frame-mixed values (golden key *_rmsf_f2_idx3 documents them); we return the all-atom result of the
+    # sliced trajectory instead (see mdtraj_b200/rmsf_impl.py)
+    sliced = mdb.Trajectory(X[:, idx].copy())
+    assert_close(mdb.rmsf(t, t, 2, atom_indices=idx), mdb.rmsf(sliced, sliced, 2), atol=2e-6, what="rmsf idx == sliced")
+    assert np.abs(golden[key + "_rmsf_f2_idx3"] - mdb.rmsf(sliced, sliced, 2)).max() > 1e-2  # upstream bug still there
+    raw = X[:, idx].astype(np.float64)
+    assert_close(mdb.rmsf(t, None, atom_indices=idx), np.sqrt(3 * np.mean((raw - raw.mean(0)) ** 2, axis=(0, 2))),
+                 atol=2e-5, what="rmsf prealigned idx (tests/test_rmsd.py:255-267)")
+    assert_close(mdb.rmsf(t, None), golden[key + "_rmsf_prealigned"], atol=2e-5, what="rmsf prealigned")
+    c = mdb.Trajectory(X.copy()); c.center_coordinates()
+    assert_close(mdb.rmsf(c, c, 0, precentered=True), golden[key + "_rmsf_f0_precentered"], atol=2e-5,
+                 what="rmsf precentered")
+    dt = mdb.DeviceTrajectory.from_host(X)
+    assert_close(mdb.rmsf(dt, dt, 1), golden[key + "_rmsf_f1"], atol=2e-5, what="rmsf device path")
+    # independent check of the definition (tests/test_rmsd.py:244-252)
+    # (rmsf removes each frame's own centroid on the all-atom path, then rotates onto the reference frame)
+    Y = np.einsum("fni,fij->fnj", X.astype(np.float64) - X.astype(np.float64).mean(1, keepdims=True), O.truth_superpose(X, X, 1)[1])
+    want = np.sqrt(3 * np.mean((Y - Y.mean(0)) ** 2, axis=(0, 2)))
+    assert_close(mdb.rmsf(t, t, 1), want, atol=2e-5, what="rmsf vs float64 definition")
+    with pytest.raises(ValueError, match="Mode must be one of"):
+        mdb.rmsf(t, t, 0, mode="bogus")
+    with pytest.raises(ValueError, match="Cannot calculate RMSF of frame"):
+        mdb.rmsf(t, t, F)
+    # align on the first 60 atoms, measure on the last 40
+    A = np.zeros((F, 60, 3), np.float32); D = np.zeros((F, 40, 3), np.float32)
+    A[:] = X[:, :60]; D[:] = X[:, N - 40:]
+    A -= A.mean(1, keepdims=True)
+    gA = np.einsum("ijk,ijk->i", A, A).astype(np.float32)
+    r, rot = mdb.getMultipleAlignDisplaceRMSDs_atom_major(A, A, gA, gA, D, D, 60, 40, 3)
+    m = np.arange(F) != 3
+    assert_close(r[m], golden[key + "_aligndispl_rmsd"][m], atol=2e-5, what="align/displace rmsd")
+    if kind == "md":
+        assert np.abs(rot[m] - golden[key + "_aligndispl_rot"][m]).max() < 1e-4
+    assert r.shape == (F,) and rot.shape == (F, 3, 3)
+
+
+def test_rmsf_residue_mode(mdb, oracle_mod):
+    class _El:  # minimal topology duck type (mdtraj.Topology API used at _rmsd.pyx:467-471)
+        def __init__(self, m): self.mass = m
+    class _Res:
+        def __init__(self, i): self.index = i
+    class _Atom:
+        def __init__(self, r, m): self.residue = _Res(r); self.element = _El(m)
+    class _Top:
+        def __init__(self, n): self.atoms_ = [_Atom(i // 4, 12.0 if i % 2 else 1.0) for i in range(n)]; self.n_residues = (n + 3) // 4
+        def atom(self, i): return self.atoms_[i]
+    X = oracle_mod.synth_md(30, 22, seed=8, rg=0.4, sigma=0.05)
+    t = mdb.Trajectory(X.copy(), topology=_Top(22))
+    per_atom = mdb.rmsf(t, t, 0)
+    per_res = mdb.rmsf(t, t, 0, mode="residue")
+    masses = np.array([12.0 if i % 2 else 1.0 for i in range(22)])
+    for r in range(6):
+        sel = np.arange(22)[np.arange(22) // 4 == r]
+        want = np.sqrt(np.sum(per_atom[sel] ** 2 * masses[sel]) / masses[sel].sum())
+        assert abs(per_res[r] - want) < 1e-6
+    sub = mdb.rmsf(t, t, 0, atom_indices=[0, 1, 2, 3], mode="residue")
+    assert sub[0] > 0 and np.all(sub[1:] == -1.0)

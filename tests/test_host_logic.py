@@ -86,6 +86,9 @@ def test_legacy_entry_validation():
         mdb.superpose_atom_major(a, a, g, g, np.zeros((3, 5, 3), np.float32), 0)
     with pytest.raises(ValueError, match="4\\*n"):
         mdb.getMultipleAlignDisplaceRMSDs_atom_major(a, a, g, g, a, a, 5, 5, 0)
+    t = _t()
+    with pytest.raises(ValueError, match="Mode must be one of"):
+        mdb.rmsf(t, t, 0, mode="x")
 
 
 def test_shard_bounds_cover_exactly_once():
