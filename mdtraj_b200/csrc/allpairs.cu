@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restr
                 q.Gb = (double)traces[i];
 #pragma unroll
                 for (int c = 0; c < 9; ++c) q.M[c] = (double)acc[si][sj][c];
-                r = (float)sqrt(qcp_solve(q, nullptr, nullptr));
+                r = sqrtf((float)qcp_solve(q, nullptr, nullptr));
             }
             out[(size_t)(i - row0) * ld + j] = r;
         }

@@ -8,25 +8,34 @@
 //   OP_CENTER     inplace_center_and_trace_atom_major (center_sse.h:3-112): float64 sums, float32 mean,
 //                 float32 subtraction in place, float64 trace of the float32 squares.
 //
-// One persistent CTA per SM = 16 compute warps + 1 DMA warp.  A CTA owns a contiguous range of frames and
+// One persistent CTA per SM = 16 compute warps + a loader warp + a storer warp.  A CTA owns a contiguous range of frames and
 // moves them through a ring of `nbuf` whole-frame shared-memory buffers:
-//     DMA thread : bulk load frame i (cp.async.bulk global->shared, full[i%nbuf] mbarrier), and, once the
-//                  compute group signals done[i%nbuf], bulk store it back (cp.async.bulk shared->global),
-//                  then refill the drained buffer with frame i+nbuf.
+//     loader     : bulk load frame i (cp.async.bulk global->shared, full[i%nbuf] mbarrier) as soon as the storer
+//                  reports the buffer drained.
+//     storer     : once the compute group signals done[i%nbuf], bulk store the frame back (cp.async.bulk
+//                  shared->global), wait for the store to have read the buffer, publish drained[i%nbuf].
 //     compute    : the 16 warps form G independent groups of wpf warps; group g takes frames g, g+G, ...
 //                  (sums -> float64 solve by the group's first thread -> transform in shared memory), with
 //                  group-local named barriers only.  G frames are therefore in different phases at once
 //                  and the serial QCP solve of one overlaps the streaming phases of the others; nbuf-G
 //                  buffers are in flight to/from HBM.
 // Neither the LSU nor L1 sits on the HBM path, and compute threads never wait for a store to drain.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "qcp.cuh"
 
 namespace b200 {
 
+// development aid: when set (B200RMSD_FUSED_TRACE=1), CTA 0 records clock64 stamps per frame:
+// [i*8+0] data arrived, [1] sums reduced, [2] solve done, [3] transform done, [4] handed to storer,
+// [5] store issued, [6] store drained, [7] load issued
+__device__ long long* g_fr_trace = nullptr;
+#define FR_STAMP(i, k) do { if (g_fr_trace && blockIdx.x == 0) g_fr_trace[(i) * 8 + (k)] = clock64(); } while (0)
+
 constexpr int kFrWarps = 16;                      // compute warps
-constexpr int kFrThreads = kFrWarps * 32 + 32;    // + DMA warp
+constexpr int kFrThreads = kFrWarps * 32 + 64;    // + loader warp + storer warp
 constexpr int kPartStride = 17;
 
 struct FrLayout {
@@ -44,7 +53,7 @@ __host__ __device__ inline FrLayout fr_layout(int n_pad, int nbuf, int n_sel_pad
     L.part_off = fr_align(L.idx_off + (size_t)n_idx * 4, 16);
     L.xf_off = L.part_off + (size_t)kFrWarps * kPartStride * sizeof(double);
     L.bar_off = fr_align(L.xf_off + (size_t)kFrWarps * 24 * sizeof(float), 8);
-    L.total = L.bar_off + (size_t)(2 * nbuf + 1) * sizeof(uint64_t);
+    L.total = L.bar_off + (size_t)(3 * nbuf + 1) * sizeof(uint64_t);
     return L;
 }
 
@@ -76,25 +85,32 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
     float* xf_s = reinterpret_cast<float*>(smem + L.xf_off);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* done = full + p.nbuf;
-    uint64_t* ref_bar = done + p.nbuf;
+    uint64_t* drained = done + p.nbuf;
+    uint64_t* ref_bar = drained + p.nbuf;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int G = p.batch;                     // concurrent frame groups (power of two <= 16)
-    const int wpf = kFrWarps / G;              // warps per group
+    const int G = p.batch;                     // concurrent frame groups; nbuf % G == 0
+    const int wpf = kFrWarps / G;              // warps per group (G * wpf <= 16 compute warps take part)
+    const int n_cw = G * wpf;
     const int units = p.n_pad >> 2;
     const uint32_t frame_bytes = (uint32_t)p.n_pad * 12u;
 
     const int64_t f0 = p.n_frames * blockIdx.x / gridDim.x, f1 = p.n_frames * (blockIdx.x + 1) / gridDim.x;
     const int64_t n = f1 - f0;
 
+    unsigned long long t_start_ns = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
     if (tid == 0) {
-        for (int i = 0; i < p.nbuf; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], 1); }
+        for (int i = 0; i < p.nbuf; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], 1); mbar_init(&drained[i], 1); }
         mbar_init(ref_bar, 1);
     }
     fence_mbar_init();
     __syncthreads();
 
-    // ================================================================== DMA warp
+    // ================================================================== DMA warps
+    // warp 16 lane 0: loader.  warp 17 lane 0: storer.  Two threads so that waiting for a store to drain
+    // (cp.async.bulk.wait_group.read is the only completion mechanism of shared->global bulk copies) never delays
+    // the issue of a load into another buffer: the storer publishes drained[buf], the loader refills it at once.
     if (warp == kFrWarps) {
         if (lane == 0) {
             if (OP == OP_SUPERPOSE) {
@@ -102,33 +118,47 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
                 mbar_arrive_expect_tx(ref_bar, bytes);
                 bulk_g2s(smem + L.ref_off, p.ref, bytes, ref_bar);
             }
-            auto load = [&](int64_t i) {
+            for (int64_t i = 0; i < n; ++i) {
                 const int buf = (int)(i % p.nbuf);
+                if (i >= p.nbuf) mbar_wait(&drained[buf], (uint32_t)(((i / p.nbuf) - 1) & 1));
                 mbar_arrive_expect_tx(&full[buf], frame_bytes);
                 bulk_g2s(smem + L.buf_off + (size_t)buf * L.buf_bytes, p.xyz + (f0 + i) * p.frame_stride, frame_bytes,
                          &full[buf]);
-            };
-            for (int64_t i = 0; i < p.nbuf && i < n; ++i) load(i);
+                FR_STAMP(i, 7);
+            }
+        }
+        return;
+    }
+    if (warp == kFrWarps + 1) {
+        if (lane == 0) {
             for (int64_t i = 0; i < n; ++i) {
                 const int buf = (int)(i % p.nbuf);
                 mbar_wait(&done[buf], (uint32_t)((i / p.nbuf) & 1));
                 bulk_s2g(p.xyz + (f0 + i) * p.frame_stride, smem + L.buf_off + (size_t)buf * L.buf_bytes, frame_bytes);
                 bulk_commit();
-                if (i >= 1 && i - 1 + p.nbuf < n) {
-                    bulk_wait_read<1>();  // store i-1 has finished reading its buffer
-                    load(i - 1 + p.nbuf);
-                }
+                FR_STAMP(i, 5);
+                bulk_wait_read<0>();          // the buffer has been read out ...
+                mbar_arrive(&drained[buf]);   // ... and may be refilled
+                FR_STAMP(i, 6);
             }
             bulk_wait<0>();
+            if (g_fr_trace) {  // per-CTA wall time (ns) after the per-frame stamps of CTA 0
+                unsigned long long t_end_ns;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns));
+                const long long base = (long long)(p.n_frames / gridDim.x + 2) * 8;
+                g_fr_trace[base + blockIdx.x * 2] = (long long)t_start_ns;
+                g_fr_trace[base + blockIdx.x * 2 + 1] = (long long)t_end_ns;
+            }
         }
         return;
     }
 
     // ================================================================== compute warps
+    if (warp >= n_cw) return;  // 16 is not a multiple of every G
     const int g = warp / wpf, sub = warp - g * wpf;
     const int gtid = sub * 32 + lane;  // thread index inside the group
     if (OP == OP_SUPERPOSE && p.idx)
-        for (int k = tid; k < p.n_sel; k += kFrWarps * 32) idx_s[k] = __ldg(p.idx + k);
+        for (int k = tid; k < p.n_sel; k += n_cw * 32) idx_s[k] = __ldg(p.idx + k);
     float oh[3] = {0, 0, 0}, ol[3] = {0, 0, 0};
     RefStats rs{};
     if (OP == OP_SUPERPOSE) {
@@ -137,12 +167,15 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
         for (int i = 0; i < 3; ++i) { oh[i] = (float)rs.mean[i]; ol[i] = (float)(rs.mean[i] - (double)oh[i]); }
         mbar_wait(ref_bar, 0);
     }
-    asm volatile("bar.sync 0, %0;" ::"r"(kFrWarps * 32) : "memory");  // idx_s visible to all compute warps
+    asm volatile("bar.sync 0, %0;" ::"r"(n_cw * 32) : "memory");  // idx_s visible to all compute warps
 
 #pragma unroll 1
     for (int64_t i = g; i < n; i += G) {
         const int buf = (int)(i % p.nbuf);
+        // nbuf is a multiple of G, so buffer `buf` is only ever used by this group and the group observes every phase
+        // of its barrier in order (a parity wait is ambiguous for a waiter that skips phases)
         mbar_wait(&full[buf], (uint32_t)((i / p.nbuf) & 1));
+        if (gtid == 0) FR_STAMP(i, 0);
         float* frame_s = reinterpret_cast<float*>(smem + L.buf_off + (size_t)buf * L.buf_bytes);
         float4* xs = reinterpret_cast<float4*>(frame_s);
         const int64_t f = f0 + i;
@@ -195,6 +228,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
             group_sync(g, wpf);
             // ---- solve: the group's first thread
             if (gtid == 0) {
+                FR_STAMP(i, 1);
                 double rec[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) rec[q] = 0.0;
@@ -214,7 +248,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
                 float R[9];
                 bool degen = false;
                 const double msd = qcp_solve(q, R, &degen);
-                if (p.out_rmsd) p.out_rmsd[f] = (float)sqrt(msd);
+                if (p.out_rmsd) p.out_rmsd[f] = sqrtf((float)msd);
                 if (p.out_rot) {
 #pragma unroll
                     for (int c = 0; c < 9; ++c) p.out_rot[f * 9 + c] = R[c];
@@ -230,6 +264,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
                     t[9 + c] = h; t[12 + c] = (float)(cen[c] - (double)h);
                     t[15 + c] = oh[c]; t[18 + c] = ol[c];
                 }
+                FR_STAMP(i, 2);
             }
             group_sync(g, wpf);
             // ---- phase 2: transform every atom of the frame in shared memory
@@ -300,56 +335,97 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
             if (gtid == 0 && p.traces) p.traces[f] = (float)tr;
         }
         // ---- publish the modified frame to the async proxy and hand the buffer to the DMA thread
+        if (gtid == 0) FR_STAMP(i, 3);
         fence_proxy_async_smem();
         group_sync(g, wpf);
-        if (gtid == 0) mbar_arrive(&done[buf]);
+        if (gtid == 0) { mbar_arrive(&done[buf]); FR_STAMP(i, 4); }
     }
 }
 
+static bool fr_fits(const FusedParams& p, int op, int nbuf)
+{
+    const int n_sel_pad = (p.n_sel + 3) & ~3;
+    return fr_layout(p.n_pad, nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0).total <= 232448;
+}
+
+// Geometry: G frame groups (wpf = 16/G warps each) and a ring of nbuf = G*m buffers.  nbuf must be a multiple of G so
+// that a buffer always belongs to one group (see the parity-wait note in the kernel).  Either every group has a second
+// buffer to prefetch into (m >= 2) or there are >= 3 groups so that, while one computes, the others' single buffers
+// are loading and storing (m == 1: the large-frame case, e.g. three 60 KB buffers at N = 5000).
 bool fused_config(FusedParams& p, int op)
 {
-    const size_t budget = 232448;
     const size_t frame_bytes = (size_t)p.n_pad * 12;
     if (frame_bytes >= (1u << 20)) return false;
-    const int n_sel_pad = (p.n_sel + 3) & ~3;
-    const FrLayout L1 = fr_layout(p.n_pad, 1, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0);
-    if (L1.total > budget) return false;
-    int nbuf_max = 1 + (int)((budget - L1.total - 64) / (frame_bytes + 16));
-    if (nbuf_max > 48) nbuf_max = 48;
-    if (nbuf_max < 2) return false;
-    // buffers in flight to/from HBM beyond the ones being computed on: >= 1 and >= ~48 KB worth
-    int lookahead = (int)((49152 + frame_bytes - 1) / frame_bytes);
-    if (lookahead < 1) lookahead = 1;
-    int G = op == OP_CENTER ? 4 : 16;  // centring has no serial solve to hide: fewer groups, deeper ring (measured)
-    while (G > 1 && G + lookahead > nbuf_max) G >>= 1;
-    if (G + 1 > nbuf_max || nbuf_max < 3) return false;  // a 2-deep ring cannot overlap load, compute and store
-    int nbuf = G + 2 * lookahead;
-    if (nbuf > nbuf_max) nbuf = nbuf_max;
-    while (nbuf > G + 1 &&
-           fr_layout(p.n_pad, nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0).total > budget)
-        --nbuf;
-    if (fr_layout(p.n_pad, nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0).total > budget) return false;
-    p.batch = G;
-    p.nbuf = nbuf;
+    int nbuf_max = 0;
+    while (nbuf_max < 48 && fr_fits(p, op, nbuf_max + 1)) ++nbuf_max;
+    if (nbuf_max < 3) return false;  // cannot overlap load, compute and store
+    static const int kGroups[] = {16, 8, 4, 3, 2, 1};
+    const int g_cap = op == OP_CENTER ? 4 : 8;  // centring has no serial solve to hide: fewer, wider groups (measured)
+    // first choice: m >= 2 with at least ~48 KB of prefetch in flight
+    for (int G : kGroups) {
+        if (G > g_cap || G < 2) continue;
+        int m = nbuf_max / G;
+        if (m < 2) continue;
+        if ((size_t)(m - 1) * G * frame_bytes < 49152) continue;
+        if (m > 4) m = 4;
+        p.batch = G;
+        p.nbuf = G * m;
+        return true;
+    }
+    // large frames: one buffer per group, >= 3 groups
+    for (int G : kGroups) {
+        if (G <= nbuf_max && G >= 3 && G <= g_cap + 1) {
+            p.batch = G;
+            p.nbuf = G;
+            return true;
+        }
+    }
+    // last resort: one group of 16 warps with a 3-deep ring (measured 0.64x of HBM peak at N = 5000)
+    p.batch = 1;
+    p.nbuf = 3;
     return true;
 }
 
 // development override: G concurrent frame groups and ring depth (validated against the shared-memory budget)
 bool fused_override(FusedParams& p, int op, int G, int nbuf)
 {
-    const int n_sel_pad = (p.n_sel + 3) & ~3;
     if (G <= 0) G = p.batch;
     if (nbuf <= 0) nbuf = p.nbuf;
-    if ((G & (G - 1)) != 0 || G > 16 || nbuf < G + 1) return false;
-    if (fr_layout(p.n_pad, nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0).total > 232448) return false;
+    if (G > 16 || nbuf < G || nbuf % G != 0 || nbuf < 2) return false;
+    if (!fr_fits(p, op, nbuf)) return false;
     p.batch = G;
     p.nbuf = nbuf;
     return true;
 }
 
+long long* fr_trace_buffer(size_t n_frames_cta)
+{
+    static long long* buf = nullptr;
+    static size_t cap = 0;
+    if (!getenv("B200RMSD_FUSED_TRACE")) return nullptr;
+    if (cap < n_frames_cta * 8) {
+        if (buf) cudaFree(buf);
+        cudaMalloc((void**)&buf, n_frames_cta * 8 * sizeof(long long));
+        cap = n_frames_cta * 8;
+    }
+    cudaMemset(buf, 0, cap * sizeof(long long));
+    cudaMemcpyToSymbol(g_fr_trace, &buf, sizeof(buf));
+    return buf;
+}
+
+extern "C" int b200rmsd_debug_fused_trace(long long* host_out, size_t n)
+{
+    long long* buf = nullptr;
+    cudaMemcpyFromSymbol(&buf, g_fr_trace, sizeof(buf));
+    if (!buf) return -1;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(host_out, buf, n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+
 cudaError_t launch_frame_resident(const FusedParams& p, int op, int sm_count, cudaStream_t st)
 {
     if (p.n_frames <= 0) return cudaSuccess;
+    fr_trace_buffer((size_t)(p.n_frames / (sm_count > 0 ? sm_count : 1) + 2) + 64);
     const int n_sel_pad = (p.n_sel + 3) & ~3;
     const FrLayout L = fr_layout(p.n_pad, p.nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0);
     auto kern = op == OP_SUPERPOSE ? frame_resident_kernel<OP_SUPERPOSE> : frame_resident_kernel<OP_CENTER>;

@@ -68,7 +68,7 @@ __device__ __forceinline__ void finish_frame(const double rec[16], int64_t f, co
     float R[9];
     bool degen = false;
     const double msd = qcp_solve(q, p.out_rot ? R : nullptr, &degen);
-    p.out_rmsd[f] = (float)sqrt(msd);
+    p.out_rmsd[f] = sqrtf((float)msd);
     if (p.out_rot) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) p.out_rot[f * 9 + i] = R[i];

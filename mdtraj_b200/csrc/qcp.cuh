@@ -27,19 +27,20 @@ struct QcpInput {
 // reference's own starting value, theobald_rmsd.cpp:245; the second follows from sum(lambda_i) = 0 and
 // lambda_max = s1 + s2 +- s3 <= sqrt(3)*||M||_F for the singular values s of M), and lambda_max >= s1 >=
 // ||M||_F/sqrt(3), so the start is never more than 3x above the root -- for dissimilar (e.g. iid random)
-// frames (G_a+G_b)/2 alone can be 10-30x above it and Newton would crawl down by 3/4 per step.  Newton from the right of the largest root of a real-rooted
-// polynomial is monotone, so the iteration cannot leave the basin.
-// The polynomial is normalised by lam0 (t = lambda/lam0 in (0,1]); the first iterations run in float32
-// (4-cycle FMA + MUFU reciprocal) and the last ones in float64 to full precision.
+// frames (G_a+G_b)/2 alone can be 10-30x above it and Newton would crawl down by 3/4 per step.  Newton from the
+// right of the largest root of a real-rooted polynomial is monotone, so the iteration cannot leave the basin.
+// The polynomial is scaled by an exact power of two (t = lambda * 2^-e in [1,2) at the start: no division, no
+// rounding); the first iterations run in float32 (4-cycle FMA + MUFU reciprocal), the last ones in float64 with
+// a float32-seeded, once-refined reciprocal instead of a DDIV chain.
 __device__ __forceinline__ double qcp_newton(double C2, double C1, double C0, double lam_upper, double frob2)
 {
-    double lam0 = sqrt(3.0 * frob2);
-    if (!(lam0 < lam_upper)) lam0 = lam_upper;
-    if (!(lam0 > 0.0)) return 0.0;
-    const double inv = 1.0 / lam0, inv2 = inv * inv;
-    const double c2 = C2 * inv2, c1 = C1 * inv2 * inv, c0 = C0 * inv2 * inv2;
-    // float32 phase
-    float t = 1.0f;
+    float ub = fminf(sqrtf(3.0f * (float)frob2) * 1.000001f, (float)lam_upper * 1.000001f);
+    if (!(ub > 1e-30f)) return 0.0;
+    const int e = ((__float_as_int(ub) >> 23) & 0xff) - 127;
+    const double s1 = __longlong_as_double((long long)(1023 - e) << 52);
+    const double s2 = s1 * s1;
+    const double c2 = C2 * s2, c1 = C1 * s2 * s1, c0 = C0 * s2 * s2;
+    float t = ub * (float)s1;
     {
         const float f2 = (float)c2, f1 = (float)c1, f0 = (float)c0;
 #pragma unroll 1
@@ -51,24 +52,27 @@ __device__ __forceinline__ double qcp_newton(double C2, double C1, double C0, do
             if (!(fabsf(den) > 1e-30f)) break;
             const float delta = __fdividef(fmaf(a, t, f0), den);
             t -= delta;
-            if (!(fabsf(delta) > 2e-6f * fabsf(t))) break;
+            if (!(fabsf(delta) > 4e-6f * fabsf(t))) break;
         }
-        if (!(t > 0.0f) || !(t <= 1.0f)) t = 1.0f;  // numerical accident: restart the float64 phase from the bound
+        if (!(t > 0.0f) || !(t <= 2.0f)) t = ub * (float)s1;  // numerical accident: restart the float64 phase from the bound
     }
-    // float64 polish (quadratic convergence from ~1e-6)
     double x = (double)t;
 #pragma unroll 1
-    for (int it = 0; it < 48; ++it) {
+    for (int it = 0; it < 40; ++it) {
         const double x2 = x * x;
         const double b = (x2 + c2) * x;
         const double a = b + c1;
         const double den = 2.0 * x2 * x + b + a;
-        if (den == 0.0) break;
-        const double delta = (a * x + c0) / den;
+        if (!(fabs(den) > 1e-300)) break;
+        double r = (double)__frcp_rn((float)den);
+        r = r * (2.0 - den * r);
+        r = r * (2.0 - den * r);
+        const double delta = (a * x + c0) * r;
+        if (!(delta == delta)) break;
         x -= delta;
-        if (fabs(delta) <= 1e-15 * fabs(x)) break;
+        if (fabs(delta) <= 1e-10 * fabs(x)) break;  // quadratic: the step just taken leaves an error ~delta^2
     }
-    return x * lam0;
+    return x * __longlong_as_double((long long)(1023 + e) << 52);
 }
 
 // Returns the clamped msd.  If rot != nullptr also writes the row-major rotation
@@ -121,7 +125,9 @@ __device__ __forceinline__ double qcp_solve(const QcpInput& in, float* rot, bool
             rot[0] = rot[4] = rot[8] = 1.0f;
             rot[1] = rot[2] = rot[3] = rot[5] = rot[6] = rot[7] = 0.0f;
         } else {
-            const double inv = rsqrt(n2);
+            double inv = (double)rsqrtf((float)n2);          // float32 seed, two Newton refinements in float64
+            inv = inv * (1.5 - 0.5 * n2 * inv * inv);
+            inv = inv * (1.5 - 0.5 * n2 * inv * inv);
             qa *= inv; qx *= inv; qy *= inv; qz *= inv;
             const double aa = qa * qa, xx = qx * qx, yy = qy * qy, zz = qz * qz;
             const double xy = qx * qy, az = qa * qz, zx = qz * qx, ay = qa * qy, yz = qy * qz, ax = qa * qx;

@@ -19,6 +19,7 @@ def time_fn(fn, reps):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    print("  [ok warm-up]", getattr(fn, "__name__", "?"), file=sys.stderr, flush=True)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     for a, b in evs:
         a.record(); fn(); b.record()
