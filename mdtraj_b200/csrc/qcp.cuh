@@ -64,10 +64,9 @@ __device__ __forceinline__ double qcp_newton(double C2, double C1, double C0, do
         const double a = b + c1;
         const double den = 2.0 * x2 * x + b + a;
         if (!(fabs(den) > 1e-300)) break;
-        double r = (double)__frcp_rn((float)den);
-        r = r * (2.0 - den * r);
-        r = r * (2.0 - den * r);
-        const double delta = (a * x + c0) * r;
+        // a float32 reciprocal is enough: a 1e-7 relative error in the step only perturbs the quadratically
+        // converging iterate by 1e-7 * |delta|
+        const double delta = (a * x + c0) * (double)__frcp_rn((float)den);
         if (!(delta == delta)) break;
         x -= delta;
         if (fabs(delta) <= 1e-10 * fabs(x)) break;  // quadratic: the step just taken leaves an error ~delta^2
