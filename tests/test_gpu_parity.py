@@ -442,3 +442,43 @@ def test_rmsf_residue_mode(mdb, oracle_mod):
         assert abs(per_res[r] - want) < 1e-6
     sub = mdb.rmsf(t, t, 0, atom_indices=[0, 1, 2, 3], mode="residue")
     assert sub[0] > 0 and np.all(sub[1:] == -1.0)
+
+
+# ------------------------------------------------------------------ frame-resident kernels at scale
+@pytest.mark.parametrize("F,N,stride", [(6000, 1000, 4), (1500, 5000, 5), (20000, 300, 1), (40000, 22, 1), (700, 8000, 7)])
+def test_superpose_and_center_properties_at_scale(mdb, F, N, stride):
+    """Every ring geometry of frame_resident_kernel (8 groups x 2 buffers, 3 single-buffer groups for 60 KB frames,
+    small frames, the two-pass fallback for frames that do not fit) and many frames per CTA, checked through
+    size-independent properties: superpose-then-plain-RMSD == QCP RMSD (tests/test_rmsd.py:98-108), a second superpose
+    is the identity, centring leaves zero means and traces == sum |x|^2, repeated launches are bit-identical."""
+    import torch
+    dt = mdb.DeviceTrajectory.synthetic_iid(F, N, seed=11)
+    # MD-like: one base structure + 0.1 nm noise + a per-frame offset (well-conditioned rotations, SURVEY.md section 8(d))
+    g = torch.Generator(device=dt.device); g.manual_seed(5)
+    base = torch.randn((N, 3), generator=g, device=dt.device)
+    dt.xyz_dev[:, :N] = base[None] + 0.1 * dt.xyz_dev[:, :N] + (torch.rand((F, 1, 3), generator=g, device=dt.device) * 6 - 3)
+    idx = None if stride == 1 else np.arange(0, N, stride)
+    ref = mdb.DeviceTrajectory(dt.xyz_dev[:1].clone(), N)
+    qcp = mdb.rmsd_device(dt, ref, 0, atom_indices=idx, as_numpy=False)
+    a = mdb.DeviceTrajectory(dt.xyz_dev.clone(), N)
+    b = mdb.DeviceTrajectory(dt.xyz_dev.clone(), N)
+    a.superpose(ref, 0, atom_indices=idx)
+    b.superpose(ref, 0, atom_indices=idx)
+    assert torch.equal(a.xyz_dev, b.xyz_dev)
+    assert torch.equal(a.xyz_dev[:, N:], torch.zeros_like(a.xyz_dev[:, N:]))  # padding atoms stay zero
+    # frame 0 IS the reference (true RMSD 0, where float32 sums leave ~1e-4 nm of sqrt-amplified noise): skip it
+    assert (a.last_superpose_rmsd - qcp)[1:].abs().max().item() < 1e-5
+    plain = mdb.rmsd_device(a, ref, 0, atom_indices=idx, superpose=False, as_numpy=False)
+    assert (plain - qcp)[1:].abs().max().item() < 2e-5
+    before = a.xyz_dev.clone()
+    a.superpose(ref, 0, atom_indices=idx)
+    assert (a.xyz_dev - before).abs().max().item() < 2e-5
+    # centring
+    c = mdb.DeviceTrajectory(dt.xyz_dev.clone(), N)
+    c.center_coordinates()
+    x = c.xyz_dev[:, :N].double()
+    assert x.mean(1).abs().max().item() < 2e-6
+    assert ((x * x).sum((1, 2)) - c._rmsd_traces.double()).abs().max().item() <= 2e-6 * float((x * x).sum((1, 2)).max())
+    pre = mdb.rmsd_device(c, c, 0, precentered=True, as_numpy=False)
+    fly = mdb.rmsd_device(dt, dt, 0, as_numpy=False)
+    assert (pre - fly)[1:].abs().max().item() < 1e-5
