@@ -277,12 +277,17 @@ def main():
         out = torch.empty((r1 - r0, F), dtype=torch.float32, device=dev)
         launches_per_step = 2
 
+        from mdtraj_b200 import distributed as DD
+
         def step(record=False):
-            prep = AP.prepare(dt, None)
             if record:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            AP.rows(prep, r0, r1, out=out)
+            if world == 1:
+                prep = AP.prepare(dt, None)
+                AP.rows(prep, r0, r1, out=out)
+            else:  # frames broadcast from rank 0 over NCCL, symmetric block plan, transposed blocks exchanged
+                DD.rmsd_matrix_sharded(dt, None, broadcast=True, symmetric=True)
             if record:
                 e1.record()
                 kernel_events.append((e0, e1))
@@ -386,7 +391,7 @@ def main():
         # flops actually issued: 128x128 tiles (40x40 frames), three tf32 MMAs per K-step, K padded to 32; a
         # single-rank full matrix computes the upper triangle of tiles only and mirrors it
         T = -(-F // 40)
-        tiles = T * (T + 1) // 2 if world == 1 else -(-(r1 - r0) // 40) * T
+        tiles = T * (T + 1) // 2 if world == 1 else T * (T + 1) // 2 / world  # symmetric plan: ~T^2/2 tiles over all ranks
         issued = tiles * 128 * 128 * kpad * 2 * 3 / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": dominant, "achieved": issued, "peak": tpeak, "unit": "TFLOP/s",
                     "frac": issued / tpeak, "traffic": None, "peak_source": tsrc, "kernel_ms": kern_ms,

@@ -165,6 +165,16 @@ int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atom
 int b200rmsd_allpairs_rows_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,
                                int64_t row0, int64_t row1, float* out, int64_t ld, unsigned flags, void* stream);
 
+/* One rectangular block of the matrix: rows [row0,row1) x columns [col0,col1), written at
+ * out[(i-row0)*ld + j] (absolute column index j, ld >= col1).  When out_t != NULL the transposed block is also
+ * written, out_t[(j-col0)*ld_t + (i-row0)]: D is symmetric, so a rank that computes block (r,s) can ship out_t to
+ * the owner of row block s instead of that rank recomputing it (mdtraj_b200.distributed.rmsd_matrix_sharded).
+ * A square block on the diagonal (row range == column range, out_t == NULL) computes each unordered pair once and
+ * mirrors it.  b200rmsd_allpairs_rows_dev(row0,row1) == block(row0,row1,0,n_frames). */
+int b200rmsd_allpairs_block_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,
+                                int64_t row0, int64_t row1, int64_t col0, int64_t col1, float* out, int64_t ld,
+                                float* out_t, int64_t ld_t, unsigned flags, void* stream);
+
 /* ------------------------------------------------------------------ host API */
 
 /* md.rmsd on host arrays.  target: (n_frames, n_atoms_target, 3) float32 C-contiguous

@@ -76,6 +76,29 @@ def rows(prep: PreparedAllPairs, row0: int, row1: int, out=None, diag_zero=True,
     return out
 
 
+def block(prep: PreparedAllPairs, row0, row1, col0, col1, out, out_t=None, diag_zero=True, precise=True):
+    """Rows [row0,row1) x columns [col0,col1) into ``out`` (a (row1-row0, >=col1) CUDA tensor, absolute column index);
+    ``out_t`` (col1-col0, row1-row0), when given, also receives the transposed block (for shipping to the rank that
+    owns rows [col0,col1), see distributed.rmsd_matrix_sharded)."""
+    torch = _torch()
+    dev = prep.device
+    assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape[0] == row1 - row0
+    assert out.shape[1] >= col1
+    if out_t is not None:
+        assert out_t.is_cuda and out_t.dtype == torch.float32 and out_t.stride(1) == 1
+        assert out_t.shape == (col1 - col0, row1 - row0)
+    L = _capi.lib()
+    with torch.cuda.device(dev):
+        rc = L.b200rmsd_allpairs_block_dev(prep.workspace.data_ptr(), prep.workspace.numel(), prep.n_frames, prep.n_sel,
+                                           row0, row1, col0, col1, out.data_ptr(), out.stride(0),
+                                           None if out_t is None else out_t.data_ptr(),
+                                           0 if out_t is None else out_t.stride(0),
+                                           (DIAG_ZERO if diag_zero else 0) | (0 if precise else FAST_SOLVE),
+                                           _stream_ptr(torch, dev))
+    _capi.check(rc, "b200rmsd_allpairs_block_dev")
+    return out
+
+
 def rmsd_matrix_device(traj: DeviceTrajectory, atom_indices=None, row_block=None, diag_zero=True, precise=True):
     """Full (or ``row_block=(r0, r1)``) matrix as a CUDA tensor; nothing is copied to the host."""
     prep = prepare(traj, atom_indices)

@@ -66,13 +66,14 @@ constexpr int kTile = 32, kKc = 32, kRow = kKc + 4;
 
 __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restrict__ X, const float* __restrict__ traces,
                                                             int64_t n_frames, int n_sel, int k_pad, int64_t row0,
-                                                            int64_t row1, float* __restrict__ out, int64_t ld,
-                                                            unsigned flags)
+                                                            int64_t row1, int64_t col0, int64_t col1,
+                                                            float* __restrict__ out, int64_t ld, float* __restrict__ out_t,
+                                                            int64_t ld_t, unsigned flags)
 {
     __shared__ __align__(16) float As[kTile * 3 * kRow];
     __shared__ __align__(16) float Bs[kTile * 3 * kRow];
     const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
-    const int64_t i0 = row0 + (int64_t)blockIdx.y * kTile, j0 = (int64_t)blockIdx.x * kTile;
+    const int64_t i0 = row0 + (int64_t)blockIdx.y * kTile, j0 = col0 + (int64_t)blockIdx.x * kTile;
 
     float acc[2][2][9];
 #pragma unroll
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restr
             float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
             const int64_t fi = i0 + fl, fj = j0 + fl;
             if (fi < row1) va = *reinterpret_cast<const float4*>(X + ((size_t)fi * 3 + comp) * k_pad + k0 + c4 * 4);
-            if (fj < n_frames) vb = *reinterpret_cast<const float4*>(X + ((size_t)fj * 3 + comp) * k_pad + k0 + c4 * 4);
+            if (fj < col1) vb = *reinterpret_cast<const float4*>(X + ((size_t)fj * 3 + comp) * k_pad + k0 + c4 * 4);
             *reinterpret_cast<float4*>(&As[row * kRow + c4 * 4]) = va;
             *reinterpret_cast<float4*>(&Bs[row * kRow + c4 * 4]) = vb;
         }
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restr
 #pragma unroll
         for (int sj = 0; sj < 2; ++sj) {
             const int64_t i = i0 + ti + 16 * si, j = j0 + tj + 16 * sj;
-            if (i >= row1 || j >= n_frames) continue;
+            if (i >= row1 || j >= col1) continue;
             float r;
             if (i == j && (flags & 1u)) {
                 r = 0.f;  // a frame against itself in the same memory: theobald_rmsd_sse.h:256-262
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restr
                 r = sqrtf((float)qcp_solve(q, nullptr, nullptr));
             }
             out[(size_t)(i - row0) * ld + j] = r;
+            if (out_t) out_t[(size_t)(j - col0) * ld_t + (i - row0)] = r;
         }
 }
 
@@ -198,26 +200,36 @@ int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atom
     return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "allpairs_prepare: %s", cudaGetErrorString(e));
 }
 
+int b200rmsd_allpairs_block_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,
+                                int64_t row0, int64_t row1, int64_t col0, int64_t col1, float* out, int64_t ld,
+                                float* out_t, int64_t ld_t, unsigned flags, void* stream)
+{
+    if (!workspace || !out || n_frames <= 0 || n_sel <= 0 || row0 < 0 || row1 > n_frames || row0 > row1 || col0 < 0 ||
+        col1 > n_frames || col0 > col1 || ld < col1 || (out_t && ld_t < row1 - row0))
+        return fail(B200RMSD_EINVAL, "allpairs_block: bad arguments");
+    const ApGeometry g = ap_geometry(n_frames, n_sel);
+    if (workspace_bytes < g.total) return fail(B200RMSD_EINVAL, "allpairs_block: workspace too small");
+    if (row0 == row1 || col0 == col1) return 0;
+    const char* base = (const char*)workspace;
+    if (g.tc)
+        return launch_allpairs_tc_block((const float*)(base + g.hi_off), (const float*)(base + g.lo_off),
+                                        (const float*)(base + g.traces_off), n_frames, n_sel, g.k_pad, g.rows_pad, row0,
+                                        row1, col0, col1, out, ld, out_t, ld_t, flags, ap_sm_count(), (cudaStream_t)stream);
+    dim3 grid((unsigned)((col1 - col0 + kTile - 1) / kTile), (unsigned)((row1 - row0 + kTile - 1) / kTile));
+    if (grid.y > 65535) return fail(B200RMSD_EINVAL, "allpairs_block: at most 65535*32 rows per call");
+    allpairs_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)(base + g.x_off),
+                                                                 (const float*)(base + g.traces_off), n_frames, n_sel,
+                                                                 g.k_pad, row0, row1, col0, col1, out, ld, out_t, ld_t, flags);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "allpairs_block: %s", cudaGetErrorString(e));
+}
+
 int b200rmsd_allpairs_rows_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,
                                int64_t row0, int64_t row1, float* out, int64_t ld, unsigned flags, void* stream)
 {
-    if (!workspace || !out || n_frames <= 0 || n_sel <= 0 || row0 < 0 || row1 > n_frames || row0 > row1 || ld < n_frames)
-        return fail(B200RMSD_EINVAL, "allpairs_rows: bad arguments");
-    const ApGeometry g = ap_geometry(n_frames, n_sel);
-    if (workspace_bytes < g.total) return fail(B200RMSD_EINVAL, "allpairs_rows: workspace too small");
-    if (row0 == row1) return 0;
-    const char* base = (const char*)workspace;
-    if (g.tc)
-        return launch_allpairs_tc_rows((const float*)(base + g.hi_off), (const float*)(base + g.lo_off),
-                                       (const float*)(base + g.traces_off), n_frames, n_sel, g.k_pad, g.rows_pad, row0,
-                                       row1, out, ld, flags, ap_sm_count(), (cudaStream_t)stream);
-    dim3 grid((unsigned)((n_frames + kTile - 1) / kTile), (unsigned)((row1 - row0 + kTile - 1) / kTile));
-    if (grid.y > 65535) return fail(B200RMSD_EINVAL, "allpairs_rows: at most 65535*32 rows per call");
-    allpairs_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)(base + g.x_off),
-                                                                 (const float*)(base + g.traces_off), n_frames, n_sel,
-                                                                 g.k_pad, row0, row1, out, ld, flags);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "allpairs_rows: %s", cudaGetErrorString(e));
+    if (ld < n_frames) return fail(B200RMSD_EINVAL, "allpairs_rows: ld < n_frames");
+    return b200rmsd_allpairs_block_dev(workspace, workspace_bytes, n_frames, n_sel, row0, row1, 0, n_frames, out, ld,
+                                       nullptr, 0, flags, stream);
 }
 
 }  // extern "C"

@@ -53,8 +53,8 @@ inline ApGeometry ap_geometry(int64_t n_frames, int n_sel)
 cudaError_t launch_allpairs_tc_prepare(const float* xyz, int64_t n_frames, int64_t frame_stride, const int* idx, int n_sel,
                                        int k_pad, float* hi, float* lo, float* traces, int64_t rows_pad, int sm_count,
                                        cudaStream_t st);
-int launch_allpairs_tc_rows(const float* hi, const float* lo, const float* traces, int64_t n_frames, int n_sel, int k_pad,
-                            int64_t rows_pad, int64_t row0, int64_t row1, float* out, int64_t ld, unsigned flags,
-                            int sm_count, cudaStream_t st);
+int launch_allpairs_tc_block(const float* hi, const float* lo, const float* traces, int64_t n_frames, int n_sel, int k_pad,
+                             int64_t rows_pad, int64_t row0, int64_t row1, int64_t col0, int64_t col1, float* out,
+                             int64_t ld, float* out_t, int64_t ld_t, unsigned flags, int sm_count, cudaStream_t st);
 
 }  // namespace b200

@@ -157,6 +157,10 @@ struct TcParams {
     int64_t ld;
     int64_t n_frames;
     int64_t row0, row1;      // output rows [row0, row1)
+    int64_t col0, col1;      // output columns [col0, col1)
+    float* out_t;            // optional transposed copy of the block: out_t[(j-col0)*ld_t + (i-row0)]
+    int64_t ld_t;
+    int tiles_j0;            // first j-tile (= col0 / 40)
     int n_sel;
     int nk;                  // K blocks of 32
     int tiles_i0;            // first i-tile (= row0 / 40)
@@ -183,9 +187,10 @@ __device__ __forceinline__ bool tile_coords(int64_t t, const TcParams& p, int& t
         while (bi > 0 && (int64_t)bi * p.n_super - (int64_t)bi * (bi - 1) / 2 > blk) --bi;
         while ((int64_t)(bi + 1) * p.n_super - (int64_t)(bi + 1) * bi / 2 <= blk) ++bi;
         const int bj = bi + (int)(blk - ((int64_t)bi * p.n_super - (int64_t)bi * (bi - 1) / 2));
-        ti = bi * kSuper + in / kSuper;
-        tj = bj * kSuper + in % kSuper;
-        return ti < p.tiles_i && tj < p.tiles_j && tj >= ti;
+        const int li = bi * kSuper + in / kSuper, lj = bj * kSuper + in % kSuper;  // tile offsets inside the square block
+        ti = p.tiles_i0 + li;
+        tj = p.tiles_i0 + lj;
+        return li < p.tiles_i && lj < p.tiles_i && lj >= li;
     }
     const int bj_count = (p.tiles_j + kSuper - 1) / kSuper;
     const int64_t full_row = (int64_t)kSuper * p.tiles_j;          // tiles in one full block row
@@ -198,7 +203,7 @@ __device__ __forceinline__ bool tile_coords(int64_t t, const TcParams& p, int& t
     r -= (int64_t)bj * per_block;
     const int cols_here = min(kSuper, p.tiles_j - bj * kSuper);
     ti = p.tiles_i0 + bi * kSuper + (int)(r / cols_here);
-    tj = bj * kSuper + (int)(r % cols_here);
+    tj = p.tiles_j0 + bj * kSuper + (int)(r % cols_here);
     return true;
 }
 
@@ -340,7 +345,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                         }
                         const int jl = 3 * jg + c;  // j-frame slot inside the chunk
                         fj[u] = (int64_t)tj * kFramesPerTile + chunk * 10 + jl;
-                        ok[u] = i_ok && jl < 10 && fj[u] < p.n_frames;
+                        ok[u] = i_ok && jl < 10 && fj[u] >= p.col0 && fj[u] < p.col1;
                         Ga[u] = ok[u] ? __ldg(p.traces + fj[u]) : 1.0f;
                         Gb[u] = Gi;
                     }
@@ -358,9 +363,10 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                             const float v = (fi == fj[u] && (p.flags & B200RMSD_DIAG_ZERO)) ? 0.f : res[u];
                             if (!p.symmetric) {
                                 p.out[(size_t)(fi - p.row0) * p.ld + fj[u]] = v;
+                                if (p.out_t) p.out_t[(size_t)(fj[u] - p.col0) * p.ld_t + (fi - p.row0)] = v;
                             } else if (fj[u] >= fi) {  // each unordered pair once, mirrored: D is exactly symmetric
-                                p.out[(size_t)fi * p.ld + fj[u]] = v;
-                                if (fj[u] != fi) p.out[(size_t)fj[u] * p.ld + fi] = v;
+                                p.out[(size_t)(fi - p.row0) * p.ld + fj[u]] = v;
+                                if (fj[u] != fi) p.out[(size_t)(fj[u] - p.row0) * p.ld + fi] = v;
                             }
                         }
                 }
@@ -428,9 +434,9 @@ cudaError_t launch_allpairs_tc_prepare(const float* xyz, int64_t n_frames, int64
     return cudaGetLastError();
 }
 
-int launch_allpairs_tc_rows(const float* hi, const float* lo, const float* traces, int64_t n_frames, int n_sel, int k_pad,
-                            int64_t rows_pad, int64_t row0, int64_t row1, float* out, int64_t ld, unsigned flags,
-                            int sm_count, cudaStream_t st)
+int launch_allpairs_tc_block(const float* hi, const float* lo, const float* traces, int64_t n_frames, int n_sel, int k_pad,
+                             int64_t rows_pad, int64_t row0, int64_t row1, int64_t col0, int64_t col1, float* out,
+                             int64_t ld, float* out_t, int64_t ld_t, unsigned flags, int sm_count, cudaStream_t st)
 {
     CUtensorMap map_hi, map_lo;
     if (!make_operand_map(&map_hi, hi, rows_pad, k_pad) || !make_operand_map(&map_lo, lo, rows_pad, k_pad))
@@ -442,19 +448,26 @@ int launch_allpairs_tc_rows(const float* hi, const float* lo, const float* trace
     p.n_frames = n_frames;
     p.row0 = row0;
     p.row1 = row1;
+    p.col0 = col0;
+    p.col1 = col1;
+    p.out_t = out_t;
+    p.ld_t = ld_t;
     p.n_sel = n_sel;
     p.nk = k_pad / kBK;
     p.tiles_i0 = (int)(row0 / kFramesPerTile);
     p.tiles_i = (int)((row1 + kFramesPerTile - 1) / kFramesPerTile) - p.tiles_i0;
-    p.tiles_j = (int)((n_frames + kFramesPerTile - 1) / kFramesPerTile);
+    p.tiles_j0 = (int)(col0 / kFramesPerTile);
+    p.tiles_j = (int)((col1 + kFramesPerTile - 1) / kFramesPerTile) - p.tiles_j0;
     p.flags = flags;
-    p.symmetric = (row0 == 0 && row1 == n_frames && !getenv("B200RMSD_NO_SYMMETRIC")) ? 1 : 0;
-    p.n_super = (p.tiles_j + kSuper - 1) / kSuper;
+    // a square block on the diagonal: compute tiles tj >= ti only and mirror them (exactly symmetric, half the flops)
+    p.symmetric = (row0 == col0 && row1 == col1 && !out_t && !getenv("B200RMSD_NO_SYMMETRIC")) ? 1 : 0;
+    p.n_super = (p.tiles_i + kSuper - 1) / kSuper;
     if (const char* dbg = getenv("B200RMSD_TC_DEBUG")) p.flags |= (unsigned)strtoul(dbg, nullptr, 0) & 0xff02u;
     const size_t smem = (size_t)kStages * kStageBytes + 1024 + 256;
     int64_t ctas = sm_count;
-    const int64_t n_tiles = p.symmetric ? ((int64_t)p.tiles_j * (p.tiles_j + 1)) / 2 : (int64_t)p.tiles_i * p.tiles_j;
+    const int64_t n_tiles = p.symmetric ? ((int64_t)p.tiles_i * (p.tiles_i + 1)) / 2 : (int64_t)p.tiles_i * p.tiles_j;
     if (ctas > n_tiles) ctas = n_tiles;
+    if (ctas < 1) ctas = 1;
     const char* cfg = getenv("B200RMSD_TC_EPILOGUE");  // development: "<warps>x<np>", e.g. 16x1
     int ew = 16, np = 2;  // measured best on B200 (16x2 > 16x1 > 8x2 > 8x1)
     if (cfg) sscanf(cfg, "%dx%d", &ew, &np);

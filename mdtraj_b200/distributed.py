@@ -86,15 +86,82 @@ def broadcast_frames(xyz_dev, src=0, group=None):
     return xyz_dev
 
 
-def rmsd_matrix_sharded(traj_dev, atom_indices=None, group=None, broadcast=True, diag_zero=True):
+def symmetric_plan(n_frames: int, world: int):
+    """Work split of the symmetric all-pairs matrix over ``world`` ranks that own contiguous row blocks.
+
+    D[i][j] == D[j][i], so each off-diagonal block pair {(r,s),(s,r)} is computed once and its transpose shipped.
+    Returns ``plan[rank] = {"compute": [(r0,r1,c0,c1,send_to)], "recv": [(src, r0,r1,c0,c1)]}`` in absolute frame
+    indices; ``send_to`` is None for blocks that stay local.  Rank r computes its diagonal block, the blocks (r,s)
+    with 0 < (s-r) mod W < W/2, and -- for even W -- half of the antipodal block (r, r+W/2), so the work is balanced.
+    Every entry of every rank's row block is produced exactly once (tests/test_host_logic.py checks this).
+    """
+    bounds = all_shard_bounds(n_frames, world)
+    plan = [{"compute": [], "recv": []} for _ in range(world)]
+    for r in range(world):
+        r0, r1 = bounds[r]
+        if r1 > r0:
+            plan[r]["compute"].append((r0, r1, r0, r1, None))
+        for s in range(world):
+            if s == r:
+                continue
+            s0, s1 = bounds[s]
+            if s1 == s0 or r1 == r0:
+                continue
+            d = (s - r) % world
+            if 2 * d < world:                      # r computes the whole block (r,s) and ships its transpose to s
+                plan[r]["compute"].append((r0, r1, s0, s1, s))
+                plan[s]["recv"].append((r, s0, s1, r0, r1))
+            elif 2 * d == world and r < s:         # antipodal pair: split the rows of the lower rank in two halves
+                h = r0 + (r1 - r0) // 2
+                if h > r0:                         # r computes rows [r0,h) x cols of s, ships the transpose to s
+                    plan[r]["compute"].append((r0, h, s0, s1, s))
+                    plan[s]["recv"].append((r, s0, s1, r0, h))
+                if r1 > h:                         # s computes its rows x cols [h,r1) of r, ships the transpose to r
+                    plan[s]["compute"].append((s0, s1, h, r1, r))
+                    plan[r]["recv"].append((s, h, r1, s0, s1))
+    return plan
+
+
+def rmsd_matrix_sharded(traj_dev, atom_indices=None, group=None, broadcast=True, diag_zero=True, precise=True,
+                        symmetric=True):
     """Row-block sharded all-pairs matrix.  ``traj_dev``: a DeviceTrajectory with identical shape on every rank
-    (rank 0's coordinates are broadcast unless ``broadcast=False``).  Returns ``(row0, row1, block)`` where
-    ``block`` is this rank's ``(row1-row0, F)`` CUDA tensor; the matrix is never gathered."""
+    (rank 0's coordinates are broadcast over NCCL unless ``broadcast=False``).  Returns ``(row0, row1, block)`` where
+    ``block`` is this rank's ``(row1-row0, F)`` CUDA tensor; the matrix is never gathered.
+
+    ``symmetric=True`` (default): every unordered pair of frames is computed once (``symmetric_plan``); the ranks
+    exchange transposed blocks with NCCL send/recv over NVLink -- half the tensor work for F^2/(2W) floats of traffic
+    per rank.  ``symmetric=False``: every rank computes its whole row block, no exchange.
+    """
+    import torch
     from . import allpairs
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if broadcast and world > 1:
         broadcast_frames(traj_dev.xyz_dev, 0, group)
     prep = allpairs.prepare(traj_dev, atom_indices)
-    r0, r1 = shard_bounds(traj_dev.n_frames, rank, world)
-    return r0, r1, allpairs.rows(prep, r0, r1, diag_zero=diag_zero)
+    F = traj_dev.n_frames
+    r0, r1 = shard_bounds(F, rank, world)
+    if not symmetric or world == 1:
+        return r0, r1, allpairs.rows(prep, r0, r1, diag_zero=diag_zero, precise=precise)
+    dev = traj_dev.device
+    out = torch.empty((r1 - r0, F), dtype=torch.float32, device=dev)
+    plan = symmetric_plan(F, world)[rank]
+    sends = []
+    for (a0, a1, c0, c1, dst) in plan["compute"]:
+        rows_view = out[a0 - r0: a1 - r0]
+        if dst is None:
+            allpairs.block(prep, a0, a1, c0, c1, rows_view, None, diag_zero, precise)
+        else:
+            t = torch.empty((c1 - c0, a1 - a0), dtype=torch.float32, device=dev)
+            allpairs.block(prep, a0, a1, c0, c1, rows_view, t, diag_zero, precise)
+            sends.append((dst, t))
+    recvs = [(src, a0, a1, c0, c1, torch.empty((a1 - a0, c1 - c0), dtype=torch.float32, device=dev))
+             for (src, a0, a1, c0, c1) in plan["recv"]]
+    ops = [dist.P2POp(dist.isend, t, dst, group) for dst, t in sends] + \
+          [dist.P2POp(dist.irecv, buf, src, group) for (src, _, _, _, _, buf) in recvs]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for (_, a0, a1, c0, c1, buf) in recvs:
+        out[a0 - r0: a1 - r0, c0:c1] = buf
+    return r0, r1, out

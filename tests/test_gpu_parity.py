@@ -482,3 +482,28 @@ def test_superpose_and_center_properties_at_scale(mdb, F, N, stride):
     pre = mdb.rmsd_device(c, c, 0, precentered=True, as_numpy=False)
     fly = mdb.rmsd_device(dt, dt, 0, as_numpy=False)
     assert (pre - fly)[1:].abs().max().item() < 1e-5
+
+
+def test_allpairs_block_api(mdb, oracle_mod, monkeypatch):
+    """b200rmsd_allpairs_block_dev: rectangular blocks, transposed copies and diagonal squares on both kernels."""
+    import torch
+    from mdtraj_b200 import allpairs as AP
+    X = oracle_mod.synth_md(700, 64, seed=33, rg=0.8, sigma=0.1)
+    dt = mdb.DeviceTrajectory.from_host(X)
+    for path in ("tc", "simt"):
+        monkeypatch.setenv("B200RMSD_ALLPAIRS", path)
+        monkeypatch.setenv("B200RMSD_NO_SYMMETRIC", "1")
+        full = mdb.rmsd_matrix_device(dt)
+        monkeypatch.delenv("B200RMSD_NO_SYMMETRIC")
+        prep = AP.prepare(dt)
+        out = torch.zeros((190, 700), dtype=torch.float32, device=dt.device)
+        out_t = torch.zeros((251, 190), dtype=torch.float32, device=dt.device)
+        AP.block(prep, 123, 313, 407, 658, out, out_t)
+        assert torch.equal(out[:, 407:658], full[123:313, 407:658])
+        assert torch.equal(out_t, full[123:313, 407:658].t())
+        assert torch.count_nonzero(out[:, :407]) == 0 and torch.count_nonzero(out[:, 658:]) == 0
+        sq = torch.zeros((190, 700), dtype=torch.float32, device=dt.device)
+        AP.block(prep, 123, 313, 123, 313, sq)  # diagonal square: each pair once, mirrored
+        blk = sq[:, 123:313]
+        assert torch.equal(blk, blk.t()) and torch.count_nonzero(torch.diagonal(blk)) == 0
+        assert (blk - full[123:313, 123:313]).abs().max().item() < 2e-6

