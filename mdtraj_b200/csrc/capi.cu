@@ -103,10 +103,15 @@ void configure_tma(OvmParams& p)
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 // development overrides of the frame-resident kernel geometry
-void apply_fused_env(FusedParams& p, int op)
+bool apply_fused_env(FusedParams& p, int op)
 {
-    const int g = env_int("B200RMSD_FUSED_GROUPS", 0), n = env_int("B200RMSD_FUSED_NBUF", 0);
-    if (g > 0 || n > 0) fused_override(p, op, g, n);
+    const int g = env_int("B200RMSD_FUSED_GROUPS", 0), n = env_int("B200RMSD_FUSED_NBUF", 0),
+              f = env_int("B200RMSD_FUSED_FPB", 0), l = env_int("B200RMSD_FUSED_LANES", 0);
+    if ((g > 0 || n > 0 || f > 0 || l > 0) && !fused_override(p, op, g, n, f, l)) return false;
+    if (env_int("B200RMSD_FUSED_VERBOSE", 0))
+        fprintf(stderr, "b200rmsd: frame_resident op=%d n_pad=%d G=%d nbuf=%d fpb=%d team_warps=%d lanes=%d\n", op, p.n_pad,
+                p.batch, p.nbuf, p.fpb, p.team_warps, p.lanes);
+    return true;
 }
 
 }  // namespace
@@ -162,7 +167,7 @@ int b200rmsd_center_trace_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t
     fp.n_sel = n_atoms;
     fp.traces = traces;
     if (!env_int("B200RMSD_NO_FUSED", 0) && fused_config(fp, OP_CENTER)) {
-        apply_fused_env(fp, OP_CENTER);
+        if (!apply_fused_env(fp, OP_CENTER)) return fail(B200RMSD_EINVAL, "center_trace: B200RMSD_FUSED_* override does not fit");
         CU(launch_frame_resident(fp, OP_CENTER, sm, (cudaStream_t)stream));
         return 0;
     }
@@ -285,7 +290,7 @@ int b200rmsd_superpose_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t fr
         fp.out_rot = out_rot;
         fp.degenerate = n_degenerate;
         if (!env_int("B200RMSD_NO_FUSED", 0) && aligned16(ref) && fused_config(fp, OP_SUPERPOSE)) {
-            apply_fused_env(fp, OP_SUPERPOSE);
+            if (!apply_fused_env(fp, OP_SUPERPOSE)) return fail(B200RMSD_EINVAL, "superpose: B200RMSD_FUSED_* override does not fit");
             CU(launch_frame_resident(fp, OP_SUPERPOSE, sm1, (cudaStream_t)stream));
             return 0;
         }

@@ -167,6 +167,30 @@ __device__ __forceinline__ void warp_reduce_scatter16(float (&v)[16], int lane)
     v[0] += __shfl_xor_sync(full, v[0], 1);
 }
 
+// Same butterfly inside aligned groups of L lanes (L = 2, 4, 8, 16): L lanes share one frame.
+template <int L>
+__device__ __forceinline__ int group_reduce_scatter16(float (&v)[16], int lane)
+{
+    // after the call v[0 .. 16/L) of this lane hold the group sums of value indices base .. base + 16/L - 1
+    int base = 0;
+    int cnt = 8;
+#pragma unroll
+    for (int h = L / 2; h >= 1; h >>= 1) {
+        const bool up = lane & h;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < cnt) {
+                const float send = up ? v[j] : v[j + cnt];
+                const float keep = up ? v[j + cnt] : v[j];
+                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+            }
+        }
+        base += up ? cnt : 0;
+        cnt >>= 1;
+    }
+    return base;
+}
+
 __device__ __forceinline__ double warp_sum(double x)
 {
 #pragma unroll

@@ -8,17 +8,20 @@
 //   OP_CENTER     inplace_center_and_trace_atom_major (center_sse.h:3-112): float64 sums, float32 mean,
 //                 float32 subtraction in place, float64 trace of the float32 squares.
 //
-// One persistent CTA per SM = 16 compute warps + a loader warp + a storer warp.  A CTA owns a contiguous range of frames and
-// moves them through a ring of `nbuf` whole-frame shared-memory buffers:
-//     loader     : bulk load frame i (cp.async.bulk global->shared, full[i%nbuf] mbarrier) as soon as the storer
+// One persistent CTA per SM = 16 compute warps + a loader warp + a storer warp.  A CTA owns a contiguous range of frames,
+// cuts it into *slots* of `fpb` consecutive frames (fpb > 1 only for frames that are contiguous in memory; one bulk copy
+// then moves fpb frames, which is what keeps small frames off the per-copy issue limit) and moves the slots through a
+// ring of `nbuf` shared-memory buffers:
+//     loader     : bulk load slot s (cp.async.bulk global->shared, full[s%nbuf] mbarrier) as soon as the storer
 //                  reports the buffer drained.
-//     storer     : once the compute group signals done[i%nbuf], bulk store the frame back (cp.async.bulk
-//                  shared->global), wait for the store to have read the buffer, publish drained[i%nbuf].
-//     compute    : the 16 warps form G independent groups of wpf warps; group g takes frames g, g+G, ...
-//                  (sums -> float64 solve by the group's first thread -> transform in shared memory), with
-//                  group-local named barriers only.  G frames are therefore in different phases at once
-//                  and the serial QCP solve of one overlaps the streaming phases of the others; nbuf-G
-//                  buffers are in flight to/from HBM.
+//     storer     : once the compute group signals done[s%nbuf], bulk store the slot back (cp.async.bulk
+//                  shared->global), wait for the store to have read the buffer, publish drained[s%nbuf].
+//     compute    : the 16 warps form G independent groups of wpf warps; group g takes slots g, g+G, ...
+//                  (sums of every frame of the slot -> float64 solves, one lane per frame, side by side -> transform
+//                  in shared memory), with group-local named barriers only.  Inside a group the warps either share
+//                  each frame (team_warps == wpf) or take whole frames each (team_warps == 1, fpb >= wpf).
+//                  G slots are in different phases at once, so the serial QCP solve latency of one overlaps the
+//                  streaming phases of the others; nbuf-G buffers are in flight to/from HBM.
 // Neither the LSU nor L1 sits on the HBM path, and compute threads never wait for a store to drain.
 #include <cstdlib>
 
@@ -28,7 +31,7 @@
 
 namespace b200 {
 
-// development aid: when set (B200RMSD_FUSED_TRACE=1), CTA 0 records clock64 stamps per frame:
+// development aid: when set (B200RMSD_FUSED_TRACE=1), CTA 0 records clock64 stamps per slot:
 // [i*8+0] data arrived, [1] sums reduced, [2] solve done, [3] transform done, [4] handed to storer,
 // [5] store issued, [6] store drained, [7] load issued
 __device__ long long* g_fr_trace = nullptr;
@@ -36,23 +39,27 @@ __device__ long long* g_fr_trace = nullptr;
 
 constexpr int kFrWarps = 16;                      // compute warps
 constexpr int kFrThreads = kFrWarps * 32 + 64;    // + loader warp + storer warp
-constexpr int kPartStride = 17;
+constexpr int kRecStride = 25;  // floats per frame record (odd: the solver lanes read one record each, conflict-free)
 
 struct FrLayout {
-    size_t buf_off, ref_off, idx_off, part_off, xf_off, bar_off, total;
+    size_t buf_off, ref_off, idx_off, rec_off, cpart_off, bar_off, total;
     size_t buf_bytes;
 };
 __host__ __device__ inline size_t fr_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
-__host__ __device__ inline FrLayout fr_layout(int n_pad, int nbuf, int n_sel_pad, int n_idx)
+// rec: one record per (group, frame of the slot, warp of the team): first the 16 float32 partial sums, then -- written by
+// the solver lane of that frame into the team's first record -- the 15 floats of its transform;
+// cpart: float64 partials of OP_CENTER, 4 per compute warp
+__host__ __device__ inline FrLayout fr_layout(int n_pad, int nbuf, int n_sel_pad, int n_idx, int G, int fpb, int team_warps,
+                                              bool records)
 {
     FrLayout L;
-    L.buf_bytes = (size_t)n_pad * 12;
+    L.buf_bytes = (size_t)n_pad * 12 * fpb;
     L.buf_off = 0;
     L.ref_off = fr_align((size_t)nbuf * L.buf_bytes, 128);
     L.idx_off = L.ref_off + fr_align((size_t)n_sel_pad * 12, 16);
-    L.part_off = fr_align(L.idx_off + (size_t)n_idx * 4, 16);
-    L.xf_off = L.part_off + (size_t)kFrWarps * kPartStride * sizeof(double);
-    L.bar_off = fr_align(L.xf_off + (size_t)kFrWarps * 24 * sizeof(float), 8);
+    L.rec_off = fr_align(L.idx_off + (size_t)n_idx * 4, 16);
+    L.cpart_off = fr_align(L.rec_off + (records ? (size_t)G * fpb * team_warps * kRecStride * sizeof(float) : 0), 8);
+    L.bar_off = L.cpart_off + (size_t)kFrWarps * 4 * sizeof(double);
     L.total = L.bar_off + (size_t)(3 * nbuf + 1) * sizeof(uint64_t);
     return L;
 }
@@ -63,14 +70,35 @@ __device__ __forceinline__ void group_sync(int group, int wpf)
     else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(wpf * 32) : "memory");
 }
 
+// x' = (x - c) R + o with the float64 centroid c = c_hi + c_lo and the float64 reference mean o (the reference does both
+// broadcasts in float64 numpy, trajectory.py:1140,1171) as 12 float32 operations per atom:
+//   t = x - c_hi  (a difference of nearby float32 numbers: at most half an ulp of the centred coordinate),
+//   x' = t R + d,  d = o - c_lo R  evaluated in float64 by the solver lane, added first in the FMA chain.
+// Worst case ~2 ulp of the result (1e-6 nm at |x'| = 5 nm) against the reference's ~0.5 ulp + 1.5 ulp of t.
 __device__ __forceinline__ void xf_atom(float& x, float& y, float& z, const float* __restrict__ t)
 {
-    // t: R[0..8], c_hi[9..11], c_lo[12..14], o_hi[15..17], o_lo[18..20]
-    const float tx = (x - t[9]) - t[12], ty = (y - t[10]) - t[13], tz = (z - t[11]) - t[14];
-    const float rx = tx * t[0] + ty * t[3] + tz * t[6];
-    const float ry = tx * t[1] + ty * t[4] + tz * t[7];
-    const float rz = tx * t[2] + ty * t[5] + tz * t[8];
-    x = (rx + t[15]) + t[18]; y = (ry + t[16]) + t[19]; z = (rz + t[17]) + t[20];
+    // t: R[0..8], c_hi[9..11], d[12..14]
+    const float tx = x - t[9], ty = y - t[10], tz = z - t[11];
+    x = fmaf(tx, t[0], fmaf(ty, t[3], fmaf(tz, t[6], t[12])));
+    y = fmaf(tx, t[1], fmaf(ty, t[4], fmaf(tz, t[7], t[13])));
+    z = fmaf(tx, t[2], fmaf(ty, t[5], fmaf(tz, t[8], t[14])));
+}
+
+// reduce the 16 lane partials over the L lanes that share a frame and drop them into the frame's record
+template <int L>
+__device__ __forceinline__ void team_reduce_store(float (&v)[16], int lane, bool act, float* rec)
+{
+    const int base = group_reduce_scatter16<L>(v, lane);
+    if (act) {
+#pragma unroll
+        for (int k = 0; k < 16 / L; ++k) rec[base + k] = v[k];
+    }
+}
+
+__device__ __forceinline__ double lanes_sum(double x, int L)  // all-reduce over aligned groups of L lanes
+{
+    for (int h = L >> 1; h >= 1; h >>= 1) x += __shfl_xor_sync(0xffffffffu, x, h);
+    return x;
 }
 
 template <int OP>
@@ -78,25 +106,30 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int n_sel_pad = (p.n_sel + 3) & ~3;
-    const FrLayout L = fr_layout(p.n_pad, p.nbuf, OP == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0);
+    const int G = p.batch;                     // concurrent slot groups; nbuf % G == 0
+    const int fpb = p.fpb;                     // frames per slot
+    const int wpf = kFrWarps / G;              // warps per group (G * wpf <= 16 compute warps take part)
+    const int tw = p.team_warps;               // warps sharing one frame: wpf (whole group) or 1
+    const FrLayout L = fr_layout(p.n_pad, p.nbuf, OP == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0, G, fpb, tw,
+                                 OP == OP_SUPERPOSE);
     const float* ref_s = reinterpret_cast<const float*>(smem + L.ref_off);
     int* idx_s = reinterpret_cast<int*>(smem + L.idx_off);
-    double* part_s = reinterpret_cast<double*>(smem + L.part_off);
-    float* xf_s = reinterpret_cast<float*>(smem + L.xf_off);
+    float* rec_all = reinterpret_cast<float*>(smem + L.rec_off);
+    double* cpart_s = reinterpret_cast<double*>(smem + L.cpart_off);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* done = full + p.nbuf;
     uint64_t* drained = done + p.nbuf;
     uint64_t* ref_bar = drained + p.nbuf;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int G = p.batch;                     // concurrent frame groups; nbuf % G == 0
-    const int wpf = kFrWarps / G;              // warps per group (G * wpf <= 16 compute warps take part)
     const int n_cw = G * wpf;
     const int units = p.n_pad >> 2;
     const uint32_t frame_bytes = (uint32_t)p.n_pad * 12u;
+    const int frame_floats = p.n_pad * 3;
 
     const int64_t f0 = p.n_frames * blockIdx.x / gridDim.x, f1 = p.n_frames * (blockIdx.x + 1) / gridDim.x;
     const int64_t n = f1 - f0;
+    const int64_t n_slots = (n + fpb - 1) / fpb;
 
     unsigned long long t_start_ns = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
@@ -118,42 +151,46 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
                 mbar_arrive_expect_tx(ref_bar, bytes);
                 bulk_g2s(smem + L.ref_off, p.ref, bytes, ref_bar);
             }
-            for (int64_t i = 0; i < n; ++i) {
-                const int buf = (int)(i % p.nbuf);
-                if (i >= p.nbuf) mbar_wait(&drained[buf], (uint32_t)(((i / p.nbuf) - 1) & 1));
-                mbar_arrive_expect_tx(&full[buf], frame_bytes);
-                bulk_g2s(smem + L.buf_off + (size_t)buf * L.buf_bytes, p.xyz + (f0 + i) * p.frame_stride, frame_bytes,
+            for (int64_t s = 0; s < n_slots; ++s) {
+                const int buf = (int)(s % p.nbuf);
+                const int64_t left = n - s * fpb;
+                const uint32_t bytes = (uint32_t)(left < fpb ? left : fpb) * frame_bytes;
+                if (s >= p.nbuf) mbar_wait(&drained[buf], (uint32_t)(((s / p.nbuf) - 1) & 1));
+                mbar_arrive_expect_tx(&full[buf], bytes);
+                bulk_g2s(smem + L.buf_off + (size_t)buf * L.buf_bytes, p.xyz + (f0 + s * fpb) * p.frame_stride, bytes,
                          &full[buf]);
-                FR_STAMP(i, 7);
+                FR_STAMP(s, 7);
             }
         }
         return;
     }
     if (warp == kFrWarps + 1) {
         if (lane == 0) {
-            // Up to K stores in flight: store i is issued, then the storer waits only until store i-K has drained and
-            // publishes that buffer.  K = 0 when every buffer is busy computing or loading (nbuf == G); small frames
+            // Up to K stores in flight: store s is issued, then the storer waits only until store s-K has drained and
+            // publishes that buffer.  K = 0 when every buffer is busy computing or loading (nbuf == G); small slots
             // need K > 0 or the drain latency of each 4-12 KB store would serialise the whole pipeline.
             const int K = p.nbuf == G ? 0 : min(3, p.nbuf - G - 1);
-            for (int64_t i = 0; i < n; ++i) {
-                const int buf = (int)(i % p.nbuf);
-                mbar_wait(&done[buf], (uint32_t)((i / p.nbuf) & 1));
-                bulk_s2g(p.xyz + (f0 + i) * p.frame_stride, smem + L.buf_off + (size_t)buf * L.buf_bytes, frame_bytes);
+            for (int64_t s = 0; s < n_slots; ++s) {
+                const int buf = (int)(s % p.nbuf);
+                const int64_t left = n - s * fpb;
+                const uint32_t bytes = (uint32_t)(left < fpb ? left : fpb) * frame_bytes;
+                mbar_wait(&done[buf], (uint32_t)((s / p.nbuf) & 1));
+                bulk_s2g(p.xyz + (f0 + s * fpb) * p.frame_stride, smem + L.buf_off + (size_t)buf * L.buf_bytes, bytes);
                 bulk_commit();
-                FR_STAMP(i, 5);
+                FR_STAMP(s, 5);
                 switch (K) {
                     case 0: bulk_wait_read<0>(); break;
                     case 1: bulk_wait_read<1>(); break;
                     case 2: bulk_wait_read<2>(); break;
                     default: bulk_wait_read<3>(); break;
                 }
-                if (i >= K) mbar_arrive(&drained[(int)((i - K) % p.nbuf)]);  // that buffer may be refilled
-                FR_STAMP(i, 6);
+                if (s >= K) mbar_arrive(&drained[(int)((s - K) % p.nbuf)]);  // that buffer may be refilled
+                FR_STAMP(s, 6);
             }
             bulk_wait_read<0>();
-            for (int64_t i = max((int64_t)0, n - K); i < n; ++i) mbar_arrive(&drained[(int)(i % p.nbuf)]);
+            for (int64_t s = max((int64_t)0, n_slots - K); s < n_slots; ++s) mbar_arrive(&drained[(int)(s % p.nbuf)]);
             bulk_wait<0>();
-            if (g_fr_trace) {  // per-CTA wall time (ns) after the per-frame stamps of CTA 0
+            if (g_fr_trace) {  // per-CTA wall time (ns) after the per-slot stamps of CTA 0
                 unsigned long long t_end_ns;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns));
                 const long long base = (long long)(p.n_frames / gridDim.x + 2) * 8;
@@ -168,84 +205,108 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
     if (warp >= n_cw) return;  // 16 is not a multiple of every G
     const int g = warp / wpf, sub = warp - g * wpf;
     const int gtid = sub * 32 + lane;  // thread index inside the group
+    // teams: tw warps share a frame; a group has wpf/tw teams, team `team` takes frames team, team+n_teams, ... of a slot
+    const int n_teams = wpf / tw, team = sub / tw, ts = sub - team * tw;
+    // inside a team: tw > 1 -> all tw*32 threads stride over one frame; tw == 1 -> the warp is cut into 32/Lt lane groups
+    // of Lt lanes and passes over 32/Lt frames at a time (small frames would leave most of a warp idle)
+    const int Lt = tw > 1 ? 32 : p.lanes;
+    const int fpi = 32 / Lt;                       // frames per warp pass
+    const int sj = lane / Lt;                      // which of them this lane works on
+    const int ttid = tw > 1 ? ts * 32 + lane : lane - sj * Lt, tthreads = tw > 1 ? tw * 32 : Lt;
     if (OP == OP_SUPERPOSE && p.idx)
         for (int k = tid; k < p.n_sel; k += n_cw * 32) idx_s[k] = __ldg(p.idx + k);
-    float oh[3] = {0, 0, 0}, ol[3] = {0, 0, 0};
     RefStats rs{};
     if (OP == OP_SUPERPOSE) {
         rs = *p.ref_stats;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { oh[i] = (float)rs.mean[i]; ol[i] = (float)(rs.mean[i] - (double)oh[i]); }
         mbar_wait(ref_bar, 0);
     }
     asm volatile("bar.sync 0, %0;" ::"r"(n_cw * 32) : "memory");  // idx_s visible to all compute warps
 
 #pragma unroll 1
-    for (int64_t i = g; i < n; i += G) {
-        const int buf = (int)(i % p.nbuf);
+    for (int64_t s = g; s < n_slots; s += G) {
+        const int buf = (int)(s % p.nbuf);
         // nbuf is a multiple of G, so buffer `buf` is only ever used by this group and the group observes every phase
         // of its barrier in order (a parity wait is ambiguous for a waiter that skips phases)
-        mbar_wait(&full[buf], (uint32_t)((i / p.nbuf) & 1));
-        if (gtid == 0) FR_STAMP(i, 0);
-        float* frame_s = reinterpret_cast<float*>(smem + L.buf_off + (size_t)buf * L.buf_bytes);
-        float4* xs = reinterpret_cast<float4*>(frame_s);
-        const int64_t f = f0 + i;
+        mbar_wait(&full[buf], (uint32_t)((s / p.nbuf) & 1));
+        if (gtid == 0) FR_STAMP(s, 0);
+        float* slot_s = reinterpret_cast<float*>(smem + L.buf_off + (size_t)buf * L.buf_bytes);
+        const int64_t left = n - s * fpb;
+        const int cnt = (int)(left < fpb ? left : fpb);
+        const int64_t fbase = f0 + s * fpb;
 
         if (OP == OP_SUPERPOSE) {
-            // ---- phase 1: sums over the align selection (pivot = first selected atom)
-            float v[16];
+            // ---- phase 1: sums over the align selection (pivot = first selected atom), frame by frame
+#pragma unroll 1
+            for (int j0 = team * fpi; j0 < cnt; j0 += n_teams * fpi) {
+                const bool act = j0 + sj < cnt;            // idle lane groups of a partial pass still take part in shuffles
+                const int j = act ? j0 + sj : j0;
+                const int n_sel_t = act ? p.n_sel : 0, units_t = act ? units : 0;
+                const float* frame_s = slot_s + (size_t)j * frame_floats;
+                const float4* xs = reinterpret_cast<const float4*>(frame_s);
+                float v[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = 0.f;
-            const int a0 = p.idx ? idx_s[0] : 0;
-            const float px = frame_s[3 * a0], py = frame_s[3 * a0 + 1], pz = frame_s[3 * a0 + 2];
-            if (p.idx) {
+                for (int q = 0; q < 16; ++q) v[q] = 0.f;
+                const int a0 = p.idx ? idx_s[0] : 0;
+                const float px = frame_s[3 * a0], py = frame_s[3 * a0 + 1], pz = frame_s[3 * a0 + 2];
+                if (p.idx) {
 #pragma unroll 4
-                for (int k = gtid; k < p.n_sel; k += wpf * 32) {
-                    const int a = idx_s[k];
-                    const float ax = frame_s[3 * a] - px, ay = frame_s[3 * a + 1] - py, az = frame_s[3 * a + 2] - pz;
-                    const float bx = ref_s[3 * k], by = ref_s[3 * k + 1], bz = ref_s[3 * k + 2];
-                    v[0] += ax; v[1] += ay; v[2] += az;
-                    v[3] = fmaf(ax, ax, v[3]); v[3] = fmaf(ay, ay, v[3]); v[3] = fmaf(az, az, v[3]);
-                    v[4] = fmaf(ax, bx, v[4]); v[5] = fmaf(ax, by, v[5]); v[6] = fmaf(ax, bz, v[6]);
-                    v[7] = fmaf(ay, bx, v[7]); v[8] = fmaf(ay, by, v[8]); v[9] = fmaf(ay, bz, v[9]);
-                    v[10] = fmaf(az, bx, v[10]); v[11] = fmaf(az, by, v[11]); v[12] = fmaf(az, bz, v[12]);
-                }
-            } else {
-                const float4* ys = reinterpret_cast<const float4*>(ref_s);
-                for (int u = gtid; u < units; u += wpf * 32) {
-                    const float4 a0v = xs[3 * u], a1v = xs[3 * u + 1], a2v = xs[3 * u + 2];
-                    const float4 b0v = ys[3 * u], b1v = ys[3 * u + 1], b2v = ys[3 * u + 2];
-                    const int nvalid = p.n_atoms - 4 * u;
-                    const float ax[4] = {a0v.x, a0v.w, a1v.z, a2v.y}, ay[4] = {a0v.y, a1v.x, a1v.w, a2v.z},
-                                az[4] = {a0v.z, a1v.y, a2v.x, a2v.w};
-                    const float bx[4] = {b0v.x, b0v.w, b1v.z, b2v.y}, by[4] = {b0v.y, b1v.x, b1v.w, b2v.z},
-                                bz[4] = {b0v.z, b1v.y, b2v.x, b2v.w};
+                    for (int k = ttid; k < n_sel_t; k += tthreads) {
+                        const int a = idx_s[k];
+                        const float ax = frame_s[3 * a] - px, ay = frame_s[3 * a + 1] - py, az = frame_s[3 * a + 2] - pz;
+                        const float bx = ref_s[3 * k], by = ref_s[3 * k + 1], bz = ref_s[3 * k + 2];
+                        v[0] += ax; v[1] += ay; v[2] += az;
+                        v[3] = fmaf(ax, ax, v[3]); v[3] = fmaf(ay, ay, v[3]); v[3] = fmaf(az, az, v[3]);
+                        v[4] = fmaf(ax, bx, v[4]); v[5] = fmaf(ax, by, v[5]); v[6] = fmaf(ax, bz, v[6]);
+                        v[7] = fmaf(ay, bx, v[7]); v[8] = fmaf(ay, by, v[8]); v[9] = fmaf(ay, bz, v[9]);
+                        v[10] = fmaf(az, bx, v[10]); v[11] = fmaf(az, by, v[11]); v[12] = fmaf(az, bz, v[12]);
+                    }
+                } else {
+                    const float4* ys = reinterpret_cast<const float4*>(ref_s);
+                    for (int u = ttid; u < units_t; u += tthreads) {
+                        const float4 a0v = xs[3 * u], a1v = xs[3 * u + 1], a2v = xs[3 * u + 2];
+                        const float4 b0v = ys[3 * u], b1v = ys[3 * u + 1], b2v = ys[3 * u + 2];
+                        const int nvalid = p.n_atoms - 4 * u;
+                        const float ax[4] = {a0v.x, a0v.w, a1v.z, a2v.y}, ay[4] = {a0v.y, a1v.x, a1v.w, a2v.z},
+                                    az[4] = {a0v.z, a1v.y, a2v.x, a2v.w};
+                        const float bx[4] = {b0v.x, b0v.w, b1v.z, b2v.y}, by[4] = {b0v.y, b1v.x, b1v.w, b2v.z},
+                                    bz[4] = {b0v.z, b1v.y, b2v.x, b2v.w};
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (q < nvalid) {
-                            const float dx = ax[q] - px, dy = ay[q] - py, dz = az[q] - pz;
-                            v[0] += dx; v[1] += dy; v[2] += dz;
-                            v[3] = fmaf(dx, dx, v[3]); v[3] = fmaf(dy, dy, v[3]); v[3] = fmaf(dz, dz, v[3]);
-                            v[4] = fmaf(dx, bx[q], v[4]); v[5] = fmaf(dx, by[q], v[5]); v[6] = fmaf(dx, bz[q], v[6]);
-                            v[7] = fmaf(dy, bx[q], v[7]); v[8] = fmaf(dy, by[q], v[8]); v[9] = fmaf(dy, bz[q], v[9]);
-                            v[10] = fmaf(dz, bx[q], v[10]); v[11] = fmaf(dz, by[q], v[11]); v[12] = fmaf(dz, bz[q], v[12]);
+                        for (int q = 0; q < 4; ++q) {
+                            if (q < nvalid) {
+                                const float dx = ax[q] - px, dy = ay[q] - py, dz = az[q] - pz;
+                                v[0] += dx; v[1] += dy; v[2] += dz;
+                                v[3] = fmaf(dx, dx, v[3]); v[3] = fmaf(dy, dy, v[3]); v[3] = fmaf(dz, dz, v[3]);
+                                v[4] = fmaf(dx, bx[q], v[4]); v[5] = fmaf(dx, by[q], v[5]); v[6] = fmaf(dx, bz[q], v[6]);
+                                v[7] = fmaf(dy, bx[q], v[7]); v[8] = fmaf(dy, by[q], v[8]); v[9] = fmaf(dy, bz[q], v[9]);
+                                v[10] = fmaf(dz, bx[q], v[10]); v[11] = fmaf(dz, by[q], v[11]); v[12] = fmaf(dz, bz[q], v[12]);
+                            }
                         }
                     }
                 }
+                if (ttid == 0 && act) { v[13] = px; v[14] = py; v[15] = pz; }
+                float* rec_s = rec_all + (((size_t)g * fpb + j) * tw + ts) * kRecStride;
+                switch (Lt) {
+                    case 2: team_reduce_store<2>(v, lane, act, rec_s); break;
+                    case 4: team_reduce_store<4>(v, lane, act, rec_s); break;
+                    case 8: team_reduce_store<8>(v, lane, act, rec_s); break;
+                    case 16: team_reduce_store<16>(v, lane, act, rec_s); break;
+                    default:
+                        warp_reduce_scatter16(v, lane);
+                        if (!(lane & 1)) rec_s[lane >> 1] = v[0];
+                }
             }
-            if (gtid == 0) { v[13] = px; v[14] = py; v[15] = pz; }
-            warp_reduce_scatter16(v, lane);
-            if (!(lane & 1)) part_s[warp * kPartStride + (lane >> 1)] = (double)v[0];
             group_sync(g, wpf);
-            // ---- solve: the group's first thread
-            if (gtid == 0) {
-                FR_STAMP(i, 1);
+            // ---- solve: one lane per frame of the slot, side by side
+            if (gtid < cnt) {
+                if (gtid == 0) FR_STAMP(s, 1);
+                const int j = gtid;
+                const int64_t f = fbase + j;
                 double rec[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) rec[q] = 0.0;
-                for (int s = 0; s < wpf; ++s)
+                for (int w = 0; w < tw; ++w)
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) rec[q] += part_s[(g * wpf + s) * kPartStride + q];
+                    for (int q = 0; q < 16; ++q) rec[q] += (double)rec_all[(((size_t)g * fpb + j) * tw + w) * kRecStride + q];
                 const double invn = 1.0 / (double)p.n_sel;
                 const double mx = rec[0] * invn, my = rec[1] * invn, mz = rec[2] * invn;
                 QcpInput q;
@@ -265,26 +326,34 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
                     for (int c = 0; c < 9; ++c) p.out_rot[f * 9 + c] = R[c];
                 }
                 if (degen && p.degenerate) atomicAdd(p.degenerate, 1u);
-                float* t = xf_s + g * 24;
+                float* t = rec_all + ((size_t)g * fpb + j) * tw * kRecStride;  // every partial of this frame has been read
 #pragma unroll
                 for (int c = 0; c < 9; ++c) t[c] = R[c];
                 const double cen[3] = {rec[13] + mx, rec[14] + my, rec[15] + mz};
+                double clo[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float h = (float)cen[c];
-                    t[9 + c] = h; t[12 + c] = (float)(cen[c] - (double)h);
-                    t[15 + c] = oh[c]; t[18 + c] = ol[c];
+                    t[9 + c] = h;
+                    clo[c] = cen[c] - (double)h;
                 }
-                FR_STAMP(i, 2);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    t[12 + c] = (float)(rs.mean[c] - (clo[0] * (double)R[c] + clo[1] * (double)R[3 + c] + clo[2] * (double)R[6 + c]));
+                if (gtid == 0) FR_STAMP(s, 2);
             }
             group_sync(g, wpf);
-            // ---- phase 2: transform every atom of the frame in shared memory
-            {
-                float t[21];
+            // ---- phase 2: transform every atom of every frame of the slot in shared memory
+#pragma unroll 1
+            for (int j0 = team * fpi; j0 < cnt; j0 += n_teams * fpi) {
+                const int j = j0 + sj;
+                if (j >= cnt) continue;
+                float4* xs = reinterpret_cast<float4*>(slot_s + (size_t)j * frame_floats);
+                float t[15];
 #pragma unroll
-                for (int c = 0; c < 21; ++c) t[c] = xf_s[g * 24 + c];
+                for (int c = 0; c < 15; ++c) t[c] = rec_all[((size_t)g * fpb + j) * tw * kRecStride + c];
 #pragma unroll 2
-                for (int u = gtid; u < units; u += wpf * 32) {
+                for (int u = ttid; u < units; u += tthreads) {
                     float4 a0v = xs[3 * u], a1v = xs[3 * u + 1], a2v = xs[3 * u + 2];
                     const int nvalid = p.n_atoms - 4 * u;
                     xf_atom(a0v.x, a0v.y, a0v.z, t);
@@ -295,117 +364,223 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
                 }
             }
         } else {  // ---------------------------------------------------------------- OP_CENTER
-            double sx = 0, sy = 0, sz = 0;
-            for (int u = gtid; u < units; u += wpf * 32) {
-                const float4 a0v = xs[3 * u], a1v = xs[3 * u + 1], a2v = xs[3 * u + 2];
-                sx += (double)a0v.x; sy += (double)a0v.y; sz += (double)a0v.z;
-                sx += (double)a0v.w; sy += (double)a1v.x; sz += (double)a1v.y;
-                sx += (double)a1v.z; sy += (double)a1v.w; sz += (double)a2v.x;
-                sx += (double)a2v.y; sy += (double)a2v.z; sz += (double)a2v.w;
+            // tw == wpf: the group's warps share each frame (cnt frames one after the other, the loop is uniform across
+            // the group so the named barriers inside are safe); tw == 1: every warp centres whole frames by itself
+#pragma unroll 1
+            for (int j0 = team * fpi; j0 < cnt; j0 += n_teams * fpi) {
+                const bool act = j0 + sj < cnt;
+                const int j = act ? j0 + sj : j0;
+                const int units_t = act ? units : 0;
+                float4* xs = reinterpret_cast<float4*>(slot_s + (size_t)j * frame_floats);
+                double sx = 0, sy = 0, sz = 0;
+                for (int u = ttid; u < units_t; u += tthreads) {
+                    const float4 a0v = xs[3 * u], a1v = xs[3 * u + 1], a2v = xs[3 * u + 2];
+                    sx += (double)a0v.x; sy += (double)a0v.y; sz += (double)a0v.z;
+                    sx += (double)a0v.w; sy += (double)a1v.x; sz += (double)a1v.y;
+                    sx += (double)a1v.z; sy += (double)a1v.w; sz += (double)a2v.x;
+                    sx += (double)a2v.y; sy += (double)a2v.z; sz += (double)a2v.w;
+                }
+                sx = lanes_sum(sx, Lt); sy = lanes_sum(sy, Lt); sz = lanes_sum(sz, Lt);
+                if (tw > 1) {
+                    if (lane == 0) { cpart_s[warp * 4] = sx; cpart_s[warp * 4 + 1] = sy; cpart_s[warp * 4 + 2] = sz; }
+                    group_sync(g, wpf);
+                    sx = sy = sz = 0;
+                    for (int w = 0; w < tw; ++w) {
+                        sx += cpart_s[(g * wpf + w) * 4]; sy += cpart_s[(g * wpf + w) * 4 + 1];
+                        sz += cpart_s[(g * wpf + w) * 4 + 2];
+                    }
+                }
+                const float mx = (float)(sx / p.n_atoms), my = (float)(sy / p.n_atoms), mz = (float)(sz / p.n_atoms);
+                double tr = 0;
+                for (int u = ttid; u < units_t; u += tthreads) {
+                    float4 a0v = xs[3 * u], a1v = xs[3 * u + 1], a2v = xs[3 * u + 2];
+                    const int nvalid = p.n_atoms - 4 * u;
+                    a0v.x -= mx; a0v.y -= my; a0v.z -= mz;
+                    tr += (double)(a0v.x * a0v.x); tr += (double)(a0v.y * a0v.y); tr += (double)(a0v.z * a0v.z);
+                    if (nvalid > 1) {
+                        a0v.w -= mx; a1v.x -= my; a1v.y -= mz;
+                        tr += (double)(a0v.w * a0v.w); tr += (double)(a1v.x * a1v.x); tr += (double)(a1v.y * a1v.y);
+                    }
+                    if (nvalid > 2) {
+                        a1v.z -= mx; a1v.w -= my; a2v.x -= mz;
+                        tr += (double)(a1v.z * a1v.z); tr += (double)(a1v.w * a1v.w); tr += (double)(a2v.x * a2v.x);
+                    }
+                    if (nvalid > 3) {
+                        a2v.y -= mx; a2v.z -= my; a2v.w -= mz;
+                        tr += (double)(a2v.y * a2v.y); tr += (double)(a2v.z * a2v.z); tr += (double)(a2v.w * a2v.w);
+                    }
+                    xs[3 * u] = a0v; xs[3 * u + 1] = a1v; xs[3 * u + 2] = a2v;
+                }
+                tr = lanes_sum(tr, Lt);
+                if (tw > 1) {
+                    if (lane == 0) cpart_s[warp * 4 + 3] = tr;
+                    group_sync(g, wpf);
+                    if (ttid == 0) {
+                        tr = 0;
+                        for (int w = 0; w < tw; ++w) tr += cpart_s[(g * wpf + w) * 4 + 3];
+                    }
+                }
+                if (ttid == 0 && act && p.traces) p.traces[fbase + j] = (float)tr;
             }
-            sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-            if (wpf > 1) {
-                if (lane == 0) { part_s[warp * kPartStride] = sx; part_s[warp * kPartStride + 1] = sy; part_s[warp * kPartStride + 2] = sz; }
-                group_sync(g, wpf);
-                sx = sy = sz = 0;
-                for (int s = 0; s < wpf; ++s) {
-                    sx += part_s[(g * wpf + s) * kPartStride]; sy += part_s[(g * wpf + s) * kPartStride + 1];
-                    sz += part_s[(g * wpf + s) * kPartStride + 2];
-                }
-            }
-            const float mx = (float)(sx / p.n_atoms), my = (float)(sy / p.n_atoms), mz = (float)(sz / p.n_atoms);
-            double tr = 0;
-            for (int u = gtid; u < units; u += wpf * 32) {
-                float4 a0v = xs[3 * u], a1v = xs[3 * u + 1], a2v = xs[3 * u + 2];
-                const int nvalid = p.n_atoms - 4 * u;
-                a0v.x -= mx; a0v.y -= my; a0v.z -= mz;
-                tr += (double)(a0v.x * a0v.x); tr += (double)(a0v.y * a0v.y); tr += (double)(a0v.z * a0v.z);
-                if (nvalid > 1) {
-                    a0v.w -= mx; a1v.x -= my; a1v.y -= mz;
-                    tr += (double)(a0v.w * a0v.w); tr += (double)(a1v.x * a1v.x); tr += (double)(a1v.y * a1v.y);
-                }
-                if (nvalid > 2) {
-                    a1v.z -= mx; a1v.w -= my; a2v.x -= mz;
-                    tr += (double)(a1v.z * a1v.z); tr += (double)(a1v.w * a1v.w); tr += (double)(a2v.x * a2v.x);
-                }
-                if (nvalid > 3) {
-                    a2v.y -= mx; a2v.z -= my; a2v.w -= mz;
-                    tr += (double)(a2v.y * a2v.y); tr += (double)(a2v.z * a2v.z); tr += (double)(a2v.w * a2v.w);
-                }
-                xs[3 * u] = a0v; xs[3 * u + 1] = a1v; xs[3 * u + 2] = a2v;
-            }
-            tr = warp_sum(tr);
-            if (wpf > 1) {
-                if (lane == 0) part_s[warp * kPartStride + 3] = tr;
-                group_sync(g, wpf);
-                if (gtid == 0) {
-                    tr = 0;
-                    for (int s = 0; s < wpf; ++s) tr += part_s[(g * wpf + s) * kPartStride + 3];
-                }
-            }
-            if (gtid == 0 && p.traces) p.traces[f] = (float)tr;
         }
-        // ---- publish the modified frame to the async proxy and hand the buffer to the DMA thread
-        if (gtid == 0) FR_STAMP(i, 3);
+        // ---- publish the modified slot to the async proxy and hand the buffer to the DMA thread
+        if (gtid == 0) FR_STAMP(s, 3);
         fence_proxy_async_smem();
         group_sync(g, wpf);
-        if (gtid == 0) { mbar_arrive(&done[buf]); FR_STAMP(i, 4); }
+        if (gtid == 0) { mbar_arrive(&done[buf]); FR_STAMP(s, 4); }
     }
 }
 
-static bool fr_fits(const FusedParams& p, int op, int nbuf)
+static int fr_team_warps(int G, int fpb)
 {
-    const int n_sel_pad = (p.n_sel + 3) & ~3;
-    return fr_layout(p.n_pad, nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0).total <= 232448;
+    const int wpf = kFrWarps / G;
+    return fpb >= wpf ? 1 : wpf;  // enough frames per slot to give every warp its own, else share each frame
 }
 
-// Geometry: G frame groups (wpf = 16/G warps each) and a ring of nbuf = G*m buffers.  nbuf must be a multiple of G so
-// that a buffer always belongs to one group (see the parity-wait note in the kernel).  Either every group has a second
-// buffer to prefetch into (m >= 2) or there are >= 3 groups so that, while one computes, the others' single buffers
-// are loading and storing (m == 1: the large-frame case, e.g. three 60 KB buffers at N = 5000).
+static bool fr_fits(const FusedParams& p, int op, int G, int fpb, int nbuf)
+{
+    const int n_sel_pad = (p.n_sel + 3) & ~3;
+    return fr_layout(p.n_pad, nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0, G, fpb, fr_team_warps(G, fpb),
+                     op == OP_SUPERPOSE).total <= 232448;
+}
+
+// Work split inside a group for (G, fpb):
+//   fpb <  wpf : the group's wpf warps share each frame (team_warps = wpf, lanes = 32);
+//   fpb >= wpf : every warp takes whole frames (team_warps = 1), and a warp is cut into lane groups of `lanes` lanes, one
+//                frame each, so that a warp passes over 32/lanes frames at a time.
+static void fr_set(FusedParams& p, int G, int fpb, int nbuf, int lanes)
+{
+    p.batch = G; p.nbuf = nbuf; p.fpb = fpb; p.team_warps = fr_team_warps(G, fpb);
+    p.lanes = p.team_warps == 1 ? lanes : 32;
+}
+
+// Lanes per frame when every warp takes whole frames: the widest lane group that still covers the slot in ONE pass of the
+// group's warps.  Every pass costs ~1800 cycles (reduction, pivot and transform loads, loop set-up, barriers) against
+// 350-950 per unit a lane walks: N = 50 with 32 frames per slot runs at 0.88x of HBM peak on 2 lanes per frame (one pass)
+// and 0.78x on 4 (two passes); 39 frames per slot (two passes on 2 lanes) 0.80x.
+static int fr_one_pass_lanes(int G, int fpb)
+{
+    const int wpf = kFrWarps / G;
+    int lanes = 32;
+    while (lanes > 2 && wpf * (32 / lanes) < fpb) lanes >>= 1;
+    return lanes;
+}
+
+// frames per slot: one solver lane per frame, the solver lanes are the group's first min(64, wpf*32) threads
+static int fr_cap(int G, bool contiguous) { return !contiguous ? 1 : (kFrWarps / G >= 2 ? 64 : 32); }
+
+static int fr_max_fpb(const FusedParams& p, int op, int G, int nbuf, int cap)
+{
+    int fpb = 0;
+    while (fpb < cap && fr_fits(p, op, G, fpb + 1, nbuf)) ++fpb;  // the layout grows monotonically with fpb
+    return fpb;
+}
+
+// Cost model of one group working through one single-buffer slot, least-squares fit (median error 5 %) to ~900
+// geometries per operation measured with tools/fused_sweep.py (N = 22 ... 1000).  Nothing overlaps inside a group, so a
+// slot costs  F (load/store latency + the float64 solve, ~4400 cycles however many frames are solved side by side)
+//           + S per KB moved + per pass of the group's warps over the slot ( P + c per unit a lane walks ).
+// Returns bytes per clock per SM (22.5 = HBM peak).
+static double fr_model(const FusedParams& p, int op, int G, int fpb, int lanes)
+{
+    const int wpf = kFrWarps / G, units = p.n_pad / 4, tw = fr_team_warps(G, fpb);
+    const double sel = (op == OP_SUPERPOSE && p.idx) ? (double)p.n_sel / p.n_atoms : 1.0;
+    const double F = op == OP_SUPERPOSE ? 7250.0 : 2800.0, S = op == OP_SUPERPOSE ? 110.0 : 90.0;
+    const double c = op == OP_SUPERPOSE ? 216.0 + 552.0 * sel : 690.0;
+    double P = op == OP_SUPERPOSE ? 1740.0 : 1980.0;
+    int passes, iters;
+    if (tw == 1) {
+        const int frames_per_pass = wpf * (32 / lanes);
+        passes = (fpb + frames_per_pass - 1) / frames_per_pass;
+        iters = (units + lanes - 1) / lanes;
+    } else {
+        passes = fpb;
+        iters = (units + wpf * 32 - 1) / (wpf * 32);
+        P += op == OP_SUPERPOSE ? 50.0 : 600.0;  // named barriers between the warps of the group
+    }
+    const double slot_kb = (double)fpb * p.n_pad * 12.0 / 1000.0;
+    const double t = F + S * slot_kb + passes * (P + iters * c);
+    return (double)G * slot_kb * 2000.0 / t;
+}
+
+// Geometry (measured with tools/fused_sweep.py, N = 22 ... 5000):
+//  * nbuf is a multiple of G so that a buffer always belongs to one group (see the parity-wait note in the kernel);
+//  * superpose: the serial float64 solve makes the compute phase long, so what pays is many groups with ONE slot each,
+//    as large as shared memory allows: contiguous frames are packed fpb to a slot (N = 1000: 2 frames = 24 KB per slot on
+//    8 groups, N = 300: 12 frames on 5 groups, N = 22: 64).  That also takes small frames off the DMA threads' issue
+//    limit (~1 bulk copy per 100-150 ns each way);
+//    (G, fpb) is the best of the cost model above, lanes the one-pass choice;
+//  * centring: 5 single-slot groups up to 12 KB frames, the model up to 20 KB, larger frames two slots per group (one
+//    computing, one in flight).
 bool fused_config(FusedParams& p, int op)
 {
     const size_t frame_bytes = (size_t)p.n_pad * 12;
     if (frame_bytes >= (1u << 20)) return false;
-    int nbuf_max = 0;
-    while (nbuf_max < 48 && fr_fits(p, op, nbuf_max + 1)) ++nbuf_max;
-    if (nbuf_max < 3) return false;  // cannot overlap load, compute and store
-    static const int kGroups[] = {16, 8, 4, 3, 2, 1};
-    const int g_cap = 8;  // measured at N = 1000: throughput grows with G up to 8 for both operations
-    // first choice: m >= 2 with at least ~48 KB of prefetch in flight
-    for (int G : kGroups) {
-        if (G > g_cap || G < 2) continue;
-        int m = nbuf_max / G;
-        if (m < 2) continue;
-        if ((size_t)(m - 1) * G * frame_bytes < 49152) continue;
-        if (m > 4) m = 4;
-        p.batch = G;
-        p.nbuf = G * m;
-        return true;
-    }
-    // large frames: one buffer per group, >= 3 groups
-    for (int G : kGroups) {
-        if (G <= nbuf_max && G >= 3 && G <= g_cap + 1) {
-            p.batch = G;
-            p.nbuf = G;
+    const bool contiguous = p.frame_stride == (int64_t)p.n_pad * 3;
+    if (op == OP_CENTER && frame_bytes <= 12288) {
+        // centring is light enough to be HBM-bound in the model whatever the geometry; measured best (0.96-0.99x for
+        // N = 50 ... 1000) are 5 groups with one slot of 24-45 KB each
+        const int fit = fr_max_fpb(p, op, 5, 5, fr_cap(5, contiguous));
+        if ((size_t)fit * frame_bytes >= 24576) {
+            fr_set(p, 5, fit, 5, fr_one_pass_lanes(5, fit));
             return true;
         }
     }
-    // last resort: one group of 16 warps with a 3-deep ring (measured 0.64x of HBM peak at N = 5000)
-    p.batch = 1;
-    p.nbuf = 3;
-    return true;
+    if (op == OP_SUPERPOSE || frame_bytes <= 20480) {
+        static const int kGroups[] = {8, 5, 4, 3};
+        double best = 0.0;
+        for (int G : kGroups) {  // in descending order: fewer, larger slots only for a clear (2 %) modelled gain
+            const int fit = fr_max_fpb(p, op, G, G, fr_cap(G, contiguous));
+            double best_g = 0.0;
+            int fpb_g = 0;
+            for (int fpb = 1; fpb <= fit; ++fpb) {
+                const double r = fr_model(p, op, G, fpb, fr_one_pass_lanes(G, fpb));
+                if (r >= best_g) { best_g = r; fpb_g = fpb; }
+            }
+            if (fpb_g && best_g > best * 1.02) {
+                best = best_g;
+                fr_set(p, G, fpb_g, G, fr_one_pass_lanes(G, fpb_g));
+            }
+        }
+        if (best > 0.0) return true;
+    } else {
+        static const int kGroups[] = {8, 4, 3, 2};
+        const int want = (int)(16384 / frame_bytes) < 1 ? 1 : (int)(16384 / frame_bytes);
+        for (int G : kGroups) {  // the shallowest ring with at least ~48 KB of prefetch in flight
+            for (int m = 2; m <= 4; ++m) {
+                const int cap = fr_cap(G, contiguous);
+                const int fpb = fr_max_fpb(p, op, G, G * m, want < cap ? want : cap);
+                if (fpb < 1 || (size_t)(m - 1) * G * fpb * frame_bytes < 49152) continue;
+                fr_set(p, G, fpb, G * m, fr_one_pass_lanes(G, fpb));
+                return true;
+            }
+        }
+        for (int G : kGroups) {  // large frames: one buffer per group, >= 3 groups
+            if (G >= 3 && fr_fits(p, op, G, 1, G)) {
+                fr_set(p, G, 1, G, 32);
+                return true;
+            }
+        }
+    }
+    if (fr_fits(p, op, 1, 1, 3)) {  // one group of 16 warps with a 3-deep ring (measured 0.64x of HBM peak at N = 5000)
+        fr_set(p, 1, 1, 3, 32);
+        return true;
+    }
+    return false;
 }
 
-// development override: G concurrent frame groups and ring depth (validated against the shared-memory budget)
-bool fused_override(FusedParams& p, int op, int G, int nbuf)
+// development override: frames per slot, G concurrent groups, ring depth, lanes per frame (checked against shared memory)
+bool fused_override(FusedParams& p, int op, int G, int nbuf, int fpb, int lanes)
 {
     if (G <= 0) G = p.batch;
-    if (nbuf <= 0) nbuf = p.nbuf;
-    if (G > 16 || nbuf < G || nbuf % G != 0 || nbuf < 2) return false;
-    if (!fr_fits(p, op, nbuf)) return false;
-    p.batch = G;
-    p.nbuf = nbuf;
+    if (fpb <= 0) fpb = p.fpb;
+    if (nbuf <= 0) nbuf = G * (p.nbuf / p.batch);
+    if (G > 16 || G < 1 || fpb > fr_cap(G, p.frame_stride == (int64_t)p.n_pad * 3)) return false;
+    if (nbuf < G || nbuf % G != 0 || nbuf < 2) return false;
+    if (!fr_fits(p, op, G, fpb, nbuf)) return false;
+    if (lanes > 0 && ((lanes & (lanes - 1)) || lanes < 2 || lanes > 32)) return false;
+    if (lanes > 0 && lanes != 32 && fr_team_warps(G, fpb) != 1) return false;
+    fr_set(p, G, fpb, nbuf, lanes > 0 ? lanes : fr_one_pass_lanes(G, fpb));
     return true;
 }
 
@@ -424,6 +599,24 @@ long long* fr_trace_buffer(size_t n_frames_cta)
     return buf;
 }
 
+// development / test hook (no device needed): the geometry fused_config picks; out = {G, nbuf, fpb, team_warps, lanes,
+// shared-memory bytes}.  Returns 0 when the single-pass kernel does not apply.
+extern "C" int b200rmsd_debug_fused_geometry(int op, int n_atoms, int n_sel, int has_idx, int contiguous, int* out)
+{
+    FusedParams p{};
+    p.n_atoms = n_atoms;
+    p.n_pad = (n_atoms + 3) / 4 * 4;
+    p.frame_stride = contiguous ? (int64_t)p.n_pad * 3 : (int64_t)p.n_pad * 3 + 4;
+    p.n_sel = has_idx ? n_sel : n_atoms;
+    p.idx = has_idx ? reinterpret_cast<const int*>(0x10) : nullptr;  // only tested against nullptr
+    if (!fused_config(p, op)) return 0;
+    const int n_sel_pad = (p.n_sel + 3) & ~3;
+    const FrLayout L = fr_layout(p.n_pad, p.nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0, p.batch, p.fpb,
+                                 p.team_warps, op == OP_SUPERPOSE);
+    out[0] = p.batch; out[1] = p.nbuf; out[2] = p.fpb; out[3] = p.team_warps; out[4] = p.lanes; out[5] = (int)L.total;
+    return 1;
+}
+
 extern "C" int b200rmsd_debug_fused_trace(long long* host_out, size_t n)
 {
     long long* buf = nullptr;
@@ -438,12 +631,14 @@ cudaError_t launch_frame_resident(const FusedParams& p, int op, int sm_count, cu
     if (p.n_frames <= 0) return cudaSuccess;
     fr_trace_buffer((size_t)(p.n_frames / (sm_count > 0 ? sm_count : 1) + 2) + 64);
     const int n_sel_pad = (p.n_sel + 3) & ~3;
-    const FrLayout L = fr_layout(p.n_pad, p.nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0);
+    const FrLayout L = fr_layout(p.n_pad, p.nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0, p.batch, p.fpb,
+                                 p.team_warps, op == OP_SUPERPOSE);
     auto kern = op == OP_SUPERPOSE ? frame_resident_kernel<OP_SUPERPOSE> : frame_resident_kernel<OP_CENTER>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     if (e != cudaSuccess) return e;
     int64_t ctas = sm_count;
-    const int64_t need = (p.n_frames + p.batch - 1) / p.batch;
+    const int64_t per_round = (int64_t)p.batch * p.fpb;
+    const int64_t need = (p.n_frames + per_round - 1) / per_round;
     if (ctas > need) ctas = need;
     kern<<<(unsigned)ctas, kFrThreads, L.total, st>>>(p);
     return cudaGetLastError();

@@ -54,7 +54,7 @@ struct ApplyParams {
 // frame-resident read-modify-write kernels (frame_resident.cu)
 enum { OP_SUPERPOSE = 0, OP_CENTER = 1 };
 struct FusedParams {
-    float* xyz;             // in/out, frames contiguous: frame_stride == 3*n_pad
+    float* xyz;             // in/out, padded atom-major
     int64_t n_frames;
     int64_t frame_stride;
     int n_atoms;
@@ -67,11 +67,14 @@ struct FusedParams {
     float* out_rot;         // may be nullptr
     float* traces;          // OP_CENTER output, may be nullptr
     unsigned int* degenerate;
-    int batch;              // G: frame groups computing concurrently (power of two <= 16)
-    int nbuf;               // whole-frame shared-memory buffers in the ring (>= G + 1)
+    int batch;              // G: slot groups computing concurrently (<= 16)
+    int nbuf;               // shared-memory slot buffers in the ring (a multiple of G)
+    int fpb;                // frames per slot (> 1 only when frame_stride == 3*n_pad)
+    int team_warps;         // warps sharing one frame inside a group: 16/G or 1
+    int lanes;              // team_warps == 1: lanes sharing one frame inside a warp (2, 4, 8, 16, 32)
 };
 bool fused_config(FusedParams& p, int op);
-bool fused_override(FusedParams& p, int op, int G, int nbuf);
+bool fused_override(FusedParams& p, int op, int G, int nbuf, int fpb, int lanes);
 cudaError_t launch_frame_resident(const FusedParams& p, int op, int sm_count, cudaStream_t st);
 
 cudaError_t launch_ovm_tma(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st);

@@ -269,29 +269,6 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
 // ---------------------------------------------------------------------------
 constexpr int kGroupBatch = 32;  // frames per solve batch (one per lane)
 
-template <int L>
-__device__ __forceinline__ int group_reduce_scatter16(float (&v)[16], int lane)
-{
-    // after the call v[0 .. 16/L) of this lane hold the group sums of value indices base .. base + 16/L - 1
-    int base = 0;
-    int cnt = 8;
-#pragma unroll
-    for (int h = L / 2; h >= 1; h >>= 1) {
-        const bool up = lane & h;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j < cnt) {
-                const float send = up ? v[j] : v[j + cnt];
-                const float keep = up ? v[j + cnt] : v[j];
-                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-            }
-        }
-        base += up ? cnt : 0;
-        cnt >>= 1;
-    }
-    return base;
-}
-
 struct OvmGroupLayout {
     size_t ref_off, ring_off, sums_off, bar_off, total, stage_bytes;
 };

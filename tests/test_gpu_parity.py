@@ -445,10 +445,12 @@ def test_rmsf_residue_mode(mdb, oracle_mod):
 
 
 # ------------------------------------------------------------------ frame-resident kernels at scale
-@pytest.mark.parametrize("F,N,stride", [(6000, 1000, 4), (1500, 5000, 5), (20000, 300, 1), (40000, 22, 1), (700, 8000, 7)])
+@pytest.mark.parametrize("F,N,stride", [(6000, 1000, 4), (1500, 5000, 5), (20000, 300, 1), (40000, 22, 1), (700, 8000, 7),
+                                        (30001, 100, 1), (25000, 50, 3), (4001, 1001, 4), (3000, 2000, 1)])
 def test_superpose_and_center_properties_at_scale(mdb, F, N, stride):
-    """Every ring geometry of frame_resident_kernel (8 groups x 2 buffers, 3 single-buffer groups for 60 KB frames,
-    small frames, the two-pass fallback for frames that do not fit) and many frames per CTA, checked through
+    """Every geometry of frame_resident_kernel (8 single-slot groups with 1-64 frames per slot, 2-16 lanes per frame for
+    small frames, 3 single-buffer groups for 60 KB frames, partial last slots, the two-pass fallback for frames that do
+    not fit) and many frames per CTA, checked through
     size-independent properties: superpose-then-plain-RMSD == QCP RMSD (tests/test_rmsd.py:98-108), a second superpose
     is the identity, centring leaves zero means and traces == sum |x|^2, repeated launches are bit-identical."""
     import torch

@@ -134,3 +134,38 @@ def test_symmetric_plan_covers_every_entry_once():
             work.append(area)
         if W > 1 and F >= 8 * W:
             assert max(work) <= 1.35 * (sum(work) / W), (F, W, work)
+
+
+def test_frame_resident_geometry_invariants():
+    """The slot/ring geometry of the single-pass superpose / centring kernel (csrc/frame_resident.cu: fused_config),
+    through the host-only debug hook: a buffer must belong to one group (nbuf % G == 0, the mbarrier parity rule),
+    and fit shared memory."""
+    import ctypes
+
+    from mdtraj_b200 import _capi
+    L = ctypes.CDLL(_capi.LIB_PATH)
+    geo = L.b200rmsd_debug_fused_geometry
+    geo.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_int)]
+    out = (ctypes.c_int * 6)()
+    seen_multi = False
+    for op in (0, 1):
+        for n in list(range(1, 70)) + [99, 100, 127, 128, 200, 255, 256, 300, 500, 999, 1000, 1500, 2000, 2500, 3000, 4000,
+                                        5000, 6000, 9000, 20000]:
+            for has_idx in ((0, 1) if op == 0 else (0,)):
+                for contiguous in (1, 0):
+                    n_sel = max(1, n // 5) if has_idx else n
+                    if not geo(op, n, n_sel, has_idx, contiguous, out):
+                        assert n * 12 * 3 > 150000, f"single-pass kernel refused a small frame: op={op} n={n}"
+                        continue
+                    G, nbuf, fpb, tw, lanes, smem = list(out)
+                    assert 1 <= G <= 16 and nbuf % G == 0 and nbuf >= 2 and nbuf >= G
+                    assert smem <= 232448
+                    assert fpb >= 1 and (contiguous or fpb == 1)
+                    wpf = 16 // G
+                    assert tw in (1, wpf) and lanes in (2, 4, 8, 16, 32)
+                    assert fpb <= min(64, wpf * 32)  # one solver lane per frame of a slot
+                    assert (tw == 1) == (fpb >= wpf)
+                    if tw != 1:
+                        assert lanes == 32
+                    seen_multi |= fpb > 1
+    assert seen_multi
