@@ -29,6 +29,7 @@
 //     per frame (16 shuffles), then everything -- recentring, polynomial, Newton,
 //     the G_a+G_b-2*lambda cancellation, quaternion -- in float64 on one lane per
 //     frame, kBatch frames at a time.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -272,15 +273,15 @@ constexpr int kGroupBatch = 32;  // frames per solve batch (one per lane)
 struct OvmGroupLayout {
     size_t ref_off, ring_off, sums_off, bar_off, total, stage_bytes;
 };
-__host__ __device__ inline OvmGroupLayout ovm_group_layout(int units, int fpi, int stages)
+__host__ __device__ inline OvmGroupLayout ovm_group_layout(int units, int fpi, int stages, int warps)
 {
     OvmGroupLayout G;
     G.stage_bytes = (size_t)fpi * units * 48;
     G.ref_off = 0;
     G.ring_off = align_up((size_t)units * 48, 128);
-    G.sums_off = G.ring_off + (size_t)kWarpsPerCta * stages * G.stage_bytes;
-    G.bar_off = align_up(G.sums_off + (size_t)kWarpsPerCta * kGroupBatch * kSumStride * sizeof(float), 8);
-    G.total = G.bar_off + ((size_t)kWarpsPerCta * stages + 1) * sizeof(uint64_t);
+    G.sums_off = G.ring_off + (size_t)warps * stages * G.stage_bytes;
+    G.bar_off = align_up(G.sums_off + (size_t)warps * kGroupBatch * kSumStride * sizeof(float), 8);
+    G.total = G.bar_off + ((size_t)warps * stages + 1) * sizeof(uint64_t);
     return G;
 }
 
@@ -290,14 +291,15 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_group_kernel(const OvmP
     constexpr int FPI = 32 / L;  // frames per warp iteration
     extern __shared__ __align__(128) unsigned char smem[];
     const int units = p.total_units;
-    const OvmGroupLayout G = ovm_group_layout(units, FPI, p.stages);
+    const int n_warps = blockDim.x >> 5;  // 16 for short frames, fewer when two ring stages of 32/L frames need more room
+    const OvmGroupLayout G = ovm_group_layout(units, FPI, p.stages, n_warps);
     const float4* ref_s = reinterpret_cast<const float4*>(smem + G.ref_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.bar_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / L, j = lane % L;
     unsigned char* ring = smem + G.ring_off + (size_t)warp * p.stages * G.stage_bytes;
     uint64_t* my_bars = bars + warp * p.stages;
-    uint64_t* ref_bar = bars + kWarpsPerCta * p.stages;
+    uint64_t* ref_bar = bars + n_warps * p.stages;
     float* sums = reinterpret_cast<float*>(smem + G.sums_off) + warp * kGroupBatch * kSumStride;
     const uint32_t frame_bytes = (uint32_t)units * 48u;
 
@@ -311,8 +313,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_group_kernel(const OvmP
         bulk_g2s(smem + G.ref_off, p.ref, frame_bytes, ref_bar);
     }
 
-    const int64_t W = (int64_t)gridDim.x * kWarpsPerCta;
-    const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t W = (int64_t)gridDim.x * n_warps;
+    const int64_t gw = (int64_t)blockIdx.x * n_warps + warp;
     const int64_t f_begin = p.n_frames * gw / W, f_end = p.n_frames * (gw + 1) / W;
     const int64_t n_iter = (f_end - f_begin + FPI - 1) / FPI;
     const uint64_t pol = l2_policy_evict_first();
@@ -487,49 +489,67 @@ cudaError_t launch_ovm_tma(const OvmParams& p, bool precentered, int sm_count, c
 }
 
 template <int L>
-static cudaError_t launch_group_L(const OvmParams& p, bool precentered, int sm_count, cudaStream_t st)
+static cudaError_t launch_group_L(const OvmParams& p, bool precentered, int sm_count, int warps, cudaStream_t st)
 {
-    const OvmGroupLayout G = ovm_group_layout(p.total_units, 32 / L, p.stages);
+    const OvmGroupLayout G = ovm_group_layout(p.total_units, 32 / L, p.stages, warps);
     auto kern = precentered ? ovm_group_kernel<L, true> : ovm_group_kernel<L, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
     if (e != cudaSuccess) return e;
     int64_t ctas = sm_count;
-    const int64_t need = (p.n_frames + kWarpsPerCta * (32 / L) - 1) / (kWarpsPerCta * (32 / L));
+    const int64_t need = (p.n_frames + warps * (32 / L) - 1) / (warps * (32 / L));
     if (ctas > need) ctas = need;
-    kern<<<(unsigned)ctas, kThreadsPerCta, G.total, st>>>(p);
+    kern<<<(unsigned)ctas, warps * 32, G.total, st>>>(p);
     return cudaGetLastError();
 }
 
-// Short-frame path.  Returns false (and launches nothing) when the shape is not eligible.
+// Short- and mid-size-frame path.  Returns false (and launches nothing) when the shape is not eligible.
+//   frames <= 3 KB (256 atoms): 16 warps, the fewest lanes per frame (= most frames per bulk copy and per reduction) whose
+//     per-warp ring still holds >= 2 stages;
+//   frames <= 8.25 KB (704 atoms): 16 lanes per frame (two frames per warp pass, 94 % of the lanes busy at N = 300 against
+//     78 % for a warp per frame, one reduction and one copy per two frames) on as many warps (15 ... 6) as leave every
+//     warp a two-stage ring of frame pairs: N = 300 0.67x -> 0.98x of HBM peak, N = 516 0.77x -> 1.01x.
 bool launch_ovm_group(OvmParams& p, bool precentered, int sm_count, cudaStream_t st, cudaError_t* err)
 {
     p.total_units = (p.n_atoms + 3) / 4;
     const size_t frame_bytes = (size_t)p.total_units * 48;
-    if (p.frame_stride != (int64_t)p.total_units * 12 || frame_bytes > 3072 || p.n_seg > 1) return false;
+    size_t max_bytes = 8448;  // 704 atoms: measured 0.97-1.05x of HBM peak up to here, the chunked kernel wins from ~800 atoms
+    if (const char* mb = getenv("B200RMSD_GROUP_MAX_BYTES")) max_bytes = (size_t)atol(mb);  // development override
+    if (p.frame_stride != (int64_t)p.total_units * 12 || frame_bytes > max_bytes || p.n_seg > 1) return false;
     const size_t budget = 232448;
-    const size_t fixed = align_up(frame_bytes, 128) + (size_t)kWarpsPerCta * kGroupBatch * kSumStride * sizeof(float) + 1024;
-    const size_t per_warp = (budget - fixed) / kWarpsPerCta;
-    // fewest lanes per frame (= most frames per bulk copy and per reduction) whose ring still holds >= 2 stages
-    int Lsel = 0, stages = 0;
+    auto per_warp_bytes = [&](int warps) {
+        const size_t fixed = align_up(frame_bytes, 128) + (size_t)warps * kGroupBatch * kSumStride * sizeof(float) + 1024;
+        return (budget - fixed) / warps;
+    };
+    int Lsel = 0, stages = 0, warps = kWarpsPerCta;
     for (int L = 2; L <= 16; L <<= 1) {
-        const size_t stage_bytes = (size_t)(32 / L) * frame_bytes;
-        const int st_n = (int)(per_warp / stage_bytes);
+        const int st_n = (int)(per_warp_bytes(warps) / ((size_t)(32 / L) * frame_bytes));
         if (st_n >= 2) { Lsel = L; stages = st_n > 4 ? 4 : st_n; break; }
+    }
+    if (Lsel == 0) {
+        for (warps = kWarpsPerCta - 1; warps >= 4; --warps)
+            if (per_warp_bytes(warps) / (2 * frame_bytes) >= 2) { Lsel = 16; stages = 2; break; }
     }
     if (const char* force = getenv("B200RMSD_GROUP_LANES")) {  // development override
         const int L = atoi(force);
         if (L == 2 || L == 4 || L == 8 || L == 16) {
-            const int st_n = (int)(per_warp / ((size_t)(32 / L) * frame_bytes));
-            if (st_n >= 2) { Lsel = L; stages = st_n > 4 ? 4 : st_n; }
+            const int st_n = (int)(per_warp_bytes(kWarpsPerCta) / ((size_t)(32 / L) * frame_bytes));
+            if (st_n >= 2) { Lsel = L; stages = st_n > 4 ? 4 : st_n; warps = kWarpsPerCta; }
+        }
+    }
+    if (const char* force = getenv("B200RMSD_GROUP_WARPS")) {  // development override: warps per CTA for L = 16
+        const int w = atoi(force);
+        if (w >= 4 && w <= kWarpsPerCta && per_warp_bytes(w) / (2 * frame_bytes) >= 2) {
+            Lsel = 16; warps = w;
+            stages = (int)std::min<size_t>(4, per_warp_bytes(w) / (2 * frame_bytes));
         }
     }
     if (Lsel == 0) return false;
     p.stages = stages;
     switch (Lsel) {
-        case 2: *err = launch_group_L<2>(p, precentered, sm_count, st); break;
-        case 4: *err = launch_group_L<4>(p, precentered, sm_count, st); break;
-        case 8: *err = launch_group_L<8>(p, precentered, sm_count, st); break;
-        default: *err = launch_group_L<16>(p, precentered, sm_count, st); break;
+        case 2: *err = launch_group_L<2>(p, precentered, sm_count, warps, st); break;
+        case 4: *err = launch_group_L<4>(p, precentered, sm_count, warps, st); break;
+        case 8: *err = launch_group_L<8>(p, precentered, sm_count, warps, st); break;
+        default: *err = launch_group_L<16>(p, precentered, sm_count, warps, st); break;
     }
     return true;
 }

@@ -1,4 +1,5 @@
-"""One-vs-many throughput vs atom count (development aid): python tools/ovm_sweep.py [N ...]"""
+"""One-vs-many throughput vs atom count (development aid): python tools/ovm_sweep.py [--geom] [N ...]
+   --geom also tries the development overrides of the short/mid-frame kernel (lanes per frame, warps per CTA)."""
 import json, os, sys
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import torch
@@ -7,7 +8,8 @@ from mdtraj_b200 import _capi
 from mdtraj_b200.device import _Scratch, _stream_ptr, prepare_reference
 
 def main():
-    Ns = [int(a) for a in sys.argv[1:]] or [22, 50, 100, 200, 300, 500, 1000]
+    geom = "--geom" in sys.argv
+    Ns = [int(a) for a in sys.argv[1:] if a != "--geom"] or [22, 50, 100, 200, 300, 500, 1000]
     dev = torch.device("cuda", 0)
     L = _capi.lib()
     for N in Ns:
@@ -22,15 +24,25 @@ def main():
             _capi.check(L.b200rmsd_rmsd_dev(dt.xyz_dev.data_ptr(), F, N, dt.frame_stride, None, N, prep.ref.data_ptr(),
                                             prep.stats.data_ptr(), None, 0, out.data_ptr(), None, None, None,
                                             scratch.data_ptr(), scratch.numel(), stream), "rmsd_dev")
-        for _ in range(3): run()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10): run()
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        print(json.dumps({"N": N, "F": F, "ms": round(ms, 4), "frames_per_s": F / ms * 1e3,
-                          "GBs_algorithmic": F * N * 12 / ms / 1e6, "GBs_padded": F * n_pad * 12 / ms / 1e6}))
+        envs = [{}]
+        if geom:
+            envs.append({"B200RMSD_NO_GROUP": "1"})
+            envs += [{"B200RMSD_GROUP_LANES": str(l)} for l in (2, 4, 8, 16)] if n_pad * 12 <= 3072 else \
+                    [{"B200RMSD_GROUP_WARPS": str(w), "B200RMSD_GROUP_MAX_BYTES": "14000"} for w in (4, 5, 6, 8, 10, 12)]
+        for env in envs:
+            for k in ("B200RMSD_NO_GROUP", "B200RMSD_GROUP_LANES", "B200RMSD_GROUP_WARPS", "B200RMSD_GROUP_MAX_BYTES"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            for _ in range(3): run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10): run()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print(json.dumps({"N": N, "F": F, "env": env, "ms": round(ms, 4), "frames_per_s": F / ms * 1e3,
+                              "GBs_algorithmic": F * N * 12 / ms / 1e6, "GBs_padded": F * n_pad * 12 / ms / 1e6,
+                              "frac": round(F * n_pad * 12 / ms / 1e6 / 6540.8, 3)}), flush=True)
         del dt, out
 
 if __name__ == "__main__":
