@@ -262,25 +262,11 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
                     }
                 } else {
                     const float4* ys = reinterpret_cast<const float4*>(ref_s);
+#pragma unroll 2
                     for (int u = ttid; u < units_t; u += tthreads) {
                         const float4 a0v = xs[3 * u], a1v = xs[3 * u + 1], a2v = xs[3 * u + 2];
                         const float4 b0v = ys[3 * u], b1v = ys[3 * u + 1], b2v = ys[3 * u + 2];
-                        const int nvalid = p.n_atoms - 4 * u;
-                        const float ax[4] = {a0v.x, a0v.w, a1v.z, a2v.y}, ay[4] = {a0v.y, a1v.x, a1v.w, a2v.z},
-                                    az[4] = {a0v.z, a1v.y, a2v.x, a2v.w};
-                        const float bx[4] = {b0v.x, b0v.w, b1v.z, b2v.y}, by[4] = {b0v.y, b1v.x, b1v.w, b2v.z},
-                                    bz[4] = {b0v.z, b1v.y, b2v.x, b2v.w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (q < nvalid) {
-                                const float dx = ax[q] - px, dy = ay[q] - py, dz = az[q] - pz;
-                                v[0] += dx; v[1] += dy; v[2] += dz;
-                                v[3] = fmaf(dx, dx, v[3]); v[3] = fmaf(dy, dy, v[3]); v[3] = fmaf(dz, dz, v[3]);
-                                v[4] = fmaf(dx, bx[q], v[4]); v[5] = fmaf(dx, by[q], v[5]); v[6] = fmaf(dx, bz[q], v[6]);
-                                v[7] = fmaf(dy, bx[q], v[7]); v[8] = fmaf(dy, by[q], v[8]); v[9] = fmaf(dy, bz[q], v[9]);
-                                v[10] = fmaf(dz, bx[q], v[10]); v[11] = fmaf(dz, by[q], v[11]); v[12] = fmaf(dz, bz[q], v[12]);
-                            }
-                        }
+                        acc_unit<false>(v, a0v, a1v, a2v, b0v, b1v, b2v, px, py, pz, p.n_atoms - 4 * u);
                     }
                 }
                 if (ttid == 0 && act) { v[13] = px; v[14] = py; v[15] = pz; }

@@ -82,38 +82,6 @@ __device__ __forceinline__ void finish_frame(const double rec[16], int64_t f, co
     }
 }
 
-// accumulate one atom
-template <bool PRE>
-__device__ __forceinline__ void acc_atom(float (&v)[16], float ax, float ay, float az, float bx, float by, float bz,
-                                         float px, float py, float pz)
-{
-    if (!PRE) {
-        ax -= px; ay -= py; az -= pz;
-        v[0] += ax; v[1] += ay; v[2] += az;
-        v[3] = fmaf(ax, ax, v[3]); v[3] = fmaf(ay, ay, v[3]); v[3] = fmaf(az, az, v[3]);
-    }
-    v[4] = fmaf(ax, bx, v[4]);   v[5] = fmaf(ax, by, v[5]);   v[6] = fmaf(ax, bz, v[6]);
-    v[7] = fmaf(ay, bx, v[7]);   v[8] = fmaf(ay, by, v[8]);   v[9] = fmaf(ay, bz, v[9]);
-    v[10] = fmaf(az, bx, v[10]); v[11] = fmaf(az, by, v[11]); v[12] = fmaf(az, bz, v[12]);
-}
-
-// one unit = 4 atoms held in 3 float4 (x0 y0 z0 x1 | y1 z1 x2 y2 | z2 x3 y3 z3)
-template <bool PRE>
-__device__ __forceinline__ void acc_unit(float (&v)[16], const float4& a0, const float4& a1, const float4& a2,
-                                         const float4& b0, const float4& b1, const float4& b2, float px, float py,
-                                         float pz, int nvalid)
-{
-    acc_atom<PRE>(v, a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, px, py, pz);
-    if (nvalid >= 4) {
-        acc_atom<PRE>(v, a0.w, a1.x, a1.y, b0.w, b1.x, b1.y, px, py, pz);
-        acc_atom<PRE>(v, a1.z, a1.w, a2.x, b1.z, b1.w, b2.x, px, py, pz);
-        acc_atom<PRE>(v, a2.y, a2.z, a2.w, b2.y, b2.z, b2.w, px, py, pz);
-    } else {  // ragged last unit of the frame: padding atoms must not see the pivot
-        if (nvalid > 1) acc_atom<PRE>(v, a0.w, a1.x, a1.y, b0.w, b1.x, b1.y, px, py, pz);
-        if (nvalid > 2) acc_atom<PRE>(v, a1.z, a1.w, a2.x, b1.z, b1.w, b2.x, px, py, pz);
-    }
-}
-
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct OvmSmemLayout {
