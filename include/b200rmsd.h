@@ -166,7 +166,9 @@ int b200rmsd_allpairs_rows_dev(const void* workspace, size_t workspace_bytes, in
                                int64_t row0, int64_t row1, float* out, int64_t ld, unsigned flags, void* stream);
 
 /* One rectangular block of the matrix: rows [row0,row1) x columns [col0,col1), written at
- * out[(i-row0)*ld + j] (absolute column index j, ld >= col1).  When out_t != NULL the transposed block is also
+ * out[(i-row0)*ld + j] with the absolute column index j: `out` is the address of element (row0, column 0) of a matrix
+ * with leading dimension ld.  Only columns [col0,col1) are touched, so a caller that keeps just that window passes
+ * window - col0 and ld >= col1 - col0.  When out_t != NULL the transposed block is also
  * written, out_t[(j-col0)*ld_t + (i-row0)]: D is symmetric, so a rank that computes block (r,s) can ship out_t to
  * the owner of row block s instead of that rank recomputing it (mdtraj_b200.distributed.rmsd_matrix_sharded).
  * A square block on the diagonal (row range == column range, out_t == NULL) computes each unordered pair once and
@@ -174,6 +176,30 @@ int b200rmsd_allpairs_rows_dev(const void* workspace, size_t workspace_bytes, in
 int b200rmsd_allpairs_block_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,
                                 int64_t row0, int64_t row1, int64_t col0, int64_t col1, float* out, int64_t ld,
                                 float* out_t, int64_t ld_t, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------ consumers of the matrix */
+
+/* The reference's example notebooks post-process the (F,F) matrix on the host with numpy / scipy.  These entry points
+ * run the same reductions over a device-resident float32 matrix D (rows x cols, leading dimension ld), one read of the
+ * matrix each, so that a 40 GB matrix never has to cross PCIe.
+ *
+ * matrix_moments: out2[0] = sum d_ij, out2[1] = sum d_ij^2 (float64; zeroed by the call) -- what distances.std() needs
+ *   (examples/centroids.ipynb:117).  Call once per row block and add, or once on the whole matrix. */
+int b200rmsd_matrix_moments_dev(const float* D, int64_t rows, int64_t cols, int64_t ld, double* out2, void* stream);
+
+/* exp_rowsum: rowsum[i] = (accumulate ? rowsum[i] : 0) + sum_j exp(scale * d_ij), float64 --
+ *   np.exp(-beta * distances / distances.std()).sum(axis=1) with scale = -beta / std (examples/centroids.ipynb:117). */
+int b200rmsd_exp_rowsum_dev(const float* D, int64_t rows, int64_t cols, int64_t ld, float scale, int accumulate,
+                            double* rowsum, void* stream);
+
+/* row_argmin: arg[i] = index of the first minimum of row i, val[i] (may be NULL) = that minimum -- the nearest-leader
+ *   assignment np.argmin(md.rmsd(leaders, frame, 0)) of examples/two-pass-clustering.ipynb (cell 13) for every frame. */
+int b200rmsd_row_argmin_dev(const float* D, int64_t rows, int64_t cols, int64_t ld, int32_t* arg, float* val, void* stream);
+
+/* condense: out[n*i - i*(i+1)/2 + (j-i-1)] = D[i*ld + j] for i < j < n: the condensed form scipy's linkage functions
+ *   take, scipy.spatial.distance.squareform(distances, checks=False) in examples/clustering.ipynb:101.
+ *   out: n*(n-1)/2 floats. */
+int b200rmsd_condense_dev(const float* D, int64_t n, int64_t ld, float* out, void* stream);
 
 /* ------------------------------------------------------------------ host API */
 

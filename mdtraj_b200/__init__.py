@@ -28,6 +28,9 @@ def __getattr__(name):
     if name in ("rmsd_matrix", "rmsd_matrix_device"):
         from . import allpairs
         return getattr(allpairs, name)
+    if name in ("rmsd_condensed", "similarity_scores", "centroid_index", "assign_to_leaders"):
+        from . import clustering
+        return getattr(clustering, name)
     if name == "distributed":
         import importlib
         return importlib.import_module(".distributed", __name__)

@@ -205,7 +205,7 @@ int b200rmsd_allpairs_block_dev(const void* workspace, size_t workspace_bytes, i
                                 float* out_t, int64_t ld_t, unsigned flags, void* stream)
 {
     if (!workspace || !out || n_frames <= 0 || n_sel <= 0 || row0 < 0 || row1 > n_frames || row0 > row1 || col0 < 0 ||
-        col1 > n_frames || col0 > col1 || ld < col1 || (out_t && ld_t < row1 - row0))
+        col1 > n_frames || col0 > col1 || ld < col1 - col0 || (out_t && ld_t < row1 - row0))
         return fail(B200RMSD_EINVAL, "allpairs_block: bad arguments");
     const ApGeometry g = ap_geometry(n_frames, n_sel);
     if (workspace_bytes < g.total) return fail(B200RMSD_EINVAL, "allpairs_block: workspace too small");

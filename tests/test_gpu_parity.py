@@ -509,3 +509,62 @@ def test_allpairs_block_api(mdb, oracle_mod, monkeypatch):
         blk = sq[:, 123:313]
         assert torch.equal(blk, blk.t()) and torch.count_nonzero(torch.diagonal(blk)) == 0
         assert (blk - full[123:313, 123:313]).abs().max().item() < 2e-6
+
+
+# ------------------------------------------------------------------ consumers of the matrix
+def test_clustering_consumers_ala2_known_answers(mdb, golden, ala2):
+    """examples/centroids.ipynb:117 -> centroid index 83 on the heavy atoms; examples/clustering.ipynb:101 -> squareform."""
+    heavy = golden["ala2_heavy_idx"]
+    t = mdb.Trajectory(ala2.copy())
+    assert mdb.centroid_index(t, atom_indices=heavy) == int(golden["ala2_centroid_index"]) == 83
+    Dh = golden["ala2_allpairs_heavy"].astype(np.float64)
+    want = np.exp(-1.0 * Dh / Dh.std()).sum(axis=1)
+    scores, std = mdb.similarity_scores(t, atom_indices=heavy)
+    assert abs(std - Dh.std()) < 1e-6
+    assert_close(scores, want, atol=0, rtol=2e-4, what="similarity scores")  # 1e-5 nm on d ~ 1e-4 relative on exp(-d/std)
+    D = golden["ala2_allpairs"]
+    iu = np.triu_indices(100, k=1)
+    cond = mdb.rmsd_condensed(t)
+    assert cond.dtype == np.float64 and cond.shape == (100 * 99 // 2,)
+    assert_close(cond, D[iu], what="condensed distances == squareform(D)")
+    assert abs(cond.max() - 0.188493) < 5e-6  # clustering.ipynb:73
+
+
+@pytest.mark.parametrize("F,N", [(700, 50), (300, 22)])
+def test_clustering_consumers_vs_numpy(mdb, F, N):
+    """Every reduction against numpy on the same device-computed matrix, on both all-pairs kernels (F >= 512: tcgen05),
+    with and without row blocking."""
+    import torch
+    dt = mdb.DeviceTrajectory.synthetic_iid(F, N, seed=21)
+    g = torch.Generator(device=dt.device); g.manual_seed(3)
+    base = torch.randn((N, 3), generator=g, device=dt.device)
+    dt.xyz_dev[:, :N] = base[None] + 0.3 * dt.xyz_dev[:, :N]
+    D = mdb.rmsd_matrix(dt).astype(np.float64)
+    cond = mdb.rmsd_condensed(dt, dtype=np.float32)
+    assert np.array_equal(cond, D[np.triu_indices(F, k=1)].astype(np.float32))
+    want = np.exp(-2.0 * D / D.std()).sum(axis=1)
+    for max_bytes in (1 << 40, 4 * F * 97):  # one block; many ragged row blocks
+        scores, std = mdb.similarity_scores(dt, beta=2.0, max_matrix_bytes=max_bytes)
+        assert abs(std - D.std()) < 1e-9 * max(1.0, D.std()) + 1e-7
+        assert_close(scores, want, atol=0, rtol=1e-5, what="similarity scores")
+        assert mdb.centroid_index(dt, beta=2.0, max_matrix_bytes=max_bytes) == int(want.argmax())
+    # nearest leader: leaders = frames 5, 77, 200 (+ a duplicate to pin first-minimum semantics)
+    lead_idx = [5, 77, 200, 77]
+    leaders = mdb.DeviceTrajectory(dt.xyz_dev[lead_idx].clone(), N)
+    for max_bytes in (1 << 40, 4 * len(lead_idx) * 33):
+        labels, dist = mdb.assign_to_leaders(dt, leaders, max_matrix_bytes=max_bytes)
+        block = D[:, lead_idx]
+        assert labels.dtype == np.int32 and labels.shape == (F,)
+        # a frame against a COPY of itself has true RMSD 0, where the float32 sums leave sqrt-amplified noise (~1e-3 nm on
+        # the 3xTF32 path) while D's diagonal is exactly 0 by the same-frame shortcut: leave those three rows out
+        m = ~np.isin(np.arange(F), lead_idx)
+        assert_close(dist[m], block.min(axis=1)[m], atol=2e-6, what="distance to the nearest leader")
+        assert np.all(dist[~m] < 5e-3)
+        # ties between near-equal leaders may resolve differently at the 1e-6 level: compare through the distances
+        assert np.all(np.abs(block[np.arange(F), labels] - block.min(axis=1)) < 2e-6)
+        assert labels[77] == 1 and labels[5] == 0 and labels[200] == 2  # the duplicate never wins over the first minimum
+    one = mdb.Trajectory(dt.xyz[:50].copy())
+    want_lab = np.array([np.argmin(mdb.rmsd(leaders, mdb.DeviceTrajectory.from_trajectory(one), i)) for i in range(50)])
+    got = mdb.assign_to_leaders(one, leaders)[0]
+    agree = got == want_lab
+    assert agree.mean() > 0.95 and np.all(np.abs(D[:50][:, lead_idx][np.arange(50), got] - D[:50][:, lead_idx].min(1)) < 2e-6)
