@@ -79,6 +79,54 @@ def rmsd_sharded(target, reference, frame=0, atom_indices=None, ref_atom_indices
     return full
 
 
+def gather_rows(local, n_total: int, group=None):
+    """All-gather ragged per-rank row blocks ``(n_local, ...)`` float32 into the full ``(n_total, ...)`` array."""
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bounds = all_shard_bounds(n_total, world)
+    is_tensor = isinstance(local, torch.Tensor)
+    t = local if is_tensor else torch.from_numpy(np.ascontiguousarray(local, dtype=np.float32))
+    if not t.is_cuda and dist.get_backend(group) == "nccl":
+        t = t.to(torch.device("cuda", torch.cuda.current_device()))
+    assert t.shape[0] == bounds[rank][1] - bounds[rank][0], "local block does not match this rank's shard"
+    width = max(b - a for a, b in bounds)
+    padded = torch.zeros((width,) + tuple(t.shape[1:]), dtype=torch.float32, device=t.device)
+    padded[: t.shape[0]] = t
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    full = torch.cat([p[: b - a] for p, (a, b) in zip(parts, bounds)])
+    return full if is_tensor else full.cpu().numpy()
+
+
+def superpose_sharded(traj, reference, frame=0, atom_indices=None, ref_atom_indices=None, group=None, gather=True,
+                      shard_fn=None):
+    """``Trajectory.superpose`` with the frames of ``traj`` split across the ranks of ``group`` (SURVEY.md section 8(e):
+    frames are independent, the reference frame is replicated, there is no exchange step).  ``traj`` is the whole host
+    trajectory on every rank; each rank superposes its contiguous block in place.  With ``gather=True`` the blocks are
+    all-gathered so that ``traj.xyz`` is the fully superposed trajectory on every rank; otherwise only
+    ``traj.xyz[a:b]`` (the returned bounds) is valid.  ``shard_fn(sub, reference, frame, atom_indices,
+    ref_atom_indices)`` defaults to ``Trajectory.superpose`` of this package."""
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    F = traj.xyz.shape[0]
+    a, b = shard_bounds(F, rank, world)
+    from .trajectory import Trajectory
+    ref_frame = np.array(reference.xyz[frame], dtype=np.float32, copy=True)  # before this rank's block is modified
+    ref = Trajectory(ref_frame[None])
+    sub = Trajectory(np.ascontiguousarray(traj.xyz[a:b], dtype=np.float32))
+    if b > a:
+        if shard_fn is None:
+            sub.superpose(ref, 0, atom_indices, ref_atom_indices)
+        else:
+            shard_fn(sub, ref, 0, atom_indices, ref_atom_indices)
+    if gather:
+        traj.xyz = gather_rows(sub.xyz, F, group)
+    else:
+        traj.xyz[a:b] = sub.xyz
+    return a, b
+
+
 def broadcast_frames(xyz_dev, src=0, group=None):
     """Broadcast a staged trajectory tensor from ``src`` to every rank (NCCL over NVLink on GPUs)."""
     dist = _dist()

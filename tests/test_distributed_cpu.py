@@ -55,3 +55,44 @@ def test_rmsd_sharded_world2(F):
     for rank, full, blk in res:
         assert full.shape == (F,) and np.array_equal(full, want)  # identical to the unsharded result, bit for bit
         assert np.array_equal(blk, np.concatenate([np.zeros(F // 2, np.float32), np.ones(F - F // 2, np.float32)]))
+
+
+def _worker_superpose(rank, world, port, F, N, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import mdtraj_b200 as mdb
+        from mdtraj_b200 import distributed as D
+        from oracle import oracle as O
+        X = O.synth_md(F, N, seed=9)
+        t = mdb.Trajectory(X.copy())
+        idx = np.arange(0, N, 2)
+
+        def shard_fn(sub, ref, frame, ai, rai):  # stand-in for this rank's GPU
+            sub.xyz = O.superpose(sub.xyz, ref.xyz, frame, ai, rai)
+        bounds = D.superpose_sharded(t, t, 4, atom_indices=idx, shard_fn=shard_fn)
+        q.put((rank, bounds, np.asarray(t.xyz).copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_superpose_sharded_world2():
+    """Frames split over two ranks, reference frame replicated, blocks all-gathered: identical to the unsharded call."""
+    from oracle import oracle as O
+    F, N, world = 11, 24, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_superpose, args=(r, world, port, F, N, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    X = O.synth_md(F, N, seed=9)
+    want = O.superpose(X, X, 4, np.arange(0, N, 2))
+    assert [r[1] for r in res] == [(0, 5), (5, 11)]
+    for rank, bounds, xyz in res:
+        assert xyz.shape == (F, N, 3) and np.array_equal(xyz, want)
