@@ -161,6 +161,15 @@ def cpu_reference_run(workload, steps, warmup, sample_frames=None):
 
 
 # ------------------------------------------------------------------------------------------------
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture."""
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(tpath):
+        return None
+    with open(tpath) as fh:
+        return json.load(fh).get(workload)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,7 +190,11 @@ def main():
     if args.frames:
         F = args.frames
     config = {"workload": desc, "frames_per_gpu": F, "n_atoms": N, "frame": 0,
-              "l2_policy": "inputs (%.1f GB per GPU) are larger than the 126 MB L2" % (F * N * 12 / 1e9)}
+              "l2_policy": ("the %.1f GB matrix written by every step flushes the 126 MB L2 between steps; the operands "
+                            "(%.2f GB) are meant to stay L2-resident inside a step" % (F * F * 4 / 1e9 / max(world, 1),
+                                                                                       F * N * 12 / 1e9))
+              if args.workload == "allpairs" else
+              "inputs (%.1f GB per GPU) are larger than the 126 MB L2" % (F * N * 12 / 1e9)}
 
     # ---------------- reference arm: CPU only, rank 0 only
     if args.impl == "reference":
@@ -268,7 +281,7 @@ def main():
                 kernel_events.append((e0, e1))
         units_per_step = F
         algo_bytes = 24.0 * N * F
-        dominant = "superpose (rotation + apply kernels)"
+        dominant = "frame_resident_kernel"
     else:  # allpairs
         from mdtraj_b200 import allpairs as AP
         rows_per_rank = F // world
@@ -325,7 +338,7 @@ def main():
 
     # ---------------- end-to-end through the public API with pinned host buffers
     e2e = None
-    if not args.no_e2e and args.workload in ("ovm", "ovm25k", "ala2", "superpose"):
+    if not args.no_e2e:
         host = torch.empty((F, N, 3), dtype=torch.float32, pin_memory=True)
         host.copy_(dt.xyz_dev[:, :N, :])
         torch.cuda.synchronize(dev)
@@ -343,6 +356,21 @@ def main():
                 return float(ht.xyz[0, 0, 0])
             h2d = F * N * 12 + N * 12
             d2h = F * N * 12
+        elif args.workload == "allpairs":
+            # host frames in, this rank's rows of the matrix out to page-locked host memory
+            host_out = torch.empty((r1 - r0, F), dtype=torch.float32, pin_memory=True)
+
+            def e2e_step():
+                if world == 1:
+                    mdb.rmsd_matrix(ht, out=host_out.numpy())  # row blocks, copies overlapped with compute
+                else:
+                    dte = mdb.DeviceTrajectory.from_host(ht.xyz, dev) if rank == 0 else \
+                        mdb.DeviceTrajectory(torch.zeros_like(dt.xyz_dev), N)
+                    _, _, blk = DD.rmsd_matrix_sharded(dte, None, broadcast=True, symmetric=True)
+                    host_out.copy_(blk)
+                return float(host_out[0, 1])
+            h2d = F * N * 12
+            d2h = (r1 - r0) * F * 4
         else:
             def e2e_step():
                 return float(mdb.rmsd(ht, ref_host, 0)[-1])
@@ -361,8 +389,9 @@ def main():
         e2e_ms = float(te.item())
         e2e = {"value": units_per_step * world / (e2e_ms * 1e-3), "unit": "rmsd/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
-               "api": "mdtraj_b200.rmsd(host Trajectory) -> b200rmsd_rmsd_host" if args.workload != "superpose"
-               else "Trajectory.superpose -> b200rmsd_superpose_host",
+               "api": {"superpose": "Trajectory.superpose -> b200rmsd_superpose_host",
+                       "allpairs": "mdtraj_b200.rmsd_matrix(host Trajectory, out=page-locked ndarray)"}.get(
+                           args.workload, "mdtraj_b200.rmsd(host Trajectory) -> b200rmsd_rmsd_host"),
                "h2d_GBs": h2d / e2e_ms / 1e6}
         del host
 
@@ -375,11 +404,7 @@ def main():
     roofline = None
     if algo_bytes is not None:
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                traffic = json.load(fh).get(args.workload)
+        traffic = ncu_traffic(args.workload)
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes}
@@ -394,7 +419,7 @@ def main():
         tiles = T * (T + 1) // 2 if world == 1 else T * (T + 1) // 2 / world  # symmetric plan: ~T^2/2 tiles over all ranks
         issued = tiles * 128 * 128 * kpad * 2 * 3 / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": dominant, "achieved": issued, "peak": tpeak, "unit": "TFLOP/s",
-                    "frac": issued / tpeak, "traffic": None, "peak_source": tsrc, "kernel_ms": kern_ms,
+                    "frac": issued / tpeak, "traffic": ncu_traffic("allpairs"), "peak_source": tsrc, "kernel_ms": kern_ms,
                     "useful_tflops": pairs_per_s * 18 * N / 1e12,
                     "note": "achieved = tensor flops actually issued (3 tf32 MMAs per K-step over the computed 128x128 "
                             "tiles; symmetric tiles computed once); useful = 18 * A flops per reported pair"}

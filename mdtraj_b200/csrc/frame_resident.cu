@@ -42,12 +42,13 @@ constexpr int kFrThreads = kFrWarps * 32 + 64;    // + loader warp + storer warp
 constexpr int kRecStride = 25;  // floats per frame record (odd: the solver lanes read one record each, conflict-free)
 
 struct FrLayout {
-    size_t buf_off, ref_off, idx_off, rec_off, cpart_off, bar_off, total;
+    size_t buf_off, ref_off, idx_off, rec_off, dsum_off, cpart_off, bar_off, total;
     size_t buf_bytes;
 };
 __host__ __device__ inline size_t fr_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // rec: one record per (group, frame of the slot, warp of the team): first the 16 float32 partial sums, then -- written by
 // the solver lane of that frame into the team's first record -- the 15 floats of its transform;
+// dsum: when several warps share a frame, their partials combined in float64 (16 per frame, by 16 lanes in parallel);
 // cpart: float64 partials of OP_CENTER, 4 per compute warp
 __host__ __device__ inline FrLayout fr_layout(int n_pad, int nbuf, int n_sel_pad, int n_idx, int G, int fpb, int team_warps,
                                               bool records)
@@ -58,7 +59,8 @@ __host__ __device__ inline FrLayout fr_layout(int n_pad, int nbuf, int n_sel_pad
     L.ref_off = fr_align((size_t)nbuf * L.buf_bytes, 128);
     L.idx_off = L.ref_off + fr_align((size_t)n_sel_pad * 12, 16);
     L.rec_off = fr_align(L.idx_off + (size_t)n_idx * 4, 16);
-    L.cpart_off = fr_align(L.rec_off + (records ? (size_t)G * fpb * team_warps * kRecStride * sizeof(float) : 0), 8);
+    L.dsum_off = fr_align(L.rec_off + (records ? (size_t)G * fpb * team_warps * kRecStride * sizeof(float) : 0), 8);
+    L.cpart_off = L.dsum_off + (records && team_warps > 1 ? (size_t)G * fpb * 16 * sizeof(double) : 0);
     L.bar_off = L.cpart_off + (size_t)kFrWarps * 4 * sizeof(double);
     L.total = L.bar_off + (size_t)(3 * nbuf + 1) * sizeof(uint64_t);
     return L;
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
     int* idx_s = reinterpret_cast<int*>(smem + L.idx_off);
     float* rec_all = reinterpret_cast<float*>(smem + L.rec_off);
     double* cpart_s = reinterpret_cast<double*>(smem + L.cpart_off);
+    double* dsum_s = reinterpret_cast<double*>(smem + L.dsum_off);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* done = full + p.nbuf;
     uint64_t* drained = done + p.nbuf;
@@ -282,17 +285,31 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
                 }
             }
             group_sync(g, wpf);
+            if (tw > 1 && sub == 0) {
+                // several warps per frame: 16 lanes add up the team's partials in float64, one value each (the solver
+                // lane would otherwise convert and add 16*tw numbers one after the other on the critical path)
+                if (lane < 16) {
+                    for (int j = 0; j < cnt; ++j) {
+                        double d = 0.0;
+                        for (int w = 0; w < tw; ++w) d += (double)rec_all[(((size_t)g * fpb + j) * tw + w) * kRecStride + lane];
+                        dsum_s[((size_t)g * fpb + j) * 16 + lane] = d;
+                    }
+                }
+                __syncwarp();
+            }
             // ---- solve: one lane per frame of the slot, side by side
             if (gtid < cnt) {
                 if (gtid == 0) FR_STAMP(s, 1);
                 const int j = gtid;
                 const int64_t f = fbase + j;
                 double rec[16];
+                if (tw > 1) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) rec[q] = 0.0;
-                for (int w = 0; w < tw; ++w)
+                    for (int q = 0; q < 16; ++q) rec[q] = dsum_s[((size_t)g * fpb + j) * 16 + q];
+                } else {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) rec[q] += (double)rec_all[(((size_t)g * fpb + j) * tw + w) * kRecStride + q];
+                    for (int q = 0; q < 16; ++q) rec[q] = (double)rec_all[((size_t)g * fpb + j) * kRecStride + q];
+                }
                 const double invn = 1.0 / (double)p.n_sel;
                 const double mx = rec[0] * invn, my = rec[1] * invn, mz = rec[2] * invn;
                 QcpInput q;

@@ -4,7 +4,8 @@
         tools/multi_gpu_check.py
 
   * one-vs-many: frames sharded across ranks + all_gather == single-GPU result, bit for bit;
-  * all-pairs: frames broadcast over NCCL, each rank's row block == the same rows of the single-GPU matrix.
+  * all-pairs: frames broadcast over NCCL, each rank's row block == the same rows of the single-GPU matrix;
+  * superpose: frames sharded across ranks + all_gather == single-GPU result, bit for bit.
 """
 import os
 import sys
@@ -55,6 +56,13 @@ def main():
     if truth_row is not None:
         got = blk[5 - r0].cpu().numpy()
         assert np.abs(got - truth_row).max() < 5e-6
+    # ---- superpose, frames sharded over ranks, blocks all-gathered over NCCL
+    Xs = rng.standard_normal((1, N, 3), dtype=np.float32) + 0.1 * rng.standard_normal((F, N, 3), dtype=np.float32) + 2.0
+    ts, t1 = mdb.Trajectory(Xs.copy()), mdb.Trajectory(Xs.copy())
+    idx = np.arange(0, N, 3)
+    D.superpose_sharded(ts, ts, 7, atom_indices=idx)
+    t1.superpose(t1, 7, atom_indices=idx)
+    assert np.array_equal(ts.xyz, t1.xyz), "sharded superpose differs from single GPU"
     dist.barrier()
     if rank == 0:
         print(f"multi-GPU check ok on {world} GPUs: one-vs-many shards and all-pairs row blocks match single GPU")
