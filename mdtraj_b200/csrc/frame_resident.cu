@@ -545,7 +545,16 @@ bool fused_config(FusedParams& p, int op)
                 fr_set(p, G, fpb_g, G, fr_one_pass_lanes(G, fpb_g));
             }
         }
-        if (best > 0.0) return true;
+        if (best > 0.0) {
+            // One frame per slot on 8 groups leaves shared memory half empty for 13-22 KB frames (1100-1800 atoms).  More
+            // groups of a single warp each fill it (the cost model does not cover them): measured N=1400 0.80x -> 0.94x
+            // with 12 groups, N=1600 0.90x -> 0.98x with 10; centring N=1400-1600 0.94-0.98x -> 0.97-0.99x with 10.
+            if (p.batch == 8 && p.fpb == 1) {
+                if (op == OP_SUPERPOSE && fr_fits(p, op, 12, 1, 12)) fr_set(p, 12, 1, 12, 32);
+                else if (fr_fits(p, op, 10, 1, 10)) fr_set(p, 10, 1, 10, 32);
+            }
+            return true;
+        }
     } else {
         static const int kGroups[] = {8, 4, 3, 2};
         const int want = (int)(16384 / frame_bytes) < 1 ? 1 : (int)(16384 / frame_bytes);

@@ -446,7 +446,8 @@ def test_rmsf_residue_mode(mdb, oracle_mod):
 
 # ------------------------------------------------------------------ frame-resident kernels at scale
 @pytest.mark.parametrize("F,N,stride", [(6000, 1000, 4), (1500, 5000, 5), (20000, 300, 1), (40000, 22, 1), (700, 8000, 7),
-                                        (30001, 100, 1), (25000, 50, 3), (4001, 1001, 4), (3000, 2000, 1)])
+                                        (30001, 100, 1), (25000, 50, 3), (4001, 1001, 4), (3000, 2000, 1), (2500, 1400, 4),
+                                        (2000, 1600, 1)])
 def test_superpose_and_center_properties_at_scale(mdb, F, N, stride):
     """Every geometry of frame_resident_kernel (8 single-slot groups with 1-64 frames per slot, 2-16 lanes per frame for
     small frames, 3 single-buffer groups for 60 KB frames, partial last slots, the two-pass fallback for frames that do
@@ -568,3 +569,21 @@ def test_clustering_consumers_vs_numpy(mdb, F, N):
     got = mdb.assign_to_leaders(one, leaders)[0]
     agree = got == want_lab
     assert agree.mean() > 0.95 and np.all(np.abs(D[:50][:, lead_idx][np.arange(50), got] - D[:50][:, lead_idx].min(1)) < 2e-6)
+
+
+def test_rmsd_matrix_into_host_buffer(mdb):
+    """rmsd_matrix(out=...) produces the matrix in row blocks whose device->host copies overlap the next block's
+    compute: same matrix as the single-call path (entries of the mirrored half agree to rounding), page-locked or not."""
+    import torch
+    F, N = 900, 64
+    dt = mdb.DeviceTrajectory.synthetic_iid(F, N, seed=8)
+    want = mdb.rmsd_matrix(dt)
+    for pinned in (True, False):
+        host = torch.empty((F, F), dtype=torch.float32, pin_memory=pinned)
+        host.fill_(-1.0)
+        got = mdb.rmsd_matrix(dt, out=host.numpy(), row_block=128)
+        assert got is not None and got.shape == (F, F) and np.shares_memory(got, host.numpy())
+        assert_close(got, want, atol=2e-6, what="blocked matrix vs single call")
+        assert np.all(np.diag(got) == 0.0)
+    with pytest.raises(ValueError):
+        mdb.rmsd_matrix(dt, out=np.empty((F, F), dtype=np.float64))

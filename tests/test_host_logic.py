@@ -164,7 +164,7 @@ def test_frame_resident_geometry_invariants():
                     wpf = 16 // G
                     assert tw in (1, wpf) and lanes in (2, 4, 8, 16, 32)
                     assert fpb <= min(64, wpf * 32)  # one solver lane per frame of a slot
-                    assert (tw == 1) == (fpb >= wpf)
+                    assert (tw == 1) == (fpb >= wpf) and G * wpf <= 16
                     if tw != 1:
                         assert lanes == 32
                     seen_multi |= fpb > 1

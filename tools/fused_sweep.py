@@ -33,6 +33,8 @@ def configs(N):
     out = [None]
     if quick:
         return out
+    if os.environ.get("SWEEP_WIDE") == "1":  # many single-warp groups
+        return out + [(f, G, G, 0) for G in (8, 10, 12, 16) for f in (1, 2, 3, 4, 6, 8)]
     for fpb in [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16, 18, 20, 22, 24, 28, 32, 40, 48, 56, 64]:
         if fpb * N * 12 > 100000:
             continue
