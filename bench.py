@@ -13,6 +13,7 @@ reference = frame 0.  With N > 1 (torchrun, one rank per GPU) every rank owns it
              H2D of every frame and D2H of the result inside the timed region
   roofline   dominant kernel (ovm_tma_kernel): algorithmic bytes 12*N per frame / CUDA-event launch time
   cpu_baseline  the compiled reference (oracle/_ref) on this box's host cores, bounded sample
+  parity     GPU path vs the CPU reference vs the float64 truth on a sample of the same shape (outside the timed region)
 
 --impl reference times the reference's own CPU implementation (oracle/_ref = its C++ sources compiled
 in place + our OpenMP loop shell; falls back to the C port oracle/liboracle.so if _ref was never built).
@@ -158,6 +159,50 @@ def cpu_reference_run(workload, steps, warmup, sample_frames=None):
     info = {"value": units / dt, "unit": "rmsd/s", "cores": threads, "kind": kind, "sample": sample,
             "host_cpus": os.cpu_count(), "ms_per_step": dt * 1e3}
     return units / dt, info
+
+
+def parity_block(workload, mdb):
+    """GPU path (through the public host API) against the CPU reference and the float64 truth on a sample of the
+    workload's shape (SURVEY.md section 8(d) "parity checks in the bench").  The oracle is the checker here, never the
+    thing measured.  Tolerance: 1e-5 nm absolute or 1e-4 relative (BASELINE.json north_star)."""
+    from oracle import oracle as O
+    F_full, N, _ = WORKLOADS[workload]
+    kind = "reference" if O.ref_available() else "port"
+    tol_abs, tol_rel = 1e-5, 1e-4
+
+    def verdict(got, ref, truth, what, n):
+        got, ref, truth = (np.asarray(v, dtype=np.float64) for v in (got, ref, truth))
+        e_gr, e_gt, e_rt = np.abs(got - ref), np.abs(got - truth), np.abs(ref - truth)
+        ok = bool(np.all((e_gr <= np.maximum(tol_abs, tol_rel * np.abs(ref))) | (e_gt <= np.maximum(tol_abs, e_rt))))
+        return {"what": what, "n": int(n), "max_abs_gpu_vs_ref": float(e_gr.max()), "max_abs_gpu_vs_truth": float(e_gt.max()),
+                "max_abs_ref_vs_truth": float(e_rt.max()), "tolerance": "1e-5 nm abs or 1e-4 rel", "checker": kind,
+                "pass": ok}
+    if workload == "allpairs":
+        F, rows = 4000, 8
+        X = O.synth_iid(F, N, seed=14)
+        D = mdb.rmsd_matrix(mdb.Trajectory(X.copy()))
+        Xc = X.copy()
+        tr = O.center_and_trace(Xc, kind)
+        ref = np.stack([O.one_vs_many_centered(Xc, tr, Xc[i], tr[i], impl=kind) for i in range(rows)])
+        truth = np.stack([O.truth_rmsd_batch(X, X[i]) for i in range(rows)])
+        m = np.ones((rows, F), bool); m[np.arange(rows), np.arange(rows)] = False  # a frame against itself: noise floor
+        return verdict(D[:rows][m], ref[m], truth[m], f"{rows} rows of the {F}x{F} matrix, {N} atoms, iid frames", m.sum())
+    if workload == "superpose":
+        F = 512
+        X = O.synth_md(F, N, seed=14)  # MD-like frames: rotations are well conditioned (SURVEY.md section 8(d))
+        idx = np.arange(0, N, 5)
+        t = mdb.Trajectory(X.copy())
+        t.superpose(mdb.Trajectory(X.copy()), 0, atom_indices=idx)
+        ref = O.superpose(X, X, 0, idx, impl=kind)
+        truth = O.truth_superpose(X, X, 0, idx)[0]
+        return verdict(t.xyz, ref, truth, f"superposed coordinates of {F} MD-like frames x {N} atoms, every 5th atom aligned",
+                       F * N * 3)
+    F = int(min(F_full, max(64, min(10_000, 2.4e8 // (N * 12)))))
+    X = O.synth_iid(F, N, seed=14)
+    got = mdb.rmsd(mdb.Trajectory(X.copy()), mdb.Trajectory(X.copy()), 0)
+    ref = O.rmsd(X, X, 0, impl=kind)
+    truth = O.truth_rmsd_batch(X, X[0])
+    return verdict(got[1:], ref[1:], truth[1:], f"md.rmsd(t,t,0) on {F} iid frames x {N} atoms (frame 0 itself left out)", F - 1)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -425,16 +470,21 @@ def main():
                             "tiles; symmetric tiles computed once); useful = 18 * A flops per reported pair"}
 
     cpu = None
+    parity = None
     if not args.no_cpu and args.gpus == 1:
         try:
             _, cpu = cpu_reference_run(args.workload, 3, 1)
         except Exception as e:  # noqa: BLE001
             cpu = {"error": repr(e)}
+        try:
+            parity = parity_block(args.workload, mdb)
+        except Exception as e:  # noqa: BLE001
+            parity = {"error": repr(e)}
 
     line = {"metric": METRIC, "value": value, "unit": "rmsd/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu}
+            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
