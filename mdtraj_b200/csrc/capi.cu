@@ -216,6 +216,15 @@ int b200rmsd_rmsd_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t f
 
     const int n_pad = (n_atoms + 3) / 4 * 4;
     const bool staged = aligned16(xyz) && aligned16(ref) && frame_stride % 4 == 0 && frame_stride >= 3 * (int64_t)n_pad;
+    if (idx && staged && !pre && !env_int("B200RMSD_FORCE_GATHER", 0) && !env_int("B200RMSD_NO_GROUP", 0)) {
+        // small frames with a selection: stage whole frames and gather in shared memory
+        p.frame_atoms = n_atoms;
+        cudaError_t ge = cudaSuccess;
+        if (launch_ovm_group(p, false, sm, (cudaStream_t)stream, &ge)) {
+            CU(ge);
+            return 0;
+        }
+    }
     if (!idx && staged && !env_int("B200RMSD_FORCE_GATHER", 0)) {
         if (!env_int("B200RMSD_NO_GROUP", 0)) {  // short frames: several frames per warp iteration
             cudaError_t ge = cudaSuccess;

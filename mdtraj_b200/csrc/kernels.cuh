@@ -25,6 +25,7 @@ struct OvmParams {
     int64_t frame_stride;   // floats between consecutive frames (multiple of 4)
     int n_atoms;            // real atoms taking part (== n_sel when idx != nullptr)
     const int* idx;         // optional atom selection (gather path), length n_atoms
+    int frame_atoms;        // atoms per frame in memory (>= every index); 0: same as n_atoms (no selection)
     const float* ref;       // centred reference selection, (n_pad,3) floats, zero padded
     const RefStats* ref_stats;
     const float* traces;    // precentered mode: per-frame traces, else nullptr

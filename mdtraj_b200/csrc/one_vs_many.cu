@@ -239,14 +239,17 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
 constexpr int kGroupBatch = 32;  // frames per solve batch (one per lane)
 
 struct OvmGroupLayout {
-    size_t ref_off, ring_off, sums_off, bar_off, total, stage_bytes;
+    size_t ref_off, idx_off, ring_off, sums_off, bar_off, total, stage_bytes;
 };
-__host__ __device__ inline OvmGroupLayout ovm_group_layout(int units, int fpi, int stages, int warps)
+// units: 4-atom units of a frame in memory; ref_units: units of the packed reference (== units without a selection);
+// n_idx: length of the selection kept in shared memory (0 without)
+__host__ __device__ inline OvmGroupLayout ovm_group_layout(int units, int ref_units, int n_idx, int fpi, int stages, int warps)
 {
     OvmGroupLayout G;
     G.stage_bytes = (size_t)fpi * units * 48;
     G.ref_off = 0;
-    G.ring_off = align_up((size_t)units * 48, 128);
+    G.idx_off = align_up((size_t)ref_units * 48, 16);
+    G.ring_off = align_up(G.idx_off + (size_t)n_idx * 4, 128);
     G.sums_off = G.ring_off + (size_t)warps * stages * G.stage_bytes;
     G.bar_off = align_up(G.sums_off + (size_t)warps * kGroupBatch * kSumStride * sizeof(float), 8);
     G.total = G.bar_off + ((size_t)warps * stages + 1) * sizeof(uint64_t);
@@ -258,10 +261,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_group_kernel(const OvmP
 {
     constexpr int FPI = 32 / L;  // frames per warp iteration
     extern __shared__ __align__(128) unsigned char smem[];
-    const int units = p.total_units;
+    const int units = p.total_units;           // units of a frame in memory
+    const bool sel = !PRE && p.idx != nullptr;  // selection gathered out of the staged frame (never with traces)
+    const int ref_units = sel ? (p.n_atoms + 3) / 4 : units;
     const int n_warps = blockDim.x >> 5;  // 16 for short frames, fewer when two ring stages of 32/L frames need more room
-    const OvmGroupLayout G = ovm_group_layout(units, FPI, p.stages, n_warps);
+    const OvmGroupLayout G = ovm_group_layout(units, ref_units, sel ? p.n_atoms : 0, FPI, p.stages, n_warps);
     const float4* ref_s = reinterpret_cast<const float4*>(smem + G.ref_off);
+    int* idx_s = reinterpret_cast<int*>(smem + G.idx_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.bar_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / L, j = lane % L;
@@ -274,11 +280,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_group_kernel(const OvmP
     if (lane == 0)
         for (int s = 0; s < p.stages; ++s) mbar_init(&my_bars[s], 1);
     if (threadIdx.x == 0) mbar_init(ref_bar, 1);
+    if (sel)
+        for (int k = threadIdx.x; k < p.n_atoms; k += blockDim.x) idx_s[k] = __ldg(p.idx + k);
     fence_mbar_init();
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(ref_bar, frame_bytes);
-        bulk_g2s(smem + G.ref_off, p.ref, frame_bytes, ref_bar);
+        mbar_arrive_expect_tx(ref_bar, (uint32_t)ref_units * 48u);
+        bulk_g2s(smem + G.ref_off, p.ref, (uint32_t)ref_units * 48u, ref_bar);
     }
 
     const int64_t W = (int64_t)gridDim.x * n_warps;
@@ -314,7 +322,19 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_group_kernel(const OvmP
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
         float px = 0.f, py = 0.f, pz = 0.f;
-        if (active) {
+        if (active && sel) {
+            // the whole frame is in shared memory: gather the selection from there (pivot = first selected atom)
+            const float* xf = reinterpret_cast<const float*>(xs);
+            const float* yf = reinterpret_cast<const float*>(ref_s);
+            const int a0 = idx_s[0];
+            px = xf[3 * a0]; py = xf[3 * a0 + 1]; pz = xf[3 * a0 + 2];
+#pragma unroll 2
+            for (int k = j; k < p.n_atoms; k += L) {
+                const int a = idx_s[k];
+                acc_atom<false>(v, xf[3 * a], xf[3 * a + 1], xf[3 * a + 2], yf[3 * k], yf[3 * k + 1], yf[3 * k + 2], px, py, pz);
+            }
+            if (j == 0) { v[13] = px; v[14] = py; v[15] = pz; }
+        } else if (active) {
             if (!PRE) {
                 const float4 first = xs[0];
                 px = first.x; py = first.y; pz = first.z;
@@ -459,7 +479,9 @@ cudaError_t launch_ovm_tma(const OvmParams& p, bool precentered, int sm_count, c
 template <int L>
 static cudaError_t launch_group_L(const OvmParams& p, bool precentered, int sm_count, int warps, cudaStream_t st)
 {
-    const OvmGroupLayout G = ovm_group_layout(p.total_units, 32 / L, p.stages, warps);
+    const bool sel = !precentered && p.idx != nullptr;
+    const OvmGroupLayout G = ovm_group_layout(p.total_units, sel ? (p.n_atoms + 3) / 4 : p.total_units, sel ? p.n_atoms : 0,
+                                              32 / L, p.stages, warps);
     auto kern = precentered ? ovm_group_kernel<L, true> : ovm_group_kernel<L, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
     if (e != cudaSuccess) return e;
@@ -478,15 +500,23 @@ static cudaError_t launch_group_L(const OvmParams& p, bool precentered, int sm_c
 //     warp a two-stage ring of frame pairs: N = 300 0.67x -> 0.98x of HBM peak, N = 516 0.77x -> 1.01x.
 bool launch_ovm_group(OvmParams& p, bool precentered, int sm_count, cudaStream_t st, cudaError_t* err)
 {
-    p.total_units = (p.n_atoms + 3) / 4;
+    const bool sel = p.idx != nullptr;
+    if (sel && (precentered || p.frame_atoms <= 0)) return false;
+    p.total_units = ((sel ? p.frame_atoms : p.n_atoms) + 3) / 4;
     const size_t frame_bytes = (size_t)p.total_units * 48;
+    // a selection is gathered out of the staged frame when that costs no more HBM traffic than gathering from global
+    // memory would (every selected atom touches a 32-byte sector or two) or when the frames are so small that the
+    // gather kernel's warp per frame is the limit (2.0e9 frames/s whatever N)
+    if (sel && frame_bytes > 3072 && (size_t)p.n_atoms * 64 < frame_bytes) return false;
+    const size_t sel_bytes = sel ? align_up((size_t)((p.n_atoms + 3) / 4) * 48, 16) + (size_t)p.n_atoms * 4 + 128 : 0;
     size_t max_bytes = 8448;  // 704 atoms: measured 0.97-1.05x of HBM peak up to here, the chunked kernel wins from ~800 atoms
     if (const char* mb = getenv("B200RMSD_GROUP_MAX_BYTES")) max_bytes = (size_t)atol(mb);  // development override
     if (p.frame_stride != (int64_t)p.total_units * 12 || frame_bytes > max_bytes || p.n_seg > 1) return false;
     const size_t budget = 232448;
     auto per_warp_bytes = [&](int warps) {
-        const size_t fixed = align_up(frame_bytes, 128) + (size_t)warps * kGroupBatch * kSumStride * sizeof(float) + 1024;
-        return (budget - fixed) / warps;
+        const size_t fixed = (sel ? sel_bytes : align_up(frame_bytes, 128)) +
+                             (size_t)warps * kGroupBatch * kSumStride * sizeof(float) + 1024;
+        return fixed < budget ? (budget - fixed) / warps : (size_t)0;
     };
     int Lsel = 0, stages = 0, warps = kWarpsPerCta;
     for (int L = 2; L <= 16; L <<= 1) {

@@ -7,7 +7,8 @@ from mdtraj_b200 import _capi
 from mdtraj_b200.device import _Scratch, _stream_ptr, prepare_reference
 dev = torch.device("cuda", 0)
 L = _capi.lib()
-for N, stride in ((5000, 5), (5000, 10), (5000, 2), (1000, 4), (25000, 8)):
+cases = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:]] or [(5000, 5), (5000, 10), (5000, 2), (1000, 4), (25000, 8)]
+for N, stride in cases:
     F = int(2.4e9 // (N * 12))
     dt = mdb.DeviceTrajectory.synthetic_iid(F, N, 1, dev)
     idx = torch.arange(0, N, stride, dtype=torch.int32, device=dev)
