@@ -187,7 +187,7 @@ int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atom
     const int sm = ap_sm_count();
     cudaError_t e;
     if (g.tc) {
-        e = launch_allpairs_tc_prepare(xyz, n_frames, frame_stride, idx, ns, g.k_pad, (float*)(base + g.hi_off),
+        e = (g.dense ? launch_allpairs_tc144_prepare : launch_allpairs_tc_prepare)(xyz, n_frames, frame_stride, idx, ns, g.k_pad, (float*)(base + g.hi_off),
                                        (float*)(base + g.lo_off), (float*)(base + g.traces_off), g.rows_pad, sm, st);
     } else {
         int64_t ctas = (int64_t)sm * 8;
@@ -212,7 +212,7 @@ int b200rmsd_allpairs_block_dev(const void* workspace, size_t workspace_bytes, i
     if (row0 == row1 || col0 == col1) return 0;
     const char* base = (const char*)workspace;
     if (g.tc)
-        return launch_allpairs_tc_block((const float*)(base + g.hi_off), (const float*)(base + g.lo_off),
+        return (g.dense ? launch_allpairs_tc144_block : launch_allpairs_tc_block)((const float*)(base + g.hi_off), (const float*)(base + g.lo_off),
                                         (const float*)(base + g.traces_off), n_frames, n_sel, g.k_pad, g.rows_pad, row0,
                                         row1, col0, col1, out, ld, out_t, ld_t, flags, ap_sm_count(), (cudaStream_t)stream);
     dim3 grid((unsigned)((col1 - col0 + kTile - 1) / kTile), (unsigned)((row1 - row0 + kTile - 1) / kTile));

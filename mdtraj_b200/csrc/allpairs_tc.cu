@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "qcp.cuh"
+#include "tc_ptx.cuh"
 
 namespace b200 {
 
@@ -39,80 +40,10 @@ constexpr int kStageBytes = 4 * kOperandBytes;   // A_hi, A_lo, B_hi, B_lo
 constexpr int kAccCols = kBN;                    // fp32 accumulator columns per stage
 constexpr uint32_t kTmemCols = 256;              // 2 accumulator stages
 
-// ---- tcgen05 / TMA PTX wrappers -------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64)
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(const void* smem_tile)
-{
-    const uint64_t addr = (smem_u32(smem_tile) >> 4) & 0x3FFFu;
-    return addr | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c_format=F32 [4,6) a/b_format=TF32 [7,10),[10,13)
-// a/b K-major [15],[16] = 0, N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_tf32_idesc(int M, int N)
-{
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 // ---------------------------------------------------------------------------------------------
 // prepare: centre every frame (center_generic.h:3-44 semantics), write tf32 hi/lo rows + traces.
 // one warp per frame.  Row of (frame f, component c) = 32*(f/10) + 3*(f%10) + c.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float rna_tf32(float x)
-{
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
-
 __global__ void __launch_bounds__(256) allpairs_tc_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames,
                                                                   int64_t frame_stride, const int* __restrict__ idx,
                                                                   int n_sel, int k_pad, float* __restrict__ hi,
@@ -326,36 +257,53 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                     // NP j-frame groups per pass so that NP independent solves interleave
                     float M[NP][9], Ga[NP], Gb[NP], res[NP];
                     int64_t fj[NP];
-                    bool ok[NP];
-#pragma unroll
-                    for (int u = 0; u < NP; ++u) {
-                        const int jg = NP * jp + u;  // group of three j-frames (the last group holds one frame only)
+                    bool ok[NP], trusted[NP];
+                    // rows (c, c+1, c+2) mod 3 of the 3x3 block of pair (i_t, j-frame 3*jg + c): a cyclic permutation of
+                    // x,y,z = a proper rotation of frame i, which leaves the RMSD unchanged.  Warp-collective (shuffles).
+                    auto gather = [&](int jg, float (&m)[9]) {
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
                             const float m0 = __uint_as_float(r[(jg < 3 ? 9 * jg : 27) + q]);
                             const float m1 = __uint_as_float(r[(jg < 3 ? 9 * jg + 3 : 27) + q]);
                             const float m2 = __uint_as_float(r[(jg < 3 ? 9 * jg + 6 : 27) + q]);
-                            // rows (c, c+1, c+2) mod 3: a cyclic permutation of x,y,z = a proper rotation of frame i,
-                            // which leaves the RMSD unchanged
-                            M[u][q] = sel3(c, m0, m1, m2);
+                            m[q] = sel3(c, m0, m1, m2);
                             const float send1 = sel3(c, m2, m0, m1);  // for the reader whose component is (c+2)%3
                             const float send2 = sel3(c, m1, m2, m0);  // for the reader whose component is (c+1)%3
-                            M[u][3 + q] = __shfl_sync(0xffffffffu, send1, src1);
-                            M[u][6 + q] = __shfl_sync(0xffffffffu, send2, src2);
+                            m[3 + q] = __shfl_sync(0xffffffffu, send1, src1);
+                            m[6 + q] = __shfl_sync(0xffffffffu, send2, src2);
                         }
+                    };
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        const int jg = NP * jp + u;  // group of three j-frames (the last group holds one frame only)
+                        gather(jg, M[u]);
                         const int jl = 3 * jg + c;  // j-frame slot inside the chunk
                         fj[u] = (int64_t)tj * kFramesPerTile + chunk * 10 + jl;
                         ok[u] = i_ok && jl < 10 && fj[u] >= p.col0 && fj[u] < p.col1;
                         Ga[u] = ok[u] ? __ldg(p.traces + fj[u]) : 1.0f;
                         Gb[u] = Gi;
+                        trusted[u] = true;
                     }
                     if (p.flags & 0x100u) {  // development: skip the solve to time the GEMM main loop alone
 #pragma unroll
                         for (int u = 0; u < NP; ++u) res[u] = M[u][0];
                     } else if (p.flags & B200RMSD_FAST_SOLVE) {  // all-float32 solve (reference-class precision)
-                        qcp_msd_f32<NP>(M, Ga, Gb, ok, inv_n, res);
+                        qcp_msd_f32<NP>(M, Ga, Gb, ok, inv_n, res, trusted);
                     } else {
-                        qcp_msd_fast<NP>(M, Ga, Gb, ok, inv_n, res);
+                        qcp_msd_fast<NP>(M, Ga, Gb, ok, inv_n, res, trusted);
+                    }
+                    bool all_trusted = true;
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) all_trusted = all_trusted && trusted[u];
+                    if (!__all_sync(0xffffffffu, all_trusted)) {
+                        // rare (collinear atoms, two-atom selections: a double largest root): fetch the blocks again --
+                        // M is dead by now, which keeps it out of the solver's register budget -- and take the closed form
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) {  // unrolled: the accumulator registers must stay statically indexed
+                            float m[9];
+                            gather(NP * jp + u, m);
+                            if (!trusted[u]) res[u] = qcp_rmsd_closed(m, Ga[u], Gb[u], inv_n);
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < NP; ++u)
@@ -389,36 +337,6 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-static bool make_operand_map(CUtensorMap* map, const float* base, int64_t rows, int k_pad)
-{
-    EncodeTiledFn enc = get_encode_fn();
-    if (!enc) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)k_pad * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 cudaError_t launch_allpairs_tc_prepare(const float* xyz, int64_t n_frames, int64_t frame_stride, const int* idx, int n_sel,
                                        int k_pad, float* hi, float* lo, float* traces, int64_t rows_pad, int sm_count,
                                        cudaStream_t st)
@@ -439,7 +357,7 @@ int launch_allpairs_tc_block(const float* hi, const float* lo, const float* trac
                              int64_t ld, float* out_t, int64_t ld_t, unsigned flags, int sm_count, cudaStream_t st)
 {
     CUtensorMap map_hi, map_lo;
-    if (!make_operand_map(&map_hi, hi, rows_pad, k_pad) || !make_operand_map(&map_lo, lo, rows_pad, k_pad))
+    if (!make_operand_map(&map_hi, hi, rows_pad, k_pad, kBM) || !make_operand_map(&map_lo, lo, rows_pad, k_pad, kBM))
         return set_error(B200RMSD_ECUDA, "allpairs: cuTensorMapEncodeTiled failed");
     TcParams p{};
     p.traces = traces;

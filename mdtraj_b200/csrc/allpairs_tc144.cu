@@ -1,0 +1,444 @@
+// allpairs_tc144.cu -- all-pairs RMSD matrix on the 5th-generation tensor cores, dense-row layout.
+//
+// D[i][j] = rmsd(frame j onto frame i) needs the 3x3 inner products M_ij = X_i X_j^T of the centred
+// frames: one dense contraction (3F x A).(A x 3F), computed as a tcgen05 GEMM whose epilogue solves the
+// QCP polynomial of every 3x3 block and writes only the RMSD (arithmetic of each pair == msdFromMandG,
+// theobald_rmsd.cpp:217-334; replaces the Python loop of F md.rmsd calls, examples/clustering.ipynb:78-81).
+//
+//   operands   ONE pair of K-major fp32 matrices (tf32 "hi" and "lo" parts, hi = rna_tf32(x), lo = rna_tf32(x-hi)),
+//              row 3f+c = component c of frame f, K = atoms padded to 32; no padding rows;
+//   tile       40 i-frames x 48 j-frames.  The A operand (M = 128 TMEM lanes) is brought by FOUR 32-row TMA boxes
+//              starting at rows 120*ti + 30*w, so that each epilogue warp's lane quarter holds 10 whole frames (lanes 30
+//              and 31 of a quarter carry the first rows of the next frame and are ignored); the B operand (N = 144
+//              accumulator columns) is one 144-row box = 48 whole frames.  Columns are registers of the reading
+//              thread, so frames may sit at any column: each of the 16 epilogue warps takes 36 columns = 12 j-frames
+//              = 4 passes of 3 frames per lane triplet, every pass full (the 128-column layout of allpairs_tc.cu
+//              padded every 32 columns to 10 frames and left the fourth pass two-thirds empty: 1600 pairs per tile
+//              for the same epilogue passes that now deliver 1920);
+//   loads      cp.async.bulk.tensor.2d, SWIZZLE_128B, 3-stage shared-memory ring (68 KB per stage), mbarrier
+//              full/empty pipeline;
+//   MMA        one elected thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128 N=144 K=8, three per K-step
+//              (lo.hi, hi.lo, hi.hi: "3xTF32", the dropped lo.lo term is ~2^-22 relative) accumulating fp32 in TMEM;
+//              tcgen05.commit releases smem stages and publishes finished accumulators;
+//   epilogue   tcgen05.ld.32x32b (one TMEM lane = one row per thread), 3x3 blocks regrouped with warp shuffles,
+//              QCP solve, 4 bytes per pair written; two accumulator stages in TMEM so that the epilogue of tile t
+//              overlaps the MMAs of tile t+1.
+//
+// The inner products never touch HBM.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../include/b200rmsd.h"
+#include "allpairs_layout.cuh"
+#include "common.cuh"
+#include "kernels.cuh"
+#include "qcp.cuh"
+#include "tc_ptx.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kM = 128, kN = 144, kK = 32, kRing = 3;
+constexpr int kIFrames = 40;                    // 4 lane quarters x 10 frames
+constexpr int kJFrames = 48;                    // 144 columns
+constexpr int kQuarterBytes = 32 * kK * 4;      // 4 KB: one 32-row A box
+constexpr int kABytes = kM * kK * 4;            // 16 KB
+constexpr int kBBytes = kN * kK * 4;            // 18 KB
+constexpr int kStage = 2 * kABytes + 2 * kBBytes;  // A_hi, A_lo, B_hi, B_lo = 68 KB (a multiple of 1024)
+constexpr uint32_t kAccStride = 256;            // TMEM columns between the two accumulator stages
+constexpr uint32_t kTmem = 512;                 // allocation (power of two >= 256 + 144)
+constexpr int kSegCols = 36;                    // columns per epilogue segment = 12 j-frames
+// Tile rasterisation: super-blocks of 24 x 20 tiles = 960 x 960 frames, row-major inside a block and across blocks, so
+// that the ~150 CTAs in flight share a working set of 2 x 960 frames (15 MB of operands at K = 320) that stays
+// L2-resident instead of sweeping the whole operand once per tile row.
+constexpr int kSupI = 24, kSupJ = 20;
+
+struct Tc144Params {
+    const float* traces;
+    float* out;
+    int64_t ld;
+    int64_t row0, row1;      // output rows [row0, row1)
+    int64_t col0, col1;      // output columns [col0, col1)
+    float* out_t;            // optional transposed copy of the block: out_t[(j-col0)*ld_t + (i-row0)]
+    int64_t ld_t;
+    int64_t n_slots;         // super-block slots to walk (tiles outside the block or under the diagonal are skipped)
+    int tiles_i0, tiles_j0;  // first i-tile (= row0 / 40) and j-tile (= col0 / 48)
+    int tiles_i, tiles_j;    // tile grid
+    int n_bj;                // super-blocks per block row
+    int n_sel;
+    int nk;                  // K blocks of 32
+    int symmetric;           // square block on the diagonal: tiles that hold no pair j >= i are skipped, values mirrored
+    unsigned flags;
+};
+
+// slot -> tile; false for slots outside the tile grid and, in symmetric mode, for tiles entirely under the diagonal.
+// Evaluated identically by the three warp roles.
+__host__ __device__ __forceinline__ bool tile_of_slot(int64_t t, const Tc144Params& p, int& ti, int& tj)
+{
+    const int64_t blk = t / (kSupI * kSupJ);
+    const int in = (int)(t - blk * (kSupI * kSupJ));
+    const int bi = (int)(blk / p.n_bj), bj = (int)(blk - (int64_t)bi * p.n_bj);
+    const int li = bi * kSupI + in / kSupJ, lj = bj * kSupJ + in % kSupJ;
+    ti = p.tiles_i0 + li;
+    tj = p.tiles_j0 + lj;
+    if (li >= p.tiles_i || lj >= p.tiles_j) return false;
+    // symmetric: the tile is needed iff its last j-frame is not before its first i-frame
+    return !p.symmetric || (int64_t)tj * kJFrames + (kJFrames - 1) >= (int64_t)ti * kIFrames;
+}
+
+__device__ __forceinline__ float sel3(int c, float a0, float a1, float a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// prepare: centre every frame (center_generic.h:3-44 semantics), write tf32 hi/lo rows + traces.
+// One warp per frame; row of (frame f, component c) = 3 f + c.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) allpairs_tc144_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames,
+                                                                     int64_t frame_stride, const int* __restrict__ idx,
+                                                                     int n_sel, int k_pad, float* __restrict__ hi,
+                                                                     float* __restrict__ lo, float* __restrict__ traces)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    for (int64_t f = (int64_t)blockIdx.x * 8 + warp; f < n_frames; f += n_warps) {
+        const float* fr = xyz + f * frame_stride;
+        double sx = 0, sy = 0, sz = 0;
+        for (int k = lane; k < n_sel; k += 32) {
+            const int a = idx ? __ldg(idx + k) : k;
+            sx += (double)__ldg(fr + 3 * a); sy += (double)__ldg(fr + 3 * a + 1); sz += (double)__ldg(fr + 3 * a + 2);
+        }
+        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+        const float mx = (float)(sx / n_sel), my = (float)(sy / n_sel), mz = (float)(sz / n_sel);
+        const int64_t row = ap_tc144_row(f, 0);
+        double tr = 0;
+        for (int k = lane; k < k_pad; k += 32) {
+            float v[3] = {0.f, 0.f, 0.f};
+            if (k < n_sel) {
+                const int a = idx ? __ldg(idx + k) : k;
+                v[0] = __ldg(fr + 3 * a) - mx; v[1] = __ldg(fr + 3 * a + 1) - my; v[2] = __ldg(fr + 3 * a + 2) - mz;
+                tr += (double)(v[0] * v[0]); tr += (double)(v[1] * v[1]); tr += (double)(v[2] * v[2]);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float h = rna_tf32(v[c]);
+                hi[(row + c) * k_pad + k] = h;
+                lo[(row + c) * k_pad + k] = rna_tf32(v[c] - h);
+            }
+        }
+        tr = warp_sum(tr);
+        if (lane == 0) traces[f] = (float)tr;
+    }
+}
+
+// EPI_WARPS in {8, 16}: epilogue warps (each TMEM lane quarter is served by EPI_WARPS/4 warps that split the four
+// 36-column segments of the accumulator); NP in {1, 2}: independent solves interleaved per lane.
+template <int EPI_WARPS, int NP>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                      const Tc144Params p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is not guaranteed to have it
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRing * kStage);
+    uint64_t* empty = full + kRing;
+    uint64_t* tfull = empty + kRing;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kRing; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
+        fence_mbar_init();
+    }
+    if (warp == EPI_WARPS) tmem_alloc(tmem_slot, kTmem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // Warp roles: warps [0, EPI_WARPS) epilogue, warp EPI_WARPS = TMA producer, warp EPI_WARPS+1 = MMA issuer.
+    // The two single-thread roles get the highest warp ids: the SMSP arbiter favours higher warp ids, and a late
+    // TMA or MMA issue stalls the whole pipeline while a late epilogue instruction does not.
+    if (warp == EPI_WARPS) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < p.n_slots; t += gridDim.x) {
+                int ti, tj;
+                if (!tile_of_slot(t, p, ti, tj)) continue;
+                const int a_row = ti * (3 * kIFrames), b_row = tj * kN;
+                for (int kb = 0; kb < p.nk; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    unsigned char* st = smem + stage * kStage;
+                    mbar_arrive_expect_tx(&full[stage], kStage);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {  // lane quarter w <- rows of frames 10w .. 10w+9 (+2 ignored rows)
+                        tma_load_2d(st + w * kQuarterBytes, &map_a_hi, &full[stage], kb * kK, a_row + 30 * w);
+                        tma_load_2d(st + kABytes + w * kQuarterBytes, &map_a_lo, &full[stage], kb * kK, a_row + 30 * w);
+                    }
+                    tma_load_2d(st + 2 * kABytes, &map_b_hi, &full[stage], kb * kK, b_row);
+                    tma_load_2d(st + 2 * kABytes + kBBytes, &map_b_lo, &full[stage], kb * kK, b_row);
+                    if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == EPI_WARPS + 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_tf32_idesc(kM, kN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int64_t t = blockIdx.x; t < p.n_slots; t += gridDim.x) {
+                int ti_unused, tj_unused;
+                if (!tile_of_slot(t, p, ti_unused, tj_unused)) continue;
+                mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+                for (int kb = 0; kb < p.nk; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    unsigned char* st = smem + stage * kStage;
+                    const uint64_t a_hi = make_sw128_kmajor_desc(st), a_lo = make_sw128_kmajor_desc(st + kABytes);
+                    const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * kABytes),
+                                   b_lo = make_sw128_kmajor_desc(st + 2 * kABytes + kBBytes);
+#pragma unroll
+                    for (int ks = 0; ks < ((p.flags & 0x200u) ? 0 : kK / 8); ++ks) {  // 0x200: development, skip MMAs
+                        const uint64_t off = (uint64_t)(ks * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
+                        umma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, (kb | ks) != 0 ? 1u : 0u);
+                        umma_tf32(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
+                        umma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
+                    }
+                    umma_commit(&empty[stage]);  // frees this smem stage when the MMAs above have read it
+                    if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull[acc]);        // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================================================== epilogue (TMEM -> QCP -> HBM)
+        const int ew = warp & 3;                 // TMEM lane quarter this warp may read (warp_id % 4)
+        constexpr int kSegsPerWarp = 16 / EPI_WARPS;  // 2 or 1 of the four 36-column segments
+        const int part = warp >> 2;              // which share of the segments
+        const int c = lane % 3, tq = lane / 3;   // component row and frame slot of this lane
+        const bool row_valid = lane < 30;        // lanes 30, 31: first rows of the next quarter's frame, ignored
+        const int src1 = lane - c + (c + 1) % 3, src2 = lane - c + (c + 2) % 3;
+        const float inv_n = 1.0f / (float)p.n_sel;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t t = blockIdx.x; t < p.n_slots; t += gridDim.x) {
+            int ti, tj;
+            if (!tile_of_slot(t, p, ti, tj)) continue;
+            const int64_t fi = (int64_t)ti * kIFrames + ew * 10 + tq;  // row frame of this lane
+            const bool i_ok = row_valid && fi >= p.row0 && fi < p.row1;
+            const float Gi = i_ok ? __ldg(p.traces + fi) : 1.0f;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < kSegsPerWarp; ++cc) {
+                const int seg = part * kSegsPerWarp + cc;
+                uint32_t r[kSegCols];
+                {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kAccStride +
+                                           (uint32_t)(seg * kSegCols);
+#pragma unroll
+                    for (int q4 = 0; q4 < kSegCols / 4; ++q4)
+                        tmem_ld_32x32b_x4(taddr + 4 * q4, r[4 * q4], r[4 * q4 + 1], r[4 * q4 + 2], r[4 * q4 + 3]);
+                    tmem_ld_wait();
+                }
+#pragma unroll
+                for (int jp = 0; jp < 4 / NP; ++jp) {
+                    // NP groups of three j-frames per pass so that NP independent solves interleave
+                    float M[NP][9], Ga[NP], Gb[NP], res[NP];
+                    int64_t fj[NP];
+                    bool ok[NP], trusted[NP];
+                    // column 9*jg + 3*m + q of the segment = (this lane's row) . (component q of j-frame 3*jg + m).
+                    // Lane (tq, c) ends up with rows (c, c+1, c+2) mod 3 of the block of pair (i_tq, j-frame 3*jg + c):
+                    // a cyclic permutation of x,y,z = a proper rotation of frame i, which leaves the RMSD unchanged.
+                    // Warp-collective (shuffles).
+                    auto gather = [&](int jg, float (&m)[9]) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const float m0 = __uint_as_float(r[9 * jg + q]);
+                            const float m1 = __uint_as_float(r[9 * jg + 3 + q]);
+                            const float m2 = __uint_as_float(r[9 * jg + 6 + q]);
+                            m[q] = sel3(c, m0, m1, m2);
+                            const float send1 = sel3(c, m2, m0, m1);  // for the reader whose component is (c+2)%3
+                            const float send2 = sel3(c, m1, m2, m0);  // for the reader whose component is (c+1)%3
+                            m[3 + q] = __shfl_sync(0xffffffffu, send1, src1);
+                            m[6 + q] = __shfl_sync(0xffffffffu, send2, src2);
+                        }
+                    };
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        const int jg = NP * jp + u;
+                        gather(jg, M[u]);
+                        fj[u] = (int64_t)tj * kJFrames + seg * 12 + 3 * jg + c;
+                        ok[u] = i_ok && fj[u] >= p.col0 && fj[u] < p.col1;
+                        Ga[u] = ok[u] ? __ldg(p.traces + fj[u]) : 1.0f;
+                        Gb[u] = Gi;
+                        trusted[u] = true;
+                    }
+                    if (p.flags & 0x100u) {  // development: skip the solve to time the GEMM main loop alone
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) res[u] = M[u][0];
+                    } else if (p.flags & B200RMSD_FAST_SOLVE) {  // all-float32 solve (reference-class precision)
+                        qcp_msd_f32<NP>(M, Ga, Gb, ok, inv_n, res, trusted);
+                    } else {
+                        qcp_msd_fast<NP>(M, Ga, Gb, ok, inv_n, res, trusted);
+                    }
+                    bool all_trusted = true;
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) all_trusted = all_trusted && trusted[u];
+                    if (!__all_sync(0xffffffffu, all_trusted)) {
+                        // rare (collinear atoms, two-atom selections: a double largest root): fetch the blocks again --
+                        // M is dead by now, which keeps it out of the solver's register budget -- and take the closed form
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) {  // unrolled: the accumulator registers must stay statically indexed
+                            float m[9];
+                            gather(NP * jp + u, m);
+                            if (!trusted[u]) res[u] = qcp_rmsd_closed(m, Ga[u], Gb[u], inv_n);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < NP; ++u)
+                        if (ok[u]) {
+                            const float v = (fi == fj[u] && (p.flags & B200RMSD_DIAG_ZERO)) ? 0.f : res[u];
+                            if (!p.symmetric) {
+                                p.out[(size_t)(fi - p.row0) * p.ld + fj[u]] = v;
+                                if (p.out_t) p.out_t[(size_t)(fj[u] - p.col0) * p.ld_t + (fi - p.row0)] = v;
+                            } else if (fj[u] >= fi) {  // each unordered pair once, mirrored: D is exactly symmetric
+                                p.out[(size_t)(fi - p.row0) * p.ld + fj[u]] = v;
+                                if (fj[u] != fi) p.out[(size_t)(fj[u] - p.row0) * p.ld + fi] = v;
+                            }
+                        }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EPI_WARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmem);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+// tile grid and super-block walk of the block [row0,row1) x [col0,col1)
+static Tc144Params tc144_tiling(int64_t row0, int64_t row1, int64_t col0, int64_t col1, bool has_out_t)
+{
+    Tc144Params p{};
+    p.row0 = row0;
+    p.row1 = row1;
+    p.col0 = col0;
+    p.col1 = col1;
+    p.tiles_i0 = (int)(row0 / kIFrames);
+    p.tiles_i = (int)((row1 + kIFrames - 1) / kIFrames) - p.tiles_i0;
+    p.tiles_j0 = (int)(col0 / kJFrames);
+    p.tiles_j = (int)((col1 + kJFrames - 1) / kJFrames) - p.tiles_j0;
+    // a square block on the diagonal: compute each unordered pair once and mirror it (exactly symmetric, half the flops)
+    p.symmetric = (row0 == col0 && row1 == col1 && !has_out_t && !getenv("B200RMSD_NO_SYMMETRIC")) ? 1 : 0;
+    p.n_bj = (p.tiles_j + kSupJ - 1) / kSupJ;
+    p.n_slots = (int64_t)((p.tiles_i + kSupI - 1) / kSupI) * p.n_bj * (kSupI * kSupJ);
+    return p;
+}
+
+// development / test hook (no device needed): the tiles the kernel visits for a block, in slot order, as (ti, tj) pairs
+// in tiles[0 .. 2*cap); returns how many there are, and whether the block runs in symmetric mode in *symmetric.
+extern "C" long long b200rmsd_debug_allpairs_tiles(long long row0, long long row1, long long col0, long long col1,
+                                                   int has_out_t, int* tiles, long long cap, int* symmetric)
+{
+    const Tc144Params p = tc144_tiling(row0, row1, col0, col1, has_out_t != 0);
+    if (symmetric) *symmetric = p.symmetric;
+    long long n = 0;
+    for (int64_t t = 0; t < p.n_slots; ++t) {
+        int ti, tj;
+        if (!tile_of_slot(t, p, ti, tj)) continue;
+        if (n < cap) { tiles[2 * n] = ti; tiles[2 * n + 1] = tj; }
+        ++n;
+    }
+    return n;
+}
+
+cudaError_t launch_allpairs_tc144_prepare(const float* xyz, int64_t n_frames, int64_t frame_stride, const int* idx,
+                                          int n_sel, int k_pad, float* hi, float* lo, float* traces, int64_t rows_pad,
+                                          int sm_count, cudaStream_t st)
+{
+    // rows past 3F are read by the last tiles' boxes: they must hold finite numbers
+    cudaError_t e = cudaMemsetAsync(hi, 0, (size_t)rows_pad * k_pad * 4, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(lo, 0, (size_t)rows_pad * k_pad * 4, st);
+    if (e != cudaSuccess) return e;
+    int64_t ctas = (int64_t)sm_count * 8;
+    const int64_t need = (n_frames + 7) / 8;
+    if (ctas > need) ctas = need;
+    allpairs_tc144_prepare_kernel<<<(unsigned)ctas, 256, 0, st>>>(xyz, n_frames, frame_stride, idx, n_sel, k_pad, hi, lo,
+                                                                  traces);
+    return cudaGetLastError();
+}
+
+int launch_allpairs_tc144_block(const float* hi, const float* lo, const float* traces, int64_t n_frames, int n_sel,
+                                int k_pad, int64_t rows_pad, int64_t row0, int64_t row1, int64_t col0, int64_t col1,
+                                float* out, int64_t ld, float* out_t, int64_t ld_t, unsigned flags, int sm_count,
+                                cudaStream_t st)
+{
+    (void)n_frames;
+    CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+    if (!make_operand_map(&map_a_hi, hi, rows_pad, k_pad, 32) || !make_operand_map(&map_a_lo, lo, rows_pad, k_pad, 32) ||
+        !make_operand_map(&map_b_hi, hi, rows_pad, k_pad, kN) || !make_operand_map(&map_b_lo, lo, rows_pad, k_pad, kN))
+        return set_error(B200RMSD_ECUDA, "allpairs: cuTensorMapEncodeTiled failed");
+    Tc144Params p = tc144_tiling(row0, row1, col0, col1, out_t != nullptr);
+    p.traces = traces;
+    p.out = out;
+    p.ld = ld;
+    p.out_t = out_t;
+    p.ld_t = ld_t;
+    p.n_sel = n_sel;
+    p.nk = k_pad / kK;
+    p.flags = flags;
+    if (const char* dbg = getenv("B200RMSD_TC_DEBUG")) p.flags |= (unsigned)strtoul(dbg, nullptr, 0) & 0xff02u;
+    const size_t smem = (size_t)kRing * kStage + 1024 + 256;
+    int64_t ctas = sm_count;
+    const int64_t n_tiles = (int64_t)p.tiles_i * p.tiles_j;
+    if (ctas > n_tiles) ctas = n_tiles;
+    if (ctas < 1) ctas = 1;
+    const char* cfg = getenv("B200RMSD_TC_EPILOGUE");  // development: "<warps>x<np>", e.g. 16x1
+    int ew = 16, np = 2;
+    if (cfg) sscanf(cfg, "%dx%d", &ew, &np);
+    cudaError_t e = cudaSuccess;
+#define B200_LAUNCH_TC144(EW, NP)                                                                                          \
+    do {                                                                                                                   \
+        e = cudaFuncSetAttribute(allpairs_tc144_kernel<EW, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (e == cudaSuccess)                                                                                              \
+            allpairs_tc144_kernel<EW, NP><<<(unsigned)ctas, 64 + 32 * EW, smem, st>>>(map_a_hi, map_a_lo, map_b_hi,       \
+                                                                                       map_b_lo, p);                       \
+    } while (0)
+    if (ew == 8 && np == 2) B200_LAUNCH_TC144(8, 2);
+    else if (ew == 16 && np == 1) B200_LAUNCH_TC144(16, 1);
+    else B200_LAUNCH_TC144(16, 2);
+#undef B200_LAUNCH_TC144
+    if (e != cudaSuccess) return set_error(B200RMSD_ECUDA, "allpairs: %s", cudaGetErrorString(e));
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error(B200RMSD_ECUDA, "allpairs: %s", cudaGetErrorString(e));
+}
+
+}  // namespace b200

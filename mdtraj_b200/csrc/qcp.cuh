@@ -21,6 +21,62 @@ struct QcpInput {
     int n_atoms;
 };
 
+// Closed form of the largest root, for the inputs Newton cannot be trusted on.
+//
+// The four roots of the QCP quartic are s1+s2+s3', s1-s2-s3', -s1+s2-s3', -s1-s2+s3' with s1 >= s2 >= s3 >= 0 the
+// singular values of M and s3' = sign(det M) * s3.  When s2 + s3' ~ 0 (atoms on a line -- any two-atom selection --
+// or an improper-rotation-like pair) the two largest roots (nearly) coincide: Newton then converges linearly, the
+// float32 phase is pure rounding noise below a distance of ~1e-4 * lambda and a noisy step can throw the iterate
+// under the second root, from where the iteration converges to the wrong one.  The squares mu_i = s_i^2 are the
+// eigenvalues of M^T M, i.e. the roots of  mu^3 - ss mu^2 + nc mu - det^2  (ss = |M|_F^2, nc = |cof M|_F^2):
+// mu1 comes from the trigonometric form (it is always well separated from 0), mu2 and mu3 from the two symmetric
+// functions that have no cancellation (mu2 + mu3 = (nc - det^2/mu1)/mu1, mu2 mu3 = det^2/mu1).  The reference takes
+// a closed-form route for every frame (DirectSolve, theobald_rmsd.cpp:183-193) but from float32 coefficients, and is
+// itself off by up to 2.5e-2 nm on such inputs; here the closed form is the rare slow path, in float64.
+#ifndef QCP_SLOW_PATH_HOOK
+#define QCP_SLOW_PATH_HOOK()
+#endif
+static __device__ __noinline__ double qcp_lambda_closed(const double* M)
+{
+    QCP_SLOW_PATH_HOOK();
+    const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    const double c10 = M[2] * M[7] - M[1] * M[8], c11 = M[0] * M[8] - M[2] * M[6], c12 = M[1] * M[6] - M[0] * M[7];
+    const double c20 = M[1] * M[5] - M[2] * M[4], c21 = M[2] * M[3] - M[0] * M[5], c22 = M[0] * M[4] - M[1] * M[3];
+    double ss = 0.0;
+    for (int i = 0; i < 9; ++i) ss += M[i] * M[i];
+    if (!(ss > 0.0)) return 0.0;
+    // work with M / |M|_F: every intermediate is O(1) whatever the units
+    const double inv = 1.0 / ss;
+    const double nc = (c00 * c00 + c01 * c01 + c02 * c02 + c10 * c10 + c11 * c11 + c12 * c12 + c20 * c20 + c21 * c21 +
+                       c22 * c22) * inv * inv;
+    const double det = (M[0] * c00 + M[1] * c01 + M[2] * c02) * inv / sqrt(ss);
+    const double det2 = det * det;
+    double p = (1.0 - 3.0 * nc) * (1.0 / 9.0);
+    double mu1 = 1.0 / 3.0;
+    if (p > 0.0) {
+        const double sp = sqrt(p);
+        double r = (2.0 - 9.0 * nc + 27.0 * det2) * (1.0 / 54.0) / (p * sp);
+        r = fmin(1.0, fmax(-1.0, r));
+        mu1 += 2.0 * sp * cos(acos(r) * (1.0 / 3.0));
+    }
+    const double pq = det2 / mu1;                   // mu2 * mu3
+    const double sm = fmax((nc - pq) / mu1, 0.0);   // mu2 + mu3
+    const double mu2 = 0.5 * (sm + sqrt(fmax(sm * sm - 4.0 * pq, 0.0)));
+    const double mu3 = mu2 > 0.0 ? pq / mu2 : 0.0;
+    double lam = sqrt(mu1) + sqrt(mu2) + (det < 0.0 ? -sqrt(mu3) : sqrt(mu3));
+    // polish on the (scaled) quartic where it is well conditioned; a step that is not a small correction is discarded
+    const double C2 = -2.0, C1 = -8.0 * det, C0 = 1.0 - 4.0 * nc;
+    for (int it = 0; it < 2; ++it) {
+        const double x2 = lam * lam;
+        const double b = (x2 + C2) * lam;
+        const double a = b + C1;
+        const double den = 2.0 * x2 * lam + b + a;
+        const double d = (a * lam + C0) / den;
+        if (den > 1e-3 && fabs(d) < 1e-6) lam -= d;
+    }
+    return lam * sqrt(ss);
+}
+
 // Largest root of  t^4 + C2 t^2 + C1 t + C0  (all four roots are real: K is symmetric).
 //
 // Start: lam0 = min((G_a+G_b)/2, sqrt(3)*||M||_F).  Both are upper bounds of lambda_max (the first is the
@@ -32,9 +88,15 @@ struct QcpInput {
 // The polynomial is scaled by an exact power of two (t = lambda * 2^-e in [1,2) at the start: no division, no
 // rounding); the first iterations run in float32 (4-cycle FMA + MUFU reciprocal), the last ones in float64 with
 // a float32-seeded, once-refined reciprocal instead of a DDIV chain.
-__device__ __forceinline__ double qcp_newton(double C2, double C1, double C0, double lam_upper, double frob2)
+//
+// *trusted is the certificate that the iterate sits on the LARGEST root: the last step was a negligible correction
+// and P'(x) > 0, P''(x) > 0 (for a real-rooted quartic P'' > 0 puts x right of every inflection point, where P' is
+// increasing; P' > 0 there puts x right of every critical point, where P has exactly one root).  Callers send
+// uncertified inputs (double or nearly double largest root, see qcp_lambda_closed) to the closed form.
+__device__ __forceinline__ double qcp_newton(double C2, double C1, double C0, double lam_upper, double frob2, bool* trusted)
 {
     float ub = fminf(sqrtf(3.0f * (float)frob2) * 1.000001f, (float)lam_upper * 1.000001f);
+    *trusted = true;
     if (!(ub > 1e-30f)) return 0.0;
     const int e = ((__float_as_int(ub) >> 23) & 0xff) - 127;
     const double s1 = __longlong_as_double((long long)(1023 - e) << 52);
@@ -57,20 +119,25 @@ __device__ __forceinline__ double qcp_newton(double C2, double C1, double C0, do
         if (!(t > 0.0f) || !(t <= 2.0f)) t = ub * (float)s1;  // numerical accident: restart the float64 phase from the bound
     }
     double x = (double)t;
+    bool ok = false;
 #pragma unroll 1
-    for (int it = 0; it < 40; ++it) {
+    for (int it = 0; it < 12; ++it) {
         const double x2 = x * x;
         const double b = (x2 + c2) * x;
         const double a = b + c1;
         const double den = 2.0 * x2 * x + b + a;
-        if (!(fabs(den) > 1e-300)) break;
+        if (!(den > 1e-300)) break;
         // a float32 reciprocal is enough: a 1e-7 relative error in the step only perturbs the quadratically
         // converging iterate by 1e-7 * |delta|
         const double delta = (a * x + c0) * (double)__frcp_rn((float)den);
         if (!(delta == delta)) break;
         x -= delta;
-        if (fabs(delta) <= 1e-10 * fabs(x)) break;  // quadratic: the step just taken leaves an error ~delta^2
+        if (fabs(delta) <= 1e-10 * fabs(x)) {  // quadratic: the step just taken leaves an error ~delta^2
+            ok = 6.0 * x * x > -c2;            // P''(x) > 0
+            break;
+        }
     }
+    *trusted = ok;
     return x * __longlong_as_double((long long)(1023 + e) << 52);
 }
 
@@ -105,7 +172,9 @@ __device__ __forceinline__ double qcp_solve(const QcpInput& in, float* rot, bool
     const double b12 = k12 * k23 - k22 * k13, b13 = k12 * k33 - k23 * k13, b23 = k22 * k33 - k23 * k23;
     const double C0 = a01 * b23 - a02 * b13 + a03 * b12 + a12 * b03 - a13 * b02 + a23 * b01;
 
-    const double lam = qcp_newton(C2, C1, C0, 0.5 * (in.Ga + in.Gb), ss);
+    bool trusted;
+    double lam = qcp_newton(C2, C1, C0, 0.5 * (in.Ga + in.Gb), ss, &trusted);
+    if (!trusted) lam = qcp_lambda_closed(in.M);
     double msd = (in.Ga + in.Gb - 2.0 * lam) / in.n_atoms;
     if (!(msd > 0.0)) msd = 0.0;
 
@@ -144,38 +213,50 @@ __device__ __forceinline__ double qcp_solve(const QcpInput& in, float* rot, bool
 // ---------------------------------------------------------------------------------------------
 // Throughput variant for the all-pairs epilogue (no rotation): branch-free so that two independent
 // solves interleave in one instruction stream.  Same polynomial and root as qcp_solve:
-//   * coefficients C2, C1, C0 in float64 (the Laplace minors have plenty of ILP);
+//   * coefficients in float64 from the invariants of M alone -- with ss = |M|_F^2 and cof M the cofactor matrix,
+//     C2 = -2 ss, C1 = -8 det M, C0 = det K = ss^2 - 4 |cof M|_F^2 (expand the product of the four roots
+//     s1+s2+s3', s1-s2-s3', ...: (s1^2+s2^2+s3^2)^2 - 4 (s1^2 s2^2 + s2^2 s3^2 + s3^2 s1^2)); 43 float64
+//     operations instead of 64 for the ten K entries and the Laplace minors, and det M falls out of row 0 of cof M;
 //   * scaling by an exact power of two instead of a division;
-//   * a fixed number of float32 Newton steps from the upper bound, then two float64 steps whose
+//   * float32 Newton steps from the upper bound (warp-uniform exit), then two float64 steps whose
 //     divisions are a float32 reciprocal refined by one Newton step (3 DFMA instead of a DDIV chain);
+//   * the same largest-root certificate as qcp_newton, returned in trusted[]: pairs that fail it (collinear atoms,
+//     two-atom selections) must be redone by the caller with qcp_rmsd_closed -- kept out of this function so that M
+//     is dead after the coefficients and the hot path's register footprint does not pay for the rare one;
 //   * float32 square root of the float64 msd.
 // ---------------------------------------------------------------------------------------------
+// the slow path of the two solvers below: RMSD of one pair through the closed form
+__device__ __forceinline__ float qcp_rmsd_closed(const float* M, float Ga, float Gb, float inv_n)
+{
+    double m[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m[i] = (double)M[i];
+    const double msd = 2.0 * (0.5 * ((double)Ga + (double)Gb) - qcp_lambda_closed(m)) * (double)inv_n;
+    return sqrtf(fmaxf((float)msd, 0.f));
+}
+
 template <int NP>
 __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const float (&Ga)[NP], const float (&Gb)[NP],
-                                             const bool (&active)[NP], float inv_n, float (&rmsd)[NP])
+                                             const bool (&active)[NP], float inv_n, float (&rmsd)[NP],
+                                             bool (&trusted)[NP])
 {
     double c2[NP], c1[NP], c0[NP], e0[NP], scale_back[NP];
     float t[NP], f2[NP], f1[NP], f0[NP];
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-        const double Sxx = M[p][0], Sxy = M[p][1], Sxz = M[p][2];
-        const double Syx = M[p][3], Syy = M[p][4], Syz = M[p][5];
-        const double Szx = M[p][6], Szy = M[p][7], Szz = M[p][8];
-        const double k00 = Sxx + Syy + Szz, k11 = Sxx - Syy - Szz, k22 = -Sxx + Syy - Szz, k33 = -Sxx - Syy + Szz;
-        const double k01 = Szy - Syz, k02 = Sxz - Szx, k03 = Syx - Sxy;
-        const double k12 = Syx + Sxy, k13 = Sxz + Szx, k23 = Szy + Syz;
-        const double ss = Sxx * Sxx + Sxy * Sxy + Sxz * Sxz + Syx * Syx + Syy * Syy + Syz * Syz + Szx * Szx + Szy * Szy +
-                          Szz * Szz;
-        const double detM = Sxx * (Syy * Szz - Syz * Szy) + Syx * (Szy * Sxz - Szz * Sxy) + Szx * (Sxy * Syz - Sxz * Syy);
-        const double a01 = k00 * k11 - k01 * k01, a02 = k00 * k12 - k02 * k01, a03 = k00 * k13 - k03 * k01;
-        const double a12 = k01 * k12 - k02 * k11, a13 = k01 * k13 - k03 * k11, a23 = k02 * k13 - k03 * k12;
-        const double b01 = k02 * k13 - k12 * k03, b02 = k02 * k23 - k22 * k03, b03 = k02 * k33 - k23 * k03;
-        const double b12 = k12 * k23 - k22 * k13, b13 = k12 * k33 - k23 * k13, b23 = k22 * k33 - k23 * k23;
-        const double C0 = a01 * b23 - a02 * b13 + a03 * b12 + a12 * b03 - a13 * b02 + a23 * b01;
-        const double C2 = -2.0 * ss, C1 = -8.0 * detM;
+        const double m0 = M[p][0], m1 = M[p][1], m2 = M[p][2], m3 = M[p][3], m4 = M[p][4], m5 = M[p][5], m6 = M[p][6],
+                     m7 = M[p][7], m8 = M[p][8];
+        const double k00 = m4 * m8 - m5 * m7, k01 = m5 * m6 - m3 * m8, k02 = m3 * m7 - m4 * m6;
+        const double k10 = m2 * m7 - m1 * m8, k11 = m0 * m8 - m2 * m6, k12 = m1 * m6 - m0 * m7;
+        const double k20 = m1 * m5 - m2 * m4, k21 = m2 * m3 - m0 * m5, k22 = m0 * m4 - m1 * m3;
+        const double ss = m0 * m0 + m1 * m1 + m2 * m2 + m3 * m3 + m4 * m4 + m5 * m5 + m6 * m6 + m7 * m7 + m8 * m8;
+        const double nc = k00 * k00 + k01 * k01 + k02 * k02 + k10 * k10 + k11 * k11 + k12 * k12 + k20 * k20 + k21 * k21 +
+                          k22 * k22;
+        const double detM = m0 * k00 + m1 * k01 + m2 * k02;
+        const double C0 = ss * ss - 4.0 * nc, C2 = -2.0 * ss, C1 = -8.0 * detM;
         e0[p] = 0.5 * ((double)Ga[p] + (double)Gb[p]);
         // upper bound of the largest root, float32 is enough (nudged up so rounding cannot undershoot)
-        float ub = fminf(sqrtf(3.0f * (float)ss) * 1.000001f, (float)e0[p] * 1.000001f);
+        float ub = fminf(sqrtf(3.0f * (float)ss) * 1.000001f, 0.5f * (Ga[p] + Gb[p]) * 1.000001f);
         ub = fmaxf(ub, 1e-30f);
         // exact power-of-two scale s = 2^-e with ub*s in [1,2)
         const int e = ((__float_as_int(ub) >> 23) & 0xff) - 127;
@@ -184,7 +265,7 @@ __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const floa
         scale_back[p] = __longlong_as_double((long long)(1023 + e) << 52);
         c2[p] = C2 * s2; c1[p] = C1 * s2 * s1; c0[p] = C0 * s2 * s2;
         f2[p] = (float)c2[p]; f1[p] = (float)c1[p]; f0[p] = (float)c0[p];
-        t[p] = ub * (float)s1;
+        t[p] = ub * __int_as_float((127 - e) << 23);
     }
 #pragma unroll 1
     for (int it = 0; it < 16; ++it) {
@@ -205,6 +286,7 @@ __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const floa
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         double x = (double)t[p];
+        bool ok = true;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
             const double x2 = x * x;
@@ -215,8 +297,11 @@ __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const floa
             double r = (double)__frcp_rn((float)den);
             r = r * (2.0 - den * r);
             const double d = num * r;
-            x -= (fabs(den) > 1e-300 && d == d) ? d : 0.0;
+            const bool fine = den > 1e-300 && d == d;
+            x -= fine ? d : 0.0;
+            if (it == 1) ok = fine && fabs(d) <= 1e-8 * x && 6.0 * x * x > -c2[p];  // largest-root certificate
         }
+        trusted[p] = ok || !active[p];
         const double lam = x * scale_back[p];
         double msd = 2.0 * (e0[p] - lam) * (double)inv_n;
         msd = msd > 0.0 ? msd : 0.0;
@@ -225,10 +310,11 @@ __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const floa
 }
 
 // All-float32 variant (development / comparison): coefficients, Newton and the final cancellation in float32,
-// i.e. the precision class of the reference's own msdFromMandG (theobald_rmsd.cpp:217-277).
+// i.e. the precision class of the reference's own msdFromMandG (theobald_rmsd.cpp:217-277).  ok[] as in qcp_msd_fast.
 template <int NP>
 __device__ __forceinline__ void qcp_msd_f32(const float (&M)[NP][9], const float (&Ga)[NP], const float (&Gb)[NP],
-                                            const bool (&active)[NP], float inv_n, float (&rmsd)[NP])
+                                            const bool (&active)[NP], float inv_n, float (&rmsd)[NP],
+                                            bool (&ok)[NP])
 {
     float c2[NP], c1[NP], c0[NP], e0[NP], t[NP], sc[NP];
 #pragma unroll
@@ -245,18 +331,17 @@ __device__ __forceinline__ void qcp_msd_f32(const float (&M)[NP][9], const float
         float m[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) m[i] = M[p][i] * s1;  // exact scaling: work with M/2^e
-        const float Sxx = m[0], Sxy = m[1], Sxz = m[2], Syx = m[3], Syy = m[4], Syz = m[5], Szx = m[6], Szy = m[7], Szz = m[8];
-        const float k00 = Sxx + Syy + Szz, k11 = Sxx - Syy - Szz, k22 = -Sxx + Syy - Szz, k33 = -Sxx - Syy + Szz;
-        const float k01 = Szy - Syz, k02 = Sxz - Szx, k03 = Syx - Sxy, k12 = Syx + Sxy, k13 = Sxz + Szx, k23 = Szy + Syz;
-        const float detM = Sxx * (Syy * Szz - Syz * Szy) + Syx * (Szy * Sxz - Szz * Sxy) + Szx * (Sxy * Syz - Sxz * Syy);
-        const float a01 = k00 * k11 - k01 * k01, a02 = k00 * k12 - k02 * k01, a03 = k00 * k13 - k03 * k01;
-        const float a12 = k01 * k12 - k02 * k11, a13 = k01 * k13 - k03 * k11, a23 = k02 * k13 - k03 * k12;
-        const float b01 = k02 * k13 - k12 * k03, b02 = k02 * k23 - k22 * k03, b03 = k02 * k33 - k23 * k03;
-        const float b12 = k12 * k23 - k22 * k13, b13 = k12 * k33 - k23 * k13, b23 = k22 * k33 - k23 * k23;
-        c0[p] = a01 * b23 - a02 * b13 + a03 * b12 + a12 * b03 - a13 * b02 + a23 * b01;
-        c2[p] = -2.0f * ss * s1 * s1;
-        c1[p] = -8.0f * detM;
+        const float k00 = m[4] * m[8] - m[5] * m[7], k01 = m[5] * m[6] - m[3] * m[8], k02 = m[3] * m[7] - m[4] * m[6];
+        const float k10 = m[2] * m[7] - m[1] * m[8], k11 = m[0] * m[8] - m[2] * m[6], k12 = m[1] * m[6] - m[0] * m[7];
+        const float k20 = m[1] * m[5] - m[2] * m[4], k21 = m[2] * m[3] - m[0] * m[5], k22 = m[0] * m[4] - m[1] * m[3];
+        const float nc = k00 * k00 + k01 * k01 + k02 * k02 + k10 * k10 + k11 * k11 + k12 * k12 + k20 * k20 + k21 * k21 +
+                         k22 * k22;
+        const float sss = ss * s1 * s1;
+        c0[p] = sss * sss - 4.0f * nc;
+        c2[p] = -2.0f * sss;
+        c1[p] = -8.0f * (m[0] * k00 + m[1] * k01 + m[2] * k02);
         t[p] = ub * s1;
+        ok[p] = false;
     }
 #pragma unroll 1
     for (int it = 0; it < 20; ++it) {
@@ -270,6 +355,8 @@ __device__ __forceinline__ void qcp_msd_f32(const float (&M)[NP][9], const float
             const float num = fmaf(a, t[p], c0[p]);
             const float d = (fabsf(den) > 1e-30f) ? __fdividef(num, den) : 0.0f;
             t[p] -= d;
+            // float32 noise in P is ~1e-6 t^4: trust the root only where P' is not small against t^3
+            ok[p] = den > 0.05f * t2 * t[p] && fabsf(d) <= 1e-6f * t[p] && 6.0f * t[p] * t[p] > -c2[p];
             conv = conv && (!active[p] || fabsf(d) <= 2e-7f * t[p]);
         }
         if (__all_sync(0xffffffffu, conv)) break;
@@ -278,6 +365,7 @@ __device__ __forceinline__ void qcp_msd_f32(const float (&M)[NP][9], const float
     for (int p = 0; p < NP; ++p) {
         const float msd = 2.0f * (e0[p] - t[p] * sc[p]) * inv_n;
         rmsd[p] = sqrtf(fmaxf(msd, 0.f));
+        ok[p] = ok[p] || !active[p];
     }
 }
 

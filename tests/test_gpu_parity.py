@@ -335,10 +335,16 @@ def test_allpairs_vs_truth_random(mdb, oracle_mod):
 
 
 # ------------------------------------------------------------------ tensor-core all-pairs path
-@pytest.mark.parametrize("F,N", [(600, 300), (1001, 97), (520, 22)])
-def test_allpairs_tensor_core_vs_simt_and_truth(mdb, oracle_mod, monkeypatch, F, N):
-    """The tcgen05 3xTF32 kernel (F >= 512) against the exact-fp32 SIMT kernel and float64 truth."""
+TC_LAYOUTS = ["dense", "grouped"]  # csrc/allpairs_tc144.cu (default) and csrc/allpairs_tc.cu (B200RMSD_TC_LAYOUT=grouped)
+
+
+@pytest.mark.parametrize("layout", TC_LAYOUTS)
+@pytest.mark.parametrize("F,N", [(600, 300), (1001, 97), (520, 22), (2100, 30)])
+def test_allpairs_tensor_core_vs_simt_and_truth(mdb, oracle_mod, monkeypatch, F, N, layout):
+    """The tcgen05 3xTF32 kernels (F >= 512) against the exact-fp32 SIMT kernel and float64 truth.  F = 2100 spans
+    several super-blocks of the tile walk (53 x 44 tiles of 40 x 48 frames) with ragged edges both ways."""
     O = oracle_mod
+    monkeypatch.setenv("B200RMSD_TC_LAYOUT", layout)
     X = O.synth_md(F, N, seed=21, rg=1.0, sigma=0.15)
     dt = mdb.DeviceTrajectory.from_host(X)
     monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
@@ -371,6 +377,82 @@ def test_allpairs_tensor_core_vs_simt_and_truth(mdb, oracle_mod, monkeypatch, F,
     monkeypatch.delenv("B200RMSD_NO_SYMMETRIC")
     assert np.array_equal(blk, D_full[37:123])
     assert_close(blk, D_tc[37:123], atol=2e-6, what="row block vs mirrored full matrix")
+
+
+@pytest.mark.parametrize("layout", TC_LAYOUTS)
+def test_allpairs_tensor_core_window_sweep(mdb, oracle_mod, monkeypatch, layout):
+    """Row/column windows that start and end anywhere relative to the 40- and 48-frame tile grids, incl. diagonal
+    squares off the origin (symmetric mode with different i- and j-grid origins): every entry equals the full matrix."""
+    import torch
+    from mdtraj_b200 import allpairs as AP
+    monkeypatch.setenv("B200RMSD_TC_LAYOUT", layout)
+    monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
+    X = oracle_mod.synth_md(1300, 40, seed=44, rg=0.8, sigma=0.1)
+    dt = mdb.DeviceTrajectory.from_host(X)
+    monkeypatch.setenv("B200RMSD_NO_SYMMETRIC", "1")
+    full = mdb.rmsd_matrix_device(dt)
+    monkeypatch.delenv("B200RMSD_NO_SYMMETRIC")
+    prep = AP.prepare(dt)
+    for (r0, r1, c0, c1) in [(0, 1300, 0, 1300), (50, 1251, 50, 1251), (47, 1001, 47, 1001), (960, 1300, 960, 1300),
+                             (1, 2, 0, 1300), (0, 1300, 1299, 1300), (39, 41, 47, 49), (1000, 1300, 0, 500),
+                             (119, 121, 143, 145)]:
+        out = torch.full((r1 - r0, 1300), -1.0, dtype=torch.float32, device=dt.device)
+        AP.block(prep, r0, r1, c0, c1, out)
+        got, want = out[:, c0:c1], full[r0:r1, c0:c1]
+        if (r0, r1) == (c0, c1):  # mirrored halves: exactly symmetric, equal to the unmirrored values within float32 noise
+            assert torch.equal(got, got.t())
+            assert torch.equal(torch.triu(got), torch.triu(want))
+            assert (got - want).abs().max().item() < 2e-6
+        else:
+            assert torch.equal(got, want), (r0, r1, c0, c1)
+        assert (out[:, :c0] == -1).all() and (out[:, c1:] == -1).all(), "wrote outside the column window"
+
+
+@pytest.mark.parametrize("layout", TC_LAYOUTS)
+def test_allpairs_tensor_core_degenerate_geometries(mdb, oracle_mod, monkeypatch, layout):
+    """Double largest root of the QCP quartic -- atoms on a line, two-atom selections -- where Newton alone lands on
+    the wrong root (tests/test_qcp_host.py); the epilogue's certificate sends these pairs to the closed form."""
+    O = oracle_mod
+    monkeypatch.setenv("B200RMSD_TC_LAYOUT", layout)
+    monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
+    rng = np.random.default_rng(7)
+    F = 640
+    line = rng.standard_normal((30, 1)) * np.array([[1.0, 0.0, 0.0]]) + 0.01 * rng.standard_normal((F, 30, 3))
+    line = np.einsum("fnk,fkl->fnl", line, O.random_rotations(F, np.random.default_rng(8))).astype(np.float32)
+    for X, idx in ((line, None), (O.synth_md(F, 20, seed=5, rg=0.5, sigma=0.1), [3, 11])):
+        D = mdb.rmsd_matrix(mdb.Trajectory(X.copy()), atom_indices=idx)
+        assert np.isfinite(D).all()
+        for i in (0, 17, F - 1):
+            truth = O.truth_rmsd(X, X, i, atom_indices=idx)
+            m = np.arange(F) != i
+            # sqrt amplifies the ~1e-8 relative uncertainty of a double root where the rmsd is ~0
+            assert_close(D[i][m], truth[m], atol=3e-5, what=f"degenerate all-pairs row {i}")
+
+
+def test_one_vs_many_degenerate_geometries(mdb, oracle_mod):
+    """md.rmsd / superpose on inputs whose QCP quartic has a double largest root (atoms on a line, two-atom
+    selections): qcp_solve's certificate + closed form.  The reference's closed-form root from float32 coefficients
+    is off by up to 2.5e-2 nm here, so the yardstick is float64 truth (three-way check)."""
+    O = oracle_mod
+    rng = np.random.default_rng(17)
+    F = 3000
+    line = rng.standard_normal((30, 1)) * np.array([[1.0, 0.0, 0.0]]) + 0.01 * rng.standard_normal((F, 30, 3))
+    line = np.einsum("fnk,fkl->fnl", line, O.random_rotations(F, rng)).astype(np.float32)
+    for X, idx in ((line, None), (O.synth_md(F, 20, seed=6, rg=0.5, sigma=0.1), [3, 11]), (O.synth_iid(F, 2, seed=7), None)):
+        t = mdb.Trajectory(X.copy())
+        got = mdb.rmsd(t, t, 5, atom_indices=idx)
+        truth = O.truth_rmsd(X, X, 5, atom_indices=idx)
+        m = np.arange(F) != 5
+        assert_close(got[m], truth[m], atol=3e-5, what="degenerate one-vs-many")
+        ref = O.rmsd(X, X, 5, atom_indices=idx, impl="reference" if O.ref_available() else "port")
+        assert_three_way(got[m], ref[m], truth[m], what="degenerate one-vs-many vs reference", atol=3e-5)
+        dt = mdb.DeviceTrajectory.from_host(X)
+        dt.superpose(dt, 5, atom_indices=idx)   # rotations are undetermined here; the result must stay finite and rigid
+        Y = dt.xyz
+        assert np.isfinite(Y).all()
+        d0 = np.linalg.norm(X[:, 0] - X[:, 1], axis=1)
+        d1 = np.linalg.norm(Y[:, 0] - Y[:, 1], axis=1)
+        assert np.abs(d0 - d1).max() < 1e-5
 
 
 # ------------------------------------------------------------------ "next" rows: rmsf, align/displace
@@ -487,10 +569,12 @@ def test_superpose_and_center_properties_at_scale(mdb, F, N, stride):
     assert (pre - fly)[1:].abs().max().item() < 1e-5
 
 
-def test_allpairs_block_api(mdb, oracle_mod, monkeypatch):
+@pytest.mark.parametrize("layout", TC_LAYOUTS)
+def test_allpairs_block_api(mdb, oracle_mod, monkeypatch, layout):
     """b200rmsd_allpairs_block_dev: rectangular blocks, transposed copies and diagonal squares on both kernels."""
     import torch
     from mdtraj_b200 import allpairs as AP
+    monkeypatch.setenv("B200RMSD_TC_LAYOUT", layout)
     X = oracle_mod.synth_md(700, 64, seed=33, rg=0.8, sigma=0.1)
     dt = mdb.DeviceTrajectory.from_host(X)
     for path in ("tc", "simt"):

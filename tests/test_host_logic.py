@@ -169,3 +169,51 @@ def test_frame_resident_geometry_invariants():
                         assert lanes == 32
                     seen_multi |= fpb > 1
     assert seen_multi
+
+
+def test_allpairs_tile_walk_covers_every_pair_once():
+    """The tile walk of the tensor-core all-pairs kernel (csrc/allpairs_tc144.cu: tc144_tiling + tile_of_slot, through
+    the host-only debug hook): 40 x 48-frame tiles, super-block order, tiles under the diagonal skipped in symmetric
+    mode.  Every pair of the block (every pair with j >= i in symmetric mode) must lie in exactly one visited tile."""
+    import ctypes
+
+    import numpy as np
+
+    from mdtraj_b200 import _capi
+    L = ctypes.CDLL(_capi.LIB_PATH)
+    fn = L.b200rmsd_debug_allpairs_tiles
+    fn.restype = ctypes.c_longlong
+    fn.argtypes = [ctypes.c_longlong] * 4 + [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_longlong,
+                                             ctypes.POINTER(ctypes.c_int)]
+    cap = 200000
+    buf = (ctypes.c_int * (2 * cap))()
+    sym = ctypes.c_int()
+    cases = [(0, 512, 0, 512, 0), (0, 2000, 0, 2000, 0), (0, 2000, 0, 2000, 1), (50, 1990, 50, 1990, 0),
+             (47, 1001, 47, 1001, 0), (960, 2880, 960, 2880, 0), (0, 40, 0, 3000, 0), (123, 777, 0, 3000, 0),
+             (0, 3000, 500, 548, 0), (1000, 1500, 1500, 2500, 1), (1500, 2500, 1000, 1500, 1), (0, 1, 0, 1, 0),
+             (2999, 3000, 0, 3000, 0), (0, 5000, 0, 5000, 0)]
+    for row0, row1, col0, col1, has_t in cases:
+        n = fn(row0, row1, col0, col1, has_t, buf, cap, ctypes.byref(sym))
+        assert 0 < n <= cap, (row0, row1, col0, col1)
+        tiles = np.frombuffer(buf, dtype=np.int32, count=2 * n).reshape(n, 2).astype(np.int64)
+        assert len({(a, b) for a, b in tiles.tolist()}) == n, "a tile is visited twice"
+        symmetric = bool(sym.value)
+        assert symmetric == (row0 == col0 and row1 == col1 and not has_t)
+        # count, for every pair of the block, the visited tiles that contain it
+        cover = np.zeros((row1 - row0, col1 - col0), np.int32)
+        for ti, tj in tiles:
+            i0, i1 = max(row0, ti * 40), min(row1, ti * 40 + 40)
+            j0, j1 = max(col0, tj * 48), min(col1, tj * 48 + 48)
+            assert i0 < i1 and j0 < j1, "a visited tile lies outside the block"
+            cover[i0 - row0:i1 - row0, j0 - col0:j1 - col0] += 1
+        if symmetric:
+            need = np.triu(np.ones_like(cover))
+            assert (cover[need == 1] == 1).all()
+            # no tile that lies entirely under the diagonal is visited
+            assert all(tj * 48 + 47 >= ti * 40 for ti, tj in tiles)
+        else:
+            assert (cover == 1).all()
+        # super-block locality: the ~148 tiles in flight touch few distinct operand tiles (they stay L2-resident)
+        for k in range(0, max(1, n - 148), 97):
+            win = tiles[k:k + 148]
+            assert len(set(win[:, 0].tolist())) + len(set(win[:, 1].tolist())) <= 3 * (24 + 20)

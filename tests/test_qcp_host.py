@@ -1,0 +1,166 @@
+"""CPU: the device QCP solvers' SOURCE (mdtraj_b200/csrc/qcp.cuh), compiled for the host through a shim
+(tests/host_qcp/), against float64 truth (largest eigenvalue of the 4x4 key matrix by numpy.linalg.eigvalsh).
+
+This is a check of the arithmetic the CUDA kernels run, on inputs the GPU parity tests cannot sweep as widely --
+in particular the ill-conditioned ones: atoms on a line and two-atom selections give the QCP quartic a double largest
+root, where Newton converges linearly and float32 rounding can throw it onto the wrong root.  (The reference takes the
+closed-form root, theobald_rmsd.cpp:183-193, but from float32 coefficients: on these inputs it is itself off by up to
+2.5e-2 nm against float64 truth -- measured with oracle/_ref -- so truth, not the reference, is the yardstick here.)
+The product never runs this build: it exists under tests/."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_qcp", "qcp_host.cpp")
+P = ctypes.c_void_p
+
+
+@pytest.fixture(scope="module")
+def L(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("qcp_host") / "libqcp_host.so")
+    # -ffp-contract=off: no FMA contraction the device compiler would not also be free to undo; plain IEEE arithmetic
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off",
+                    "-I" + os.path.join(HERE, "host_qcp", "shim"), "-o", so, SRC], check=True)
+    lib = ctypes.CDLL(so)
+    lib.host_qcp_slow_count.restype = ctypes.c_long
+    return lib
+
+
+def _rot(rng, n):
+    q = rng.standard_normal((n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    a, b, c, d = q.T
+    return np.stack([a*a+b*b-c*c-d*d, 2*(b*c-a*d), 2*(b*d+a*c), 2*(b*c+a*d), a*a-b*b+c*c-d*d, 2*(c*d-a*b),
+                     2*(b*d-a*c), 2*(c*d+a*b), a*a-b*b-c*c+d*d], 1).reshape(n, 3, 3)
+
+
+def make_pairs(kind, n, n_atoms, seed):
+    """n pairs of centred frames -> (M (n,3,3), Ga, Gb) in float64 from float32-representable coordinates."""
+    rng = np.random.default_rng(seed)
+    shape = (n, n_atoms, 3)
+    if kind == "iid":
+        A, B = rng.standard_normal(shape), rng.standard_normal(shape)
+    elif kind == "same":
+        A = rng.standard_normal(shape)
+        B = A.copy()
+    else:
+        scale = {"md": (1, 1, 1), "mirror": (1, 1, 1), "planar": (1, 1, 0), "line": (1, 0, 0), "rod2": (1, 1e-2, 1e-2),
+                 "rod3": (1, 1e-3, 1e-3), "rod15": (1, 3e-2, 3e-2)}[kind]
+        base = rng.standard_normal((n_atoms, 3)) * np.array(scale, float)
+        sig = 0.1 if kind in ("md", "mirror") else 0.02
+        A = base + sig * rng.standard_normal(shape)
+        B = (base * np.array([1, 1, -1.0]) if kind == "mirror" else base) + sig * rng.standard_normal(shape)
+    B = np.einsum("pnk,pkl->pnl", B, _rot(rng, n))
+    A -= A.mean(1, keepdims=True)
+    B -= B.mean(1, keepdims=True)
+    A = A.astype(np.float32).astype(np.float64)
+    B = B.astype(np.float32).astype(np.float64)
+    return np.einsum("pni,pnj->pij", A, B), (A * A).sum((1, 2)), (B * B).sum((1, 2))
+
+
+def truth_rmsd(M, Ga, Gb, n_atoms):
+    Sxx, Sxy, Sxz, Syx, Syy, Syz, Szx, Szy, Szz = [M[:, i, j] for i in range(3) for j in range(3)]
+    K = np.zeros((len(M), 4, 4))
+    K[:, 0, 0] = Sxx + Syy + Szz; K[:, 0, 1] = Szy - Syz; K[:, 0, 2] = Sxz - Szx; K[:, 0, 3] = Syx - Sxy
+    K[:, 1, 1] = Sxx - Syy - Szz; K[:, 1, 2] = Syx + Sxy; K[:, 1, 3] = Sxz + Szx
+    K[:, 2, 2] = -Sxx + Syy - Szz; K[:, 2, 3] = Szy + Syz; K[:, 3, 3] = -Sxx - Syy + Szz
+    K = K + np.triu(K, 1).transpose(0, 2, 1)
+    lam = np.linalg.eigvalsh(K)[:, -1]
+    return np.sqrt(np.maximum(Ga + Gb - 2 * lam, 0) / n_atoms)
+
+
+def run_solve(L, M, Ga, Gb, n_atoms, want_rot=False):
+    n = len(M)
+    msd = np.empty(n)
+    deg = np.empty(n, np.uint8)
+    rot = np.empty((n, 9), np.float32) if want_rot else None
+    Mc = np.ascontiguousarray(M.reshape(n, 9))
+    L.host_qcp_solve(P(Mc.ctypes.data), P(Ga.ctypes.data), P(Gb.ctypes.data), n_atoms, ctypes.c_long(n),
+                     P(msd.ctypes.data), P(rot.ctypes.data) if want_rot else None, P(deg.ctypes.data))
+    return np.sqrt(msd), rot, deg
+
+
+def run_fast(L, M, Ga, Gb, n_atoms, f32=0):
+    n = len(M)
+    r = np.empty(n, np.float32)
+    Mc = np.ascontiguousarray(M.reshape(n, 9).astype(np.float32))
+    ga, gb = Ga.astype(np.float32), Gb.astype(np.float32)
+    L.host_qcp_msd_fast(P(Mc.ctypes.data), P(ga.ctypes.data), P(gb.ctypes.data), n_atoms, ctypes.c_long(n), f32,
+                        P(r.ctypes.data))
+    # truth for the float32-rounded inputs the epilogue actually sees
+    return r, truth_rmsd(Mc.astype(np.float64).reshape(n, 3, 3), ga.astype(np.float64), gb.astype(np.float64), n_atoms)
+
+
+WELL = [("iid", 300), ("md", 300), ("md", 22), ("mirror", 300), ("planar", 300), ("iid", 3), ("md", 3), ("iid", 4),
+        ("rod15", 300)]
+ILL = [("line", 300), ("rod3", 300), ("rod2", 300), ("iid", 2), ("md", 2)]
+
+
+@pytest.mark.parametrize("kind,n_atoms", WELL + ILL)
+def test_qcp_solve_matches_float64_truth(L, kind, n_atoms):
+    """qcp_solve (one-vs-many, superpose, SIMT all-pairs): 1e-5 nm everywhere, incl. double-root inputs."""
+    M, Ga, Gb = make_pairs(kind, 4000, n_atoms, seed=11)
+    want = truth_rmsd(M, Ga, Gb, n_atoms)
+    L.host_qcp_slow_count(1)
+    got, _, _ = run_solve(L, M, Ga, Gb, n_atoms)
+    n_slow = L.host_qcp_slow_count(1)
+    err = np.abs(got - want)
+    # sqrt amplifies the ~1e-8 relative uncertainty of a double root when the rmsd itself is ~0: allow 3e-5 there
+    assert err.max() <= (1e-5 if (kind, n_atoms) in WELL else 3e-5), (kind, n_atoms, err.max())
+    if (kind, n_atoms) in WELL:
+        assert n_slow == 0, "the closed-form slow path must stay off well-conditioned inputs"
+    if kind == "line" or n_atoms == 2:
+        assert n_slow > 0
+
+
+@pytest.mark.parametrize("kind,n_atoms", WELL + ILL)
+def test_allpairs_epilogue_solver_matches_float64_truth(L, kind, n_atoms):
+    """qcp_msd_fast + the caller-side closed form (tcgen05 all-pairs epilogue): float32 inputs, float32 sqrt."""
+    M, Ga, Gb = make_pairs(kind, 4000, n_atoms, seed=12)
+    L.host_qcp_slow_count(1)
+    got, want = run_fast(L, M, Ga, Gb, n_atoms)
+    n_slow = L.host_qcp_slow_count(1)
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= 1e-6, (kind, n_atoms, np.abs(got - want).max())
+    if (kind, n_atoms) in WELL and kind != "rod15" and (kind, n_atoms) != ("iid", 3):
+        assert n_slow == 0
+
+
+def test_identical_frames_give_zero(L):
+    M, Ga, Gb = make_pairs("same", 2000, 50, seed=5)
+    got, _, _ = run_solve(L, M, Ga, Gb, 50)
+    assert got.max() <= 1e-6   # sqrt of ~1e-14 relative cancellation noise
+    fast, _ = run_fast(L, M, Ga, Gb, 50)
+    assert fast.max() <= 2e-3  # float32 traces: the reference returns 6.3e-3 here
+
+
+def test_float32_solver_is_reference_class(L):
+    """B200RMSD_FAST_SOLVE / precise=False: all-float32 polynomial; errors of the reference's own class on
+    well-conditioned pairs, closed form when its certificate fails."""
+    for kind, n_atoms, tol in (("iid", 300, 1e-6), ("md", 300, 1e-5), ("planar", 300, 2e-5)):
+        M, Ga, Gb = make_pairs(kind, 4000, n_atoms, seed=13)
+        got, want = run_fast(L, M, Ga, Gb, n_atoms, f32=1)
+        assert np.abs(got - want).max() <= tol, (kind, np.abs(got - want).max())
+
+
+def test_rotation_superposes(L):
+    """qcp_solve's rotation: applying it to frame a reproduces the reported RMSD against frame b."""
+    rng = np.random.default_rng(3)
+    n, N = 500, 64
+    base = rng.standard_normal((N, 3))
+    A = base + 0.1 * rng.standard_normal((n, N, 3))
+    B = np.einsum("pnk,pkl->pnl", base + 0.1 * rng.standard_normal((n, N, 3)), _rot(rng, n))
+    A -= A.mean(1, keepdims=True)
+    B -= B.mean(1, keepdims=True)
+    M = np.einsum("pni,pnj->pij", A, B)
+    got, rot, deg = run_solve(L, M, (A * A).sum((1, 2)), (B * B).sum((1, 2)), N, want_rot=True)
+    assert not deg.any()
+    R = rot.reshape(n, 3, 3).astype(np.float64)
+    assert np.abs(np.linalg.det(R) - 1).max() < 1e-5
+    moved = np.einsum("pnk,pkl->pnl", A, R)  # row vector x R (rotation_generic.h:40-42)
+    rmsd = np.sqrt(((moved - B) ** 2).sum((1, 2)) / N)
+    assert np.abs(rmsd - got).max() < 1e-5
