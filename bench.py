@@ -351,7 +351,8 @@ def main():
                 kernel_events.append((e0, e1))
         units_per_step = (r1 - r0) * F
         algo_bytes = None
-        dominant = "allpairs_tc_kernel"
+        dominant = ("allpairs_tc_kernel" if os.environ.get("B200RMSD_TC_LAYOUT", "d")[0] == "g"
+                    else "allpairs_tc144_kernel")
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -458,15 +459,26 @@ def main():
         tpeak, tsrc = tf32_peak()
         kpad = (N + 31) // 32 * 32
         pairs_per_s = units_per_step / (kern_ms * 1e-3)
-        # flops actually issued: 128x128 tiles (40x40 frames), three tf32 MMAs per K-step, K padded to 32; a
-        # single-rank full matrix computes the upper triangle of tiles only and mirrors it
-        T = -(-F // 40)
-        tiles = T * (T + 1) // 2 if world == 1 else T * (T + 1) // 2 / world  # symmetric plan: ~T^2/2 tiles over all ranks
-        issued = tiles * 128 * 128 * kpad * 2 * 3 / (kern_ms * 1e-3) / 1e12
+        # flops actually issued: three tf32 MMAs per K-step over the tiles the kernel computes, K padded to 32; a
+        # single-rank full matrix computes each unordered pair once (tiles holding no pair j >= i are skipped)
+        if os.environ.get("B200RMSD_TC_LAYOUT", "d")[0] == "g":   # csrc/allpairs_tc.cu: 128x128 tiles = 40x40 frames
+            T = -(-F // 40)
+            tiles, mma_n = T * (T + 1) // 2, 128
+        else:                                                      # csrc/allpairs_tc144.cu: 128x144 tiles = 40x48 frames
+            import ctypes
+            from mdtraj_b200 import _capi
+            hook = ctypes.CDLL(_capi.LIB_PATH).b200rmsd_debug_allpairs_tiles   # host-only: walks the kernel's tile order
+            hook.restype = ctypes.c_longlong
+            hook.argtypes = [ctypes.c_longlong] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
+            tiles, mma_n = int(hook(0, F, 0, F, 0, None, 0, None)), 144
+        if world > 1:
+            tiles = tiles / world  # symmetric block plan: every unordered pair of row blocks on exactly one rank
+        issued = tiles * 128 * mma_n * kpad * 2 * 3 / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": dominant, "achieved": issued, "peak": tpeak, "unit": "TFLOP/s",
                     "frac": issued / tpeak, "traffic": ncu_traffic("allpairs"), "peak_source": tsrc, "kernel_ms": kern_ms,
                     "useful_tflops": pairs_per_s * 18 * N / 1e12,
-                    "note": "achieved = tensor flops actually issued (3 tf32 MMAs per K-step over the computed 128x128 "
+                    "tiles_per_launch": tiles, "mma_shape": [128, mma_n, 8],
+                    "note": "achieved = tensor flops actually issued (3 tf32 MMAs per K-step over the computed "
                             "tiles; symmetric tiles computed once); useful = 18 * A flops per reported pair"}
 
     cpu = None

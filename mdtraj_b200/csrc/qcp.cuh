@@ -174,7 +174,10 @@ __device__ __forceinline__ double qcp_solve(const QcpInput& in, float* rot, bool
 
     bool trusted;
     double lam = qcp_newton(C2, C1, C0, 0.5 * (in.Ga + in.Gb), ss, &trusted);
-    if (!trusted) lam = qcp_lambda_closed(in.M);
+    if (!trusted) {  // rare; the copy keeps `in` itself out of local memory (its address would escape otherwise)
+        double m[9] = {Sxx, Sxy, Sxz, Syx, Syy, Syz, Szx, Szy, Szz};
+        lam = qcp_lambda_closed(m);
+    }
     double msd = (in.Ga + in.Gb - 2.0 * lam) / in.n_atoms;
     if (!(msd > 0.0)) msd = 0.0;
 
