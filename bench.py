@@ -351,8 +351,7 @@ def main():
                 kernel_events.append((e0, e1))
         units_per_step = (r1 - r0) * F
         algo_bytes = None
-        dominant = ("allpairs_tc_kernel" if os.environ.get("B200RMSD_TC_LAYOUT", "d")[0] == "g"
-                    else "allpairs_tc144_kernel")
+        dominant = "allpairs_tc144_kernel"
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -461,16 +460,13 @@ def main():
         pairs_per_s = units_per_step / (kern_ms * 1e-3)
         # flops actually issued: three tf32 MMAs per K-step over the tiles the kernel computes, K padded to 32; a
         # single-rank full matrix computes each unordered pair once (tiles holding no pair j >= i are skipped)
-        if os.environ.get("B200RMSD_TC_LAYOUT", "d")[0] == "g":   # csrc/allpairs_tc.cu: 128x128 tiles = 40x40 frames
-            T = -(-F // 40)
-            tiles, mma_n = T * (T + 1) // 2, 128
-        else:                                                      # csrc/allpairs_tc144.cu: 128x144 tiles = 40x48 frames
-            import ctypes
-            from mdtraj_b200 import _capi
-            hook = ctypes.CDLL(_capi.LIB_PATH).b200rmsd_debug_allpairs_tiles   # host-only: walks the kernel's tile order
-            hook.restype = ctypes.c_longlong
-            hook.argtypes = [ctypes.c_longlong] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
-            tiles, mma_n = int(hook(0, F, 0, F, 0, None, 0, None)), 144
+        import ctypes
+        from mdtraj_b200 import _capi
+        hook = ctypes.CDLL(_capi.LIB_PATH).b200rmsd_debug_allpairs_tiles   # host-only: walks the kernel's tile order
+        hook.restype = ctypes.c_longlong
+        hook.argtypes = [ctypes.c_longlong] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
+        tiles, mma_n = int(hook(0, F, 0, F, 0, None, 0, None)), 144      # 128x144 tiles = 40x48 frames
+        kpad = (((N + 7) // 8 * 8) + 6 + 31) // 32 * 32                   # atoms + 6 augmentation columns, padded to 32
         if world > 1:
             tiles = tiles / world  # symmetric block plan: every unordered pair of row blocks on exactly one rank
         issued = tiles * 128 * mma_n * kpad * 2 * 3 / (kern_ms * 1e-3) / 1e12

@@ -187,8 +187,24 @@ int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atom
     const int sm = ap_sm_count();
     cudaError_t e;
     if (g.tc) {
-        e = (g.dense ? launch_allpairs_tc144_prepare : launch_allpairs_tc_prepare)(xyz, n_frames, frame_stride, idx, ns, g.k_pad, (float*)(base + g.hi_off),
-                                       (float*)(base + g.lo_off), (float*)(base + g.traces_off), g.rows_pad, sm, st);
+        // Align every frame onto frame 0 first (one one-vs-many pass with rotations): the RMSD of a pair does not change
+        // under a rigid motion of either frame, and for frames of one ensemble the aligned frames differ from the
+        // common reference by fluctuations only -- which is what keeps the tensor-core accumulators small
+        // (allpairs_tc144_prepare_kernel).
+        float* ref = (float*)(base + g.ref_off);
+        void* stats = base + g.stats_off;
+        float* rot = (float*)(base + g.rot_off);
+        double* cen = (double*)(base + g.cen_off);
+        if (int rc = b200rmsd_prepare_reference_dev(xyz, idx, ns, 1, 0.f, ref, stats, stream)) return rc;
+        if (int rc = b200rmsd_rmsd_dev(xyz, n_frames, n_atoms, frame_stride, idx, ns, ref, stats, nullptr, 0,
+                                       (float*)(base + g.rmsd_off), rot, cen, nullptr, base + g.scratch_off,
+                                       g.scratch_bytes, stream))
+            return rc;
+        e = launch_allpairs_tc144_prepare(xyz, n_frames, frame_stride, idx, ns, g.k_pad, ref, stats,
+                                          (const float*)(base + g.rmsd_off), rot, cen,
+                                          (float*)(base + g.a_hi_off), (float*)(base + g.a_lo_off),
+                                          (float*)(base + g.b_hi_off), (float*)(base + g.b_lo_off),
+                                          (float*)(base + g.traces_off), g.rows_pad, sm, st);
     } else {
         int64_t ctas = (int64_t)sm * 8;
         const int64_t need = (n_frames + 7) / 8;
@@ -212,9 +228,10 @@ int b200rmsd_allpairs_block_dev(const void* workspace, size_t workspace_bytes, i
     if (row0 == row1 || col0 == col1) return 0;
     const char* base = (const char*)workspace;
     if (g.tc)
-        return (g.dense ? launch_allpairs_tc144_block : launch_allpairs_tc_block)((const float*)(base + g.hi_off), (const float*)(base + g.lo_off),
-                                        (const float*)(base + g.traces_off), n_frames, n_sel, g.k_pad, g.rows_pad, row0,
-                                        row1, col0, col1, out, ld, out_t, ld_t, flags, ap_sm_count(), (cudaStream_t)stream);
+        return launch_allpairs_tc144_block((const float*)(base + g.a_hi_off), (const float*)(base + g.a_lo_off),
+                                           (const float*)(base + g.b_hi_off), (const float*)(base + g.b_lo_off),
+                                           (const float*)(base + g.traces_off), n_sel, g.k_pad, g.rows_pad, row0, row1,
+                                           col0, col1, out, ld, out_t, ld_t, flags, ap_sm_count(), (cudaStream_t)stream);
     dim3 grid((unsigned)((col1 - col0 + kTile - 1) / kTile), (unsigned)((row1 - row0 + kTile - 1) / kTile));
     if (grid.y > 65535) return fail(B200RMSD_EINVAL, "allpairs_block: at most 65535*32 rows per call");
     allpairs_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)(base + g.x_off),

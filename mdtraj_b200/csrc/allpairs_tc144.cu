@@ -5,8 +5,11 @@
 // QCP polynomial of every 3x3 block and writes only the RMSD (arithmetic of each pair == msdFromMandG,
 // theobald_rmsd.cpp:217-334; replaces the Python loop of F md.rmsd calls, examples/clustering.ipynb:78-81).
 //
-//   operands   ONE pair of K-major fp32 matrices (tf32 "hi" and "lo" parts, hi = rna_tf32(x), lo = rna_tf32(x-hi)),
-//              row 3f+c = component c of frame f, K = atoms padded to 32; no padding rows;
+//   operands   K-major fp32 matrices in tf32 "hi" and "lo" parts (hi = rna_tf32(x), lo = rna_tf32(x-hi)), row 3f+c =
+//              component c of frame f, no padding rows.  A = the frames aligned onto a common reference c (frame 0),
+//              B = their differences from c; six extra K columns add X'_i c^T to every block inside the GEMM, so that
+//              the accumulator holds X'_i D_j^T (fluctuation-sized) until the last K-step -- the tensor core's fp32
+//              accumulation truncates, and the bias is proportional to the running sum (allpairs_tc144_prepare_kernel);
 //   tile       40 i-frames x 48 j-frames.  The A operand (M = 128 TMEM lanes) is brought by FOUR 32-row TMA boxes
 //              starting at rows 120*ti + 30*w, so that each epilogue warp's lane quarter holds 10 whole frames (lanes 30
 //              and 31 of a quarter carry the first rows of the next frame and are ignored); the B operand (N = 144
@@ -94,43 +97,91 @@ __device__ __forceinline__ float sel3(int c, float a0, float a1, float a2) { ret
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// prepare: centre every frame (center_generic.h:3-44 semantics), write tf32 hi/lo rows + traces.
-// One warp per frame; row of (frame f, component c) = 3 f + c.
+// prepare: operands and traces.  One warp per frame.
+//
+// The tensor core accumulates in fp32 with truncation: measured on B200 (tools/tc_acc_probe.py) the sum of 300 products
+// comes out ~17 ulp short of its float64 value, always towards zero.  For frames of one ensemble the inner products are
+// large (~N Rg^2 / 3) while the quantity of interest, G_a + G_b - 2 lambda, is N rmsd^2: a 5e-4 bias on M costs 4e-5 nm
+// on a 0.24 nm RMSD (N = 300, Rg = 1 nm), outside the 1e-5 / 1e-4 parity tolerance.  The RMSD of a pair is unchanged by
+// a rigid motion of either frame, so every frame is first aligned onto one common reference c (frame 0, centred):
+// x' = (x - centroid) . R with R, centroid from the one-vs-many kernel.  With d_j = x'_j - c,
+//
+//     M_ij = sum_k x'_ik x'_jk^T = sum_k x'_ik d_jk^T  +  G_i,     G_i = sum_k x'_ik c_k^T   (3x3, float64 here),
+//
+// and the GEMM only has to accumulate X'_i D_j^T, whose entries are fluctuation-sized (~sqrt(N) Rg sigma instead of
+// N Rg^2 / 3: 50 times smaller at sigma = 0.1 nm).  G_i enters the same accumulator through six augmentation columns of
+// K placed in a K-step of their own after the atoms -- A row (i,c) carries the tf32 pieces g1, g2 of G_i[c][0..2], B row
+// (j,q) carries the unit vector e_q twice -- i.e. as the LAST non-zero K-step: one truncation at full magnitude instead
+// of one per accumulation step (a third piece g3 rides in the lo matrix).  The choice is made per column frame: a frame
+// farther from c than half its own size (N rmsd_j^2 >= G_c / 4; iid test data, other basins) keeps b_j = x'_j and a zero
+// in place of e_q, because there X'_i D_j^T and G_i would be two large numbers cancelling -- worse than the plain product.
+// Centring follows center_generic.h:3-44 (float64 mean, float32 subtraction, float64 trace of the float32 squares);
+// the float32 rotation deforms a frame by ~1e-7 relative, 1e-7 nm of RMSD.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) allpairs_tc144_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames,
-                                                                     int64_t frame_stride, const int* __restrict__ idx,
-                                                                     int n_sel, int k_pad, float* __restrict__ hi,
-                                                                     float* __restrict__ lo, float* __restrict__ traces)
+__global__ void __launch_bounds__(256)
+allpairs_tc144_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames, int64_t frame_stride,
+                              const int* __restrict__ idx, int n_sel, int k_pad, const float* __restrict__ ref,
+                              const RefStats* __restrict__ ref_stats, const float* __restrict__ rmsd_to_ref,
+                              const float* __restrict__ rot, const double* __restrict__ centroid,
+                              float* __restrict__ a_hi, float* __restrict__ a_lo, float* __restrict__ b_hi,
+                              float* __restrict__ b_lo, float* __restrict__ traces)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_warps = (int64_t)gridDim.x * 8;
+    const int k0 = ap_tc144_k0(n_sel);
+    const float near2 = 0.25f * (float)ref_stats->G / (float)n_sel;  // rmsd^2 to c below which b_j = c + d_j
     for (int64_t f = (int64_t)blockIdx.x * 8 + warp; f < n_frames; f += n_warps) {
         const float* fr = xyz + f * frame_stride;
-        double sx = 0, sy = 0, sz = 0;
+        float R[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = __ldg(rot + f * 9 + i);
+        const float mx = (float)__ldg(centroid + f * 3), my = (float)__ldg(centroid + f * 3 + 1),
+                    mz = (float)__ldg(centroid + f * 3 + 2);
+        const int64_t row = ap_tc144_row(f, 0);
+        const float r_ref = __ldg(rmsd_to_ref + f);
+        const bool near = r_ref * r_ref < near2;  // warp-uniform
+        double tr = 0, G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int k = lane; k < n_sel; k += 32) {
             const int a = idx ? __ldg(idx + k) : k;
-            sx += (double)__ldg(fr + 3 * a); sy += (double)__ldg(fr + 3 * a + 1); sz += (double)__ldg(fr + 3 * a + 2);
-        }
-        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-        const float mx = (float)(sx / n_sel), my = (float)(sy / n_sel), mz = (float)(sz / n_sel);
-        const int64_t row = ap_tc144_row(f, 0);
-        double tr = 0;
-        for (int k = lane; k < k_pad; k += 32) {
-            float v[3] = {0.f, 0.f, 0.f};
-            if (k < n_sel) {
-                const int a = idx ? __ldg(idx + k) : k;
-                v[0] = __ldg(fr + 3 * a) - mx; v[1] = __ldg(fr + 3 * a + 1) - my; v[2] = __ldg(fr + 3 * a + 2) - mz;
-                tr += (double)(v[0] * v[0]); tr += (double)(v[1] * v[1]); tr += (double)(v[2] * v[2]);
+            const float tx = __ldg(fr + 3 * a) - mx, ty = __ldg(fr + 3 * a + 1) - my, tz = __ldg(fr + 3 * a + 2) - mz;
+            float v[3], cr[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {  // row vector x R (rotation_generic.h:40-42)
+                v[m] = fmaf(tz, R[6 + m], fmaf(ty, R[3 + m], tx * R[m]));
+                cr[m] = __ldg(ref + 3 * k + m);
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
+                tr += (double)(v[c] * v[c]);
+#pragma unroll
+                for (int m = 0; m < 3; ++m) G[3 * c + m] += (double)v[c] * (double)cr[m];
                 const float h = rna_tf32(v[c]);
-                hi[(row + c) * k_pad + k] = h;
-                lo[(row + c) * k_pad + k] = rna_tf32(v[c] - h);
+                a_hi[(row + c) * k_pad + k] = h;
+                a_lo[(row + c) * k_pad + k] = rna_tf32(v[c] - h);
+                const float d = near ? v[c] - cr[c] : v[c];
+                const float dh = rna_tf32(d);
+                b_hi[(row + c) * k_pad + k] = dh;
+                b_lo[(row + c) * k_pad + k] = rna_tf32(d - dh);
             }
         }
         tr = warp_sum(tr);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) G[i] = warp_sum(G[i]);
         if (lane == 0) traces[f] = (float)tr;
+        // augmentation columns k0 + 3p + m, p = 0,1: A_hi row c <- piece p of G[c][m] (the third piece in A_lo under
+        // piece 0); B_hi row q <- (q == m) for the frames that are stored as differences
+        if (lane < 18) {
+            const int piece = lane / 9, c = (lane % 9) / 3, m = lane % 3;
+            double g = 0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) g = (i == 3 * c + m) ? G[i] : g;  // static indexing keeps G in registers
+            const float g1 = rna_tf32((float)g);
+            const float g2 = rna_tf32((float)(g - (double)g1));
+            const float g3 = rna_tf32((float)(g - (double)g1 - (double)g2));
+            a_hi[(row + c) * k_pad + k0 + 3 * piece + m] = piece == 0 ? g1 : g2;
+            if (piece == 0) a_lo[(row + c) * k_pad + k0 + m] = g3;
+            if (c == m && near) b_hi[(row + c) * k_pad + k0 + 3 * piece + m] = 1.0f;
+        }
     }
 }
 
@@ -380,31 +431,34 @@ extern "C" long long b200rmsd_debug_allpairs_tiles(long long row0, long long row
 }
 
 cudaError_t launch_allpairs_tc144_prepare(const float* xyz, int64_t n_frames, int64_t frame_stride, const int* idx,
-                                          int n_sel, int k_pad, float* hi, float* lo, float* traces, int64_t rows_pad,
+                                          int n_sel, int k_pad, const float* ref, const void* ref_stats,
+                                          const float* rmsd_to_ref, const float* rot, const double* centroid, float* a_hi,
+                                          float* a_lo, float* b_hi, float* b_lo, float* traces, int64_t rows_pad,
                                           int sm_count, cudaStream_t st)
 {
-    // rows past 3F are read by the last tiles' boxes: they must hold finite numbers
-    cudaError_t e = cudaMemsetAsync(hi, 0, (size_t)rows_pad * k_pad * 4, st);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(lo, 0, (size_t)rows_pad * k_pad * 4, st);
-    if (e != cudaSuccess) return e;
+    // K padding, the lo parts of the augmentation columns and the rows past 3F (read by the last tiles' boxes) are zero
+    float* ops[4] = {a_hi, a_lo, b_hi, b_lo};
+    for (float* o : ops) {
+        cudaError_t e = cudaMemsetAsync(o, 0, (size_t)rows_pad * k_pad * 4, st);
+        if (e != cudaSuccess) return e;
+    }
     int64_t ctas = (int64_t)sm_count * 8;
     const int64_t need = (n_frames + 7) / 8;
     if (ctas > need) ctas = need;
-    allpairs_tc144_prepare_kernel<<<(unsigned)ctas, 256, 0, st>>>(xyz, n_frames, frame_stride, idx, n_sel, k_pad, hi, lo,
-                                                                  traces);
+    allpairs_tc144_prepare_kernel<<<(unsigned)ctas, 256, 0, st>>>(xyz, n_frames, frame_stride, idx, n_sel, k_pad, ref,
+                                                                  (const RefStats*)ref_stats, rmsd_to_ref, rot, centroid,
+                                                                  a_hi, a_lo, b_hi, b_lo, traces);
     return cudaGetLastError();
 }
 
-int launch_allpairs_tc144_block(const float* hi, const float* lo, const float* traces, int64_t n_frames, int n_sel,
-                                int k_pad, int64_t rows_pad, int64_t row0, int64_t row1, int64_t col0, int64_t col1,
-                                float* out, int64_t ld, float* out_t, int64_t ld_t, unsigned flags, int sm_count,
-                                cudaStream_t st)
+int launch_allpairs_tc144_block(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
+                                const float* traces, int n_sel, int k_pad, int64_t rows_pad, int64_t row0, int64_t row1,
+                                int64_t col0, int64_t col1, float* out, int64_t ld, float* out_t, int64_t ld_t,
+                                unsigned flags, int sm_count, cudaStream_t st)
 {
-    (void)n_frames;
     CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
-    if (!make_operand_map(&map_a_hi, hi, rows_pad, k_pad, 32) || !make_operand_map(&map_a_lo, lo, rows_pad, k_pad, 32) ||
-        !make_operand_map(&map_b_hi, hi, rows_pad, k_pad, kN) || !make_operand_map(&map_b_lo, lo, rows_pad, k_pad, kN))
+    if (!make_operand_map(&map_a_hi, a_hi, rows_pad, k_pad, 32) || !make_operand_map(&map_a_lo, a_lo, rows_pad, k_pad, 32) ||
+        !make_operand_map(&map_b_hi, b_hi, rows_pad, k_pad, kN) || !make_operand_map(&map_b_lo, b_lo, rows_pad, k_pad, kN))
         return set_error(B200RMSD_ECUDA, "allpairs: cuTensorMapEncodeTiled failed");
     Tc144Params p = tc144_tiling(row0, row1, col0, col1, out_t != nullptr);
     p.traces = traces;

@@ -228,6 +228,30 @@ __device__ __forceinline__ double qcp_solve(const QcpInput& in, float* rot, bool
 //     is dead after the coefficients and the hot path's register footprint does not pay for the rare one;
 //   * float32 square root of the float64 msd.
 // ---------------------------------------------------------------------------------------------
+// single-MUFU reciprocal and square root (1-2 ulp) for the throughput solvers: the IEEE-rounded __frcp_rn / sqrtf
+// expand to a MUFU plus a ~15-instruction fix-up with a slow-path branch each, three times per pair.  The host build
+// (tests/host_qcp) has no such instruction and takes the exact operations.
+__device__ __forceinline__ float rcp_approx(float x)
+{
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+
 // the slow path of the two solvers below: RMSD of one pair through the closed form
 __device__ __forceinline__ float qcp_rmsd_closed(const float* M, float Ga, float Gb, float inv_n)
 {
@@ -259,7 +283,7 @@ __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const floa
         const double C0 = ss * ss - 4.0 * nc, C2 = -2.0 * ss, C1 = -8.0 * detM;
         e0[p] = 0.5 * ((double)Ga[p] + (double)Gb[p]);
         // upper bound of the largest root, float32 is enough (nudged up so rounding cannot undershoot)
-        float ub = fminf(sqrtf(3.0f * (float)ss) * 1.000001f, 0.5f * (Ga[p] + Gb[p]) * 1.000001f);
+        float ub = fminf(sqrt_approx(3.0f * (float)ss) * 1.000001f, 0.5f * (Ga[p] + Gb[p]) * 1.000001f);
         ub = fmaxf(ub, 1e-30f);
         // exact power-of-two scale s = 2^-e with ub*s in [1,2)
         const int e = ((__float_as_int(ub) >> 23) & 0xff) - 127;
@@ -297,18 +321,18 @@ __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const floa
             const double a = b + c1[p];
             const double den = 2.0 * x2 * x + b + a;
             const double num = a * x + c0[p];
-            double r = (double)__frcp_rn((float)den);
+            double r = (double)rcp_approx((float)den);
             r = r * (2.0 - den * r);
             const double d = num * r;
-            const bool fine = den > 1e-300 && d == d;
-            x -= fine ? d : 0.0;
-            if (it == 1) ok = fine && fabs(d) <= 1e-8 * x && 6.0 * x * x > -c2[p];  // largest-root certificate
+            x -= d;
+            // largest-root certificate, on the last step only: a vanishing or negative P'(x), a NaN or a step that
+            // is not a negligible correction all fail it, and the pair is redone through the closed form
+            if (it == 1) ok = den > 0.0 && fabs(d) <= 1e-8 * x && 6.0 * x * x > -c2[p];
         }
         trusted[p] = ok || !active[p];
         const double lam = x * scale_back[p];
         double msd = 2.0 * (e0[p] - lam) * (double)inv_n;
-        msd = msd > 0.0 ? msd : 0.0;
-        rmsd[p] = sqrtf((float)msd);
+        rmsd[p] = sqrt_approx(fmaxf((float)msd, 0.0f));
     }
 }
 
@@ -326,7 +350,7 @@ __device__ __forceinline__ void qcp_msd_f32(const float (&M)[NP][9], const float
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < 9; ++i) ss = fmaf(M[p][i], M[p][i], ss);
-        float ub = fminf(sqrtf(3.0f * ss) * 1.000001f, e0[p] * 1.000001f);
+        float ub = fminf(sqrt_approx(3.0f * ss) * 1.000001f, e0[p] * 1.000001f);
         ub = fmaxf(ub, 1e-30f);
         const int e = ((__float_as_int(ub) >> 23) & 0xff) - 127;
         const float s1 = __int_as_float((127 - e) << 23);
@@ -367,7 +391,7 @@ __device__ __forceinline__ void qcp_msd_f32(const float (&M)[NP][9], const float
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         const float msd = 2.0f * (e0[p] - t[p] * sc[p]) * inv_n;
-        rmsd[p] = sqrtf(fmaxf(msd, 0.f));
+        rmsd[p] = sqrt_approx(fmaxf(msd, 0.f));
         ok[p] = ok[p] || !active[p];
     }
 }

@@ -1,8 +1,8 @@
-"""All-pairs tensor-core kernels: A/B timing of the operand layouts and epilogue geometries (development aid).
+"""All-pairs tensor-core kernel: timing of the epilogue geometries and accuracy against float64 truth (development aid).
 
     python tools/ap_variants.py [F] [N]
 
-For every (B200RMSD_TC_LAYOUT, B200RMSD_TC_EPILOGUE) variant: the full symmetric matrix and an unsymmetric row block
+For every B200RMSD_TC_EPILOGUE variant: the full symmetric matrix and an unsymmetric row block
 on iid and MD-like frames, checked against the exact-fp32 SIMT kernel on a corner of the matrix.  One JSON line each.
 """
 import json
@@ -41,19 +41,31 @@ def main():
     for name, dt in data.items():
         prep = AP.prepare(dt)
         corner[name] = AP.rows(prep, 0, 256).clone()
+    # float64 truth for a few rows (host numpy), to tell which of the two kernels a difference belongs to
+    sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+    from oracle import oracle as O
+    truth = {}
+    for name, dt in data.items():
+        X = dt.xyz_dev[:, :N].cpu().numpy()
+        truth[name] = {i: O.truth_rmsd_batch(X, X[i]) for i in (0, 100, 255)}
+        for i, tr in truth[name].items():
+            e = (corner[name][i].cpu().numpy() - tr); e[i] = 0
+            print(json.dumps({"kernel": "simt", "data": name, "row": i, "max_err_vs_truth": float(abs(e).max())}), flush=True)
     os.environ["B200RMSD_ALLPAIRS"] = "tc"
-    variants = [("dense", "16x2"), ("grouped", "16x2"), ("dense", "16x1"), ("dense", "8x2")]
-    for layout, epi in variants:
-        os.environ["B200RMSD_TC_LAYOUT"] = layout
+    for epi in ("16x2", "16x1"):
         os.environ["B200RMSD_TC_EPILOGUE"] = epi
-        res = {"layout": layout, "epilogue": epi, "F": F, "N": N}
+        res = {"epilogue": epi, "F": F, "N": N}
         try:
             for name, dt in data.items():
+                res[name + "_prepare_ms"] = round(timed(lambda: AP.prepare(dt), 3), 3)
                 prep = AP.prepare(dt)
                 ms = timed(lambda: AP.rows(prep, 0, F, out=out))
                 res[name + "_sym_ms"] = round(ms, 3)
                 res[name + "_sym_pairs_per_s"] = F * F / ms * 1e3
                 res[name + "_max_err_vs_simt"] = (out[:256] - corner[name]).abs().max().item()
+                for i, tr in truth[name].items():
+                    e = (out[i].cpu().numpy() - tr); e[i] = 0
+                    res[f"{name}_row{i}_max_err_vs_truth"] = float(abs(e).max())
                 res[name + "_asym"] = (out[:2048, :2048] - out[:2048, :2048].t()).abs().max().item()
                 rb = F // 8
                 ms = timed(lambda: AP.rows(prep, rb, 2 * rb, out=out[:rb]))
