@@ -221,8 +221,8 @@ __device__ __forceinline__ double qcp_solve(const QcpInput& in, float* rot, bool
 //     s1+s2+s3', s1-s2-s3', ...: (s1^2+s2^2+s3^2)^2 - 4 (s1^2 s2^2 + s2^2 s3^2 + s3^2 s1^2)); 43 float64
 //     operations instead of 64 for the ten K entries and the Laplace minors, and det M falls out of row 0 of cof M;
 //   * scaling by an exact power of two instead of a division;
-//   * float32 Newton steps from the upper bound (warp-uniform exit), then two float64 steps whose
-//     divisions are a float32 reciprocal refined by one Newton step (3 DFMA instead of a DDIV chain);
+//   * float32 Newton steps from the upper bound (warp-uniform exit), then two steps with the polynomial and its
+//     derivative in float64 and the quotient in float32 (one MUFU reciprocal);
 //   * the same largest-root certificate as qcp_newton, returned in trusted[]: pairs that fail it (collinear atoms,
 //     two-atom selections) must be redone by the caller with qcp_rmsd_closed -- kept out of this function so that M
 //     is dead after the coefficients and the hot path's register footprint does not pay for the rare one;
@@ -295,18 +295,21 @@ __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const floa
         t[p] = ub * __int_as_float((127 - e) << 23);
     }
 #pragma unroll 1
-    for (int it = 0; it < 16; ++it) {
+    for (int it = 0; it < 8; ++it) {  // two steps per trip: half the votes and branches on the dependency chain
         bool conv = true;
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            const float t2 = t[p] * t[p];
-            const float b = (t2 + f2[p]) * t[p];
-            const float a = b + f1[p];
-            const float den = fmaf(2.0f * t2, t[p], b + a);
-            const float num = fmaf(a, t[p], f0[p]);
-            const float d = (fabsf(den) > 1e-30f) ? __fdividef(num, den) : 0.0f;
-            t[p] -= d;
-            conv = conv && (!active[p] || fabsf(d) <= 4e-6f * t[p]);  // idle lanes must not hold the warp back
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float t2 = t[p] * t[p];
+                const float b = (t2 + f2[p]) * t[p];
+                const float a = b + f1[p];
+                const float den = fmaf(2.0f * t2, t[p], b + a);
+                const float num = fmaf(a, t[p], f0[p]);
+                const float d = (fabsf(den) > 1e-30f) ? __fdividef(num, den) : 0.0f;
+                t[p] -= d;
+                if (half == 1) conv = conv && (!active[p] || fabsf(d) <= 4e-6f * t[p]);  // idle lanes must not hold the warp back
+            }
         }
         if (__all_sync(0xffffffffu, conv)) break;  // warp-uniform exit: no divergence inside the loop
     }
@@ -321,9 +324,9 @@ __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const floa
             const double a = b + c1[p];
             const double den = 2.0 * x2 * x + b + a;
             const double num = a * x + c0[p];
-            double r = (double)rcp_approx((float)den);
-            r = r * (2.0 - den * r);
-            const double d = num * r;
+            // the step in float32: its ~1e-7 relative error perturbs the quadratically converging iterate by
+            // 1e-7 |d| <= 1e-12 x, and the division stays off the float64 dependency chain
+            const double d = (double)((float)num * rcp_approx((float)den));
             x -= d;
             // largest-root certificate, on the last step only: a vanishing or negative P'(x), a NaN or a step that
             // is not a negligible correction all fail it, and the pair is redone through the closed form
