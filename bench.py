@@ -243,7 +243,11 @@ def main():
     F, N, desc = WORKLOADS[args.workload]
     if args.frames:
         F = args.frames
-    config = {"workload": desc, "frames_per_gpu": F, "n_atoms": N, "frame": 0,
+        if args.workload == "allpairs":
+            desc = ("all-pairs RMSD matrix: %dk x %dk frames x %d atoms (BASELINE configs[3]%s)"
+                    % (F // 1000, F // 1000, N, "" if F == 100_000 else " shape, F overridden"))
+    config = {"workload": desc, ("frames_total" if args.workload == "allpairs" else "frames_per_gpu"): F, "n_atoms": N,
+              "frame": 0,
               "l2_policy": ("the %.1f GB matrix written by every step flushes the 126 MB L2 between steps; the operands "
                             "(%.2f GB) are meant to stay L2-resident inside a step" % (F * F * 4 / 1e9 / max(world, 1),
                                                                                        F * N * 12 / 1e9))
