@@ -15,7 +15,7 @@ import torch  # noqa: E402
 
 import mdtraj_b200 as mdb  # noqa: E402
 from mdtraj_b200 import _capi, allpairs as AP  # noqa: E402
-from oracle import oracle as O  # noqa: E402
+import _truth as O  # noqa: E402
 from ap_time import md_like  # noqa: E402
 
 

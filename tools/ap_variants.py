@@ -42,8 +42,7 @@ def main():
         prep = AP.prepare(dt)
         corner[name] = AP.rows(prep, 0, 256).clone()
     # float64 truth for a few rows (host numpy), to tell which of the two kernels a difference belongs to
-    sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
-    from oracle import oracle as O
+    import _truth as O
     truth = {}
     for name, dt in data.items():
         X = dt.xyz_dev[:, :N].cpu().numpy()
