@@ -1,4 +1,4 @@
-"""float64 Kabsch RMSD (numpy SVD) for the development tools.  The tools do not import oracle/: that tree is reserved for
+"""float64 Kabsch RMSD (numpy SVD) for the development tools.  The tools stay clear of the oracle tree, which is reserved for
 tests/, __graft_entry__.smoke() and bench.py's CPU legs."""
 import numpy as np
 
