@@ -207,11 +207,21 @@ def parity_block(workload, mdb):
         return verdict(t.xyz, ref, truth, f"superposed coordinates of {F} MD-like frames x {N} atoms, every 5th atom aligned",
                        F * N * 3)
     F = int(min(F_full, max(64, min(10_000, 2.4e8 // (N * 12)))))
-    X = O.synth_iid(F, N, seed=14)
-    got = mdb.rmsd(mdb.Trajectory(X.copy()), mdb.Trajectory(X.copy()), 0)
-    ref = O.rmsd(X, X, 0, impl=kind)
-    truth = O.truth_rmsd_batch(X, X[0])
-    return verdict(got[1:], ref[1:], truth[1:], f"md.rmsd(t,t,0) on {F} iid frames x {N} atoms (frame 0 itself left out)", F - 1)
+    out = None
+    # iid frames (strict parity is meaningful at every N) and MD-like frames (realistic cancellation; the reference
+    # itself drifts from the float64 truth there, SURVEY.md Appendix C, hence the three-way verdict)
+    for name, X in (("iid", O.synth_iid(F, N, seed=14)), ("MD-like", O.synth_md(F, N, seed=14))):
+        got = mdb.rmsd(mdb.Trajectory(X.copy()), mdb.Trajectory(X.copy()), 0)
+        ref = O.rmsd(X, X, 0, impl=kind)
+        truth = O.truth_rmsd_batch(X, X[0])
+        v = verdict(got[1:], ref[1:], truth[1:], f"md.rmsd(t,t,0) on {F} {name} frames x {N} atoms (frame 0 itself left out)",
+                    F - 1)
+        if out is None:
+            out = v
+        else:
+            out["md_like"] = v
+            out["pass"] = bool(out["pass"] and v["pass"])
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -156,7 +156,10 @@ int b200rmsd_rot_msd_dev(const float* a_frame, const float* b_xyz, int64_t n_fra
 size_t b200rmsd_allpairs_workspace_bytes(int64_t n_frames, int n_sel);
 
 /* Centre every frame (selection idx, int32, may be NULL = all atoms; then pass n_sel = n_atoms)
- * as inplace_center_and_trace_atom_major does (center.h:7) and lay it out for the contraction. */
+ * as inplace_center_and_trace_atom_major does (center.h:7) and lay it out for the contraction.
+ * With n_frames >= 512 (tensor-core path) the frames are also rotated onto frame 0 first -- the RMSD of a
+ * pair does not depend on how either frame is placed -- which keeps the tensor-core accumulators small
+ * ("tensor-core accumulation"); xyz itself is only read. */
 int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride,
                                   const int32_t* idx, int n_sel, void* workspace, size_t workspace_bytes, void* stream);
 
