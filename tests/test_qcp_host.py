@@ -164,3 +164,28 @@ def test_rotation_superposes(L):
     moved = np.einsum("pnk,pkl->pnl", A, R)  # row vector x R (rotation_generic.h:40-42)
     rmsd = np.sqrt(((moved - B) ** 2).sum((1, 2)) / N)
     assert np.abs(rmsd - got).max() < 1e-5
+
+
+@pytest.mark.parametrize("scale", [1e-4, 1e-2, 1e2, 1e4])
+def test_scale_invariance(L, scale):
+    """Coordinates in other units (pm ... um): the solvers scale the polynomial by an exact power of two, so the
+    relative accuracy must not depend on the unit."""
+    M, Ga, Gb = make_pairs("md", 2000, 100, seed=21)
+    base = truth_rmsd(M, Ga, Gb, 100)
+    Ms, Gas, Gbs = M * scale ** 2, Ga * scale ** 2, Gb * scale ** 2
+    got, _, _ = run_solve(L, Ms, Gas, Gbs, 100)
+    assert np.abs(got / scale - base).max() <= 1e-9
+    fast, want = run_fast(L, Ms, Gas, Gbs, 100)
+    assert np.isfinite(fast).all()
+    assert np.abs(fast / scale - want / scale).max() <= 1e-6
+
+
+def test_zero_and_tiny_inputs(L):
+    """All-zero frames (a one-atom selection after centring) and frames of vanishing size give 0, not NaN."""
+    n = 8
+    M = np.zeros((n, 3, 3)); G = np.zeros(n)
+    got, rot, deg = run_solve(L, M, G, G, 1, want_rot=True)
+    assert np.array_equal(got, np.zeros(n)) and deg.all()
+    assert np.array_equal(rot.reshape(n, 3, 3), np.broadcast_to(np.eye(3, dtype=np.float32), (n, 3, 3)))
+    fast, _ = run_fast(L, M, G, G, 1)
+    assert np.isfinite(fast).all() and fast.max() <= 1e-15
