@@ -1,0 +1,127 @@
+"""A numpy model of the all-pairs tensor-core arithmetic (test infrastructure, CPU only).
+
+What it models, and what it was calibrated against:
+  * 3xTF32 operands: hi = rna_tf32(x), lo = rna_tf32(x - hi)  (csrc/tc_ptx.cuh: rna_tf32, cvt.rna.tf32.f32);
+  * tcgen05.mma.kind::tf32, K = 8 per instruction, three per K-step (lo.hi, hi.lo, hi.hi), fp32 accumulator in TMEM with
+    ONE truncation (round toward zero) per instruction.  That single assumption reproduces the bias measured on a B200:
+    300-term inner products of magnitude ~324 came out 5.3e-4 short (profiles/r01_tc_accumulation_probe.json); the model
+    gives 5.8e-4 on the same kind of data;
+  * the operand construction of allpairs_tc144_prepare_kernel: frames aligned onto a common reference c, A = x', B = x' - c
+    for frames near c, the 3x3 matrix X'c^T added through six augmentation columns in a K-step of their own.
+It is a design tool: it says what an operand layout does to the RMSD before a GPU is involved.  It is NOT the oracle and
+nothing in the product depends on it."""
+import numpy as np
+
+f32 = np.float32
+
+
+def rz32(x):
+    """float64 -> float32 rounding toward zero."""
+    x = np.asarray(x, np.float64)
+    y = x.astype(f32)
+    over = np.abs(y.astype(np.float64)) > np.abs(x)
+    y[over] = np.nextafter(y[over], f32(0))
+    return y
+
+
+def rna_tf32(x):
+    """cvt.rna.tf32.f32: nearest, ties away from zero, 10 explicit mantissa bits."""
+    u = np.asarray(x, f32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x1000) & 0xFFFFE000).astype(np.uint32).view(f32)
+
+
+def split(x):
+    hi = rna_tf32(x)
+    lo = rna_tf32((np.asarray(x, f32) - hi).astype(f32))
+    return hi, lo
+
+
+def tc_gemm(a_hi, a_lo, b_hi, b_lo):
+    """(m,K) x (n,K) -> (m,n) float64 view of the fp32 accumulator after the K loop."""
+    Ah, Al, Bh, Bl = (np.asarray(v, np.float64) for v in (a_hi, a_lo, b_hi, b_lo))
+    acc = np.zeros((Ah.shape[0], Bh.shape[0]), f32)
+    for k in range(0, Ah.shape[1], 8):
+        s = slice(k, k + 8)
+        for X, Y in ((Al, Bh), (Ah, Bl), (Ah, Bh)):
+            acc = rz32(acc.astype(np.float64) + X[:, s] @ Y[:, s].T)
+    return acc.astype(np.float64)
+
+
+def kabsch_rotation(mobile, target):
+    """R (float64) with mobile @ R ~ target, both centred."""
+    U, _, Vt = np.linalg.svd(mobile.T @ target)
+    d = np.sign(np.linalg.det(U @ Vt))
+    return U @ np.diag([1.0, 1.0, d]) @ Vt
+
+
+def prepare_operands(X, aligned=True):
+    """The prepare step on frames X (F,N,3) float32 -> dict of (3F, K) operand matrices and traces.
+    aligned=False: the plain layout (A = B = centred frames, no augmentation)."""
+    X = np.asarray(X, f32)
+    F, N, _ = X.shape
+    k0 = (N + 7) // 8 * 8
+    K = (k0 + 6 + 31) // 32 * 32
+    mu = X.astype(np.float64).mean(1, keepdims=True).astype(f32)
+    T = (X - mu).astype(f32)                                   # center_generic.h: float64 mean, float32 subtraction
+    c = T[0].copy()
+    g_ref = float((c.astype(np.float64) ** 2).sum())
+    A = np.zeros((F, 3, K), f32)
+    B = np.zeros((F, 3, K), f32)
+    A_lo_aug = np.zeros((F, 3, K), f32)
+    tr = np.empty(F)
+    for f in range(F):
+        if aligned:
+            R = kabsch_rotation(T[f].astype(np.float64), c.astype(np.float64)).astype(f32)
+            v = (T[f] @ R).astype(f32)
+            rmsd2 = float(((v.astype(np.float64) - c) ** 2).sum()) / N
+            near = rmsd2 < 0.25 * g_ref / N
+        else:
+            v, near = T[f], False
+        tr[f] = float(f32((v.astype(np.float64) ** 2).sum()))
+        A[f, :, :N] = v.T
+        B[f, :, :N] = ((v - c) if near else v).T
+        if aligned:
+            G = v.astype(np.float64).T @ c.astype(np.float64)  # G[c][m] = sum_k x'_k[c] c_k[m]
+            g1 = rna_tf32(G.astype(f32))
+            g2 = rna_tf32((G - g1).astype(f32))
+            g3 = rna_tf32((G - g1 - g2.astype(np.float64)).astype(f32))
+            A[f, :, k0:k0 + 3] = g1
+            A[f, :, k0 + 3:k0 + 6] = g2
+            A_lo_aug[f, :, k0:k0 + 3] = g3
+            if near:
+                B[f, :, k0:k0 + 3] = np.eye(3, dtype=f32)
+                B[f, :, k0 + 3:k0 + 6] = np.eye(3, dtype=f32)
+    a_hi, a_lo = split(A.reshape(3 * F, K))
+    b_hi, b_lo = split(B.reshape(3 * F, K))
+    a_hi = a_hi.reshape(F, 3, K); a_lo = a_lo.reshape(F, 3, K)
+    if aligned:  # augmentation columns are stored as pieces, not split again
+        a_hi[:, :, k0:k0 + 6] = A[:, :, k0:k0 + 6]
+        a_lo[:, :, k0:k0 + 6] = A_lo_aug[:, :, k0:k0 + 6]
+    return {"a_hi": a_hi.reshape(3 * F, K), "a_lo": a_lo.reshape(3 * F, K), "b_hi": b_hi, "b_lo": b_lo, "traces": tr,
+            "n_atoms": N}
+
+
+def lambda_max(M):
+    Sxx, Sxy, Sxz, Syx, Syy, Syz, Szx, Szy, Szz = [M[..., i, j] for i in range(3) for j in range(3)]
+    K = np.zeros(M.shape[:-2] + (4, 4))
+    K[..., 0, 0] = Sxx + Syy + Szz; K[..., 0, 1] = Szy - Syz; K[..., 0, 2] = Sxz - Szx; K[..., 0, 3] = Syx - Sxy
+    K[..., 1, 1] = Sxx - Syy - Szz; K[..., 1, 2] = Syx + Sxy; K[..., 1, 3] = Sxz + Szx
+    K[..., 2, 2] = -Sxx + Syy - Szz; K[..., 2, 3] = Szy + Syz; K[..., 3, 3] = -Sxx - Syy + Szz
+    K = K + np.swapaxes(np.triu(K, 1), -1, -2)
+    return np.linalg.eigvalsh(K)[..., -1]
+
+
+def rmsd_rows(ops, rows, exact=False):
+    """RMSD of frames `rows` against all frames from the modelled accumulator (exact=True: float64 product of the same
+    operands, i.e. what an ideal accumulator would give)."""
+    F = ops["b_hi"].shape[0] // 3
+    sel = np.concatenate([np.arange(3 * i, 3 * i + 3) for i in rows])
+    if exact:
+        a = ops["a_hi"][sel].astype(np.float64) + ops["a_lo"][sel]
+        b = ops["b_hi"].astype(np.float64) + ops["b_lo"]
+        acc = a @ b.T
+    else:
+        acc = tc_gemm(ops["a_hi"][sel], ops["a_lo"][sel], ops["b_hi"], ops["b_lo"])
+    M = acc.reshape(len(rows), 3, F, 3).transpose(0, 2, 1, 3)
+    tr = ops["traces"]
+    return np.sqrt(np.maximum(tr[rows][:, None] + tr[None, :] - 2 * lambda_max(M), 0) / ops["n_atoms"])

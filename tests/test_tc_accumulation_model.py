@@ -1,0 +1,69 @@
+"""CPU: the numpy model of the tensor-core all-pairs arithmetic (tests/tc_model.py) -- why the operands are stored as
+differences from a common reference.  The model's one hardware assumption (fp32 accumulator truncated once per K=8
+tcgen05.mma) is pinned to the bias measured on a B200 (profiles/r01_tc_accumulation_probe.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import tc_model as T
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def truth_rows(X, rows):
+    from oracle import oracle as O
+    return np.stack([O.truth_rmsd_batch(X, X[i]) for i in rows])
+
+
+@pytest.fixture(scope="module")
+def md_frames():
+    from oracle import oracle as O
+    return O.synth_md(160, 300, seed=3, rg=1.0, sigma=0.1)
+
+
+def test_model_reproduces_measured_accumulator_bias(md_frames):
+    probe = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "r01_tc_accumulation_probe.json")) if l.strip()]
+    measured = next(p for p in probe if p["data"] == "md")
+    ops = T.prepare_operands(md_frames, aligned=False)
+    a = slice(0, 30)
+    acc = T.tc_gemm(ops["a_hi"][a], ops["a_lo"][a], ops["b_hi"], ops["b_lo"])
+    exact = (ops["a_hi"][a].astype(np.float64) + ops["a_lo"][a]) @ (ops["b_hi"].astype(np.float64) + ops["b_lo"]).T
+    err = acc - exact
+    big = np.abs(exact) > 0.5 * np.abs(exact).max()
+    bias = float((err[big] * np.sign(exact[big])).mean())
+    # measured on hardware: -5.3e-4 on values of magnitude ~324 (17 ulp); the model must land within 25 % of it
+    assert measured["same_on_large_values"] < -3e-4
+    assert bias < 0 and abs(bias - measured["same_on_large_values"]) < 0.25 * abs(measured["same_on_large_values"]), bias
+    assert (err[big] * np.sign(exact[big])).max() <= 0.0   # truncation never overshoots
+
+
+def test_difference_operands_remove_the_bias_from_the_rmsd(md_frames):
+    rows = np.array([0, 57, 159])
+    truth = truth_rows(md_frames, rows)
+    m = np.ones_like(truth, bool); m[np.arange(len(rows)), rows] = False
+    plain = T.prepare_operands(md_frames, aligned=False)
+    diff = T.prepare_operands(md_frames, aligned=True)
+    e_plain = np.abs(T.rmsd_rows(plain, rows) - truth)[m].max()
+    e_diff = np.abs(T.rmsd_rows(diff, rows) - truth)[m].max()
+    e_diff_exact = np.abs(T.rmsd_rows(diff, rows, exact=True) - truth)[m].max()
+    # plain operands: the truncation bias costs more than the parity tolerance (GPU, before the change: 3.8e-5 nm)
+    assert e_plain > 1e-5
+    # difference operands: an order of magnitude inside it (GPU: 1.1-1.4e-6 nm); operand construction alone: 1e-7 class
+    assert e_diff < 3e-6 and e_diff < e_plain / 8
+    assert e_diff_exact < 5e-7
+
+
+def test_dissimilar_frames_keep_plain_operands():
+    """iid frames are farther from the reference than half their own size: B stays x', no unit vectors, same numbers as
+    the plain layout (the per-frame switch of allpairs_tc144_prepare_kernel)."""
+    from oracle import oracle as O
+    X = O.synth_iid(60, 100, seed=9)
+    ops = T.prepare_operands(X, aligned=True)
+    k0 = (100 + 7) // 8 * 8
+    assert ops["b_hi"][3:, k0:].sum() == 0           # only frame 0 (the reference itself) is "near"
+    rows = np.array([1, 30])
+    truth = truth_rows(X, rows)
+    m = np.ones_like(truth, bool); m[np.arange(2), rows] = False
+    assert np.abs(T.rmsd_rows(ops, rows) - truth)[m].max() < 2e-6
