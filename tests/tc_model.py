@@ -54,51 +54,89 @@ def kabsch_rotation(mobile, target):
     return U @ np.diag([1.0, 1.0, d]) @ Vt
 
 
-def prepare_operands(X, aligned=True):
+def _align_all(T, c):
+    """Every centred frame of T (F,N,3) float32 rotated onto c: (aligned frames float32, msd to c)."""
+    out = np.empty_like(T)
+    msd = np.empty(len(T))
+    for f in range(len(T)):
+        R = kabsch_rotation(T[f].astype(np.float64), c.astype(np.float64)).astype(f32)
+        out[f] = (T[f] @ R).astype(f32)
+        msd[f] = float(((out[f].astype(np.float64) - c) ** 2).sum()) / T.shape[1]
+    return out, msd
+
+
+def choose_references(T, max_refs):
+    """Greedy farthest-point references: frame 0, then the frame farthest (in RMSD) from all chosen ones, as long as
+    it is not "near" any of them (msd < Rg_c^2 / 4, the per-frame switch of the prepare kernel).  One one-vs-many
+    pass per reference.  Returns (reference frame indices, per-frame nearest reference, aligned frames, msd to it)."""
+    F = len(T)
+    refs = [0]
+    aligned, best = _align_all(T, T[0])
+    owner = np.zeros(F, int)
+    while len(refs) < max_refs:
+        cand = int(np.argmax(best))
+        g_c = float((T[refs[owner[cand]]].astype(np.float64) ** 2).sum()) / T.shape[1]
+        if best[cand] < 0.25 * g_c:
+            break
+        refs.append(cand)
+        al, msd = _align_all(T, T[cand])
+        closer = msd < best
+        aligned[closer] = al[closer]
+        best[closer] = msd[closer]
+        owner[closer] = len(refs) - 1
+    return refs, owner, aligned, best
+
+
+def prepare_operands(X, aligned=True, max_refs=1):
     """The prepare step on frames X (F,N,3) float32 -> dict of (3F, K) operand matrices and traces.
-    aligned=False: the plain layout (A = B = centred frames, no augmentation)."""
+    aligned=False: the plain layout (A = B = centred frames, no augmentation).
+    max_refs=1: what allpairs_tc144_prepare_kernel does today (one reference, frame 0); max_refs>1: the multi-reference
+    plan of DESIGN.md section 8 (six augmentation columns per reference)."""
     X = np.asarray(X, f32)
     F, N, _ = X.shape
-    k0 = (N + 7) // 8 * 8
-    K = (k0 + 6 + 31) // 32 * 32
     mu = X.astype(np.float64).mean(1, keepdims=True).astype(f32)
     T = (X - mu).astype(f32)                                   # center_generic.h: float64 mean, float32 subtraction
-    c = T[0].copy()
-    g_ref = float((c.astype(np.float64) ** 2).sum())
+    if aligned:
+        refs, owner, V, msd = choose_references(T, max_refs)
+    else:
+        refs, owner, V, msd = [], np.zeros(F, int), T, np.full(F, np.inf)
+    R = max(len(refs), 1)
+    k0 = (N + 7) // 8 * 8
+    K = (k0 + 6 * R + 31) // 32 * 32
     A = np.zeros((F, 3, K), f32)
     B = np.zeros((F, 3, K), f32)
     A_lo_aug = np.zeros((F, 3, K), f32)
     tr = np.empty(F)
     for f in range(F):
+        v = V[f]
+        near = False
         if aligned:
-            R = kabsch_rotation(T[f].astype(np.float64), c.astype(np.float64)).astype(f32)
-            v = (T[f] @ R).astype(f32)
-            rmsd2 = float(((v.astype(np.float64) - c) ** 2).sum()) / N
-            near = rmsd2 < 0.25 * g_ref / N
-        else:
-            v, near = T[f], False
+            c = T[refs[owner[f]]]
+            near = msd[f] < 0.25 * float((c.astype(np.float64) ** 2).sum()) / N
         tr[f] = float(f32((v.astype(np.float64) ** 2).sum()))
         A[f, :, :N] = v.T
         B[f, :, :N] = ((v - c) if near else v).T
-        if aligned:
-            G = v.astype(np.float64).T @ c.astype(np.float64)  # G[c][m] = sum_k x'_k[c] c_k[m]
+        for r, rf in enumerate(refs):
+            G = v.astype(np.float64).T @ T[rf].astype(np.float64)  # G[c][m] = sum_k x'_k[c] c_k[m]
             g1 = rna_tf32(G.astype(f32))
             g2 = rna_tf32((G - g1).astype(f32))
             g3 = rna_tf32((G - g1 - g2.astype(np.float64)).astype(f32))
-            A[f, :, k0:k0 + 3] = g1
-            A[f, :, k0 + 3:k0 + 6] = g2
-            A_lo_aug[f, :, k0:k0 + 3] = g3
-            if near:
-                B[f, :, k0:k0 + 3] = np.eye(3, dtype=f32)
-                B[f, :, k0 + 3:k0 + 6] = np.eye(3, dtype=f32)
+            o = k0 + 6 * r
+            A[f, :, o:o + 3] = g1
+            A[f, :, o + 3:o + 6] = g2
+            A_lo_aug[f, :, o:o + 3] = g3
+        if near:
+            o = k0 + 6 * owner[f]
+            B[f, :, o:o + 3] = np.eye(3, dtype=f32)
+            B[f, :, o + 3:o + 6] = np.eye(3, dtype=f32)
     a_hi, a_lo = split(A.reshape(3 * F, K))
     b_hi, b_lo = split(B.reshape(3 * F, K))
     a_hi = a_hi.reshape(F, 3, K); a_lo = a_lo.reshape(F, 3, K)
     if aligned:  # augmentation columns are stored as pieces, not split again
-        a_hi[:, :, k0:k0 + 6] = A[:, :, k0:k0 + 6]
-        a_lo[:, :, k0:k0 + 6] = A_lo_aug[:, :, k0:k0 + 6]
+        a_hi[:, :, k0:k0 + 6 * R] = A[:, :, k0:k0 + 6 * R]
+        a_lo[:, :, k0:k0 + 6 * R] = A_lo_aug[:, :, k0:k0 + 6 * R]
     return {"a_hi": a_hi.reshape(3 * F, K), "a_lo": a_lo.reshape(3 * F, K), "b_hi": b_hi, "b_lo": b_lo, "traces": tr,
-            "n_atoms": N}
+            "n_atoms": N, "references": refs, "owner": owner}
 
 
 def lambda_max(M):

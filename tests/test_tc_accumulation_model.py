@@ -67,3 +67,30 @@ def test_dissimilar_frames_keep_plain_operands():
     truth = truth_rows(X, rows)
     m = np.ones_like(truth, bool); m[np.arange(2), rows] = False
     assert np.abs(T.rmsd_rows(ops, rows) - truth)[m].max() < 2e-6
+
+
+def test_multi_reference_plan_on_three_basins():
+    """DESIGN.md section 8, item 2, run through the model: with one reference (today's kernel) pairs inside a basin far
+    from frame 0 keep the plain-operand error; greedy farthest-point references bring every basin to the 1e-6 class."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    N, per = 300, 40
+    b1 = rng.standard_normal((N, 3))
+    bases = [b1, b1 + 0.8 * rng.standard_normal((N, 3)), b1 + 0.8 * rng.standard_normal((N, 3))]
+    X = np.concatenate([b + 0.1 * rng.standard_normal((per, N, 3)) for b in bases])
+    X = np.einsum("fni,fij->fnj", X, O.random_rotations(len(X), rng)).astype(np.float32)
+    rows = np.array([1, per + 1, 2 * per + 1])
+    truth = truth_rows(X, rows)
+    m = np.ones_like(truth, bool); m[np.arange(3), rows] = False
+    one = T.prepare_operands(X, aligned=True, max_refs=1)
+    many = T.prepare_operands(X, aligned=True, max_refs=4)
+    assert one["references"] == [0]
+    assert len(many["references"]) == 3                       # one per basin, then the greedy rule stops
+    assert {int(many["owner"][i * per:(i + 1) * per].max()) for i in range(3)} == {0, 1, 2}
+    e_one = np.abs(T.rmsd_rows(one, rows) - truth)
+    e_many = np.abs(T.rmsd_rows(many, rows) - truth)
+    inside2 = e_one[1, per:2 * per][np.arange(per) != 1].max()
+    assert inside2 > 1e-5                                     # today: inside the second basin
+    assert e_one[0, :per][np.arange(per) != 1].max() < 3e-6   # today: inside the reference's basin
+    assert e_many[m].max() < 3e-6                             # plan: everywhere
+    assert many["a_hi"].shape[1] == 352                       # 304 + 18 augmentation columns -> one more K block at N=300
