@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define B200RMSD_ABI_VERSION 1
+#define B200RMSD_ABI_VERSION 2
 
 #define B200RMSD_OK 0
 #define B200RMSD_EINVAL (-1)    /* bad argument (NULL, misaligned, non-positive size)   */
@@ -157,11 +157,27 @@ size_t b200rmsd_allpairs_workspace_bytes(int64_t n_frames, int n_sel);
 
 /* Centre every frame (selection idx, int32, may be NULL = all atoms; then pass n_sel = n_atoms)
  * as inplace_center_and_trace_atom_major does (center.h:7) and lay it out for the contraction.
- * With n_frames >= 512 (tensor-core path) the frames are also rotated onto frame 0 first -- the RMSD of a
- * pair does not depend on how either frame is placed -- which keeps the tensor-core accumulators small
- * ("tensor-core accumulation"); xyz itself is only read. */
+ * With n_frames >= 512 (tensor-core path) a few reference structures are chosen among the frames (greedy
+ * farthest-point traversal, one one-vs-many pass each) and every frame is rotated onto the nearest one and stored
+ * as its difference from it -- the RMSD of a pair does not depend on how either frame is placed -- which keeps the
+ * tensor-core accumulators small on multi-basin trajectories too ("tensor-core accumulation").
+ * xyz itself is only read.  Unlike the other _dev entry points this one SYNCHRONISES `stream` (once per reference
+ * chosen: the traversal is data dependent). */
 int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride,
                                   const int32_t* idx, int n_sel, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Process-wide settings of the all-pairs path; a value <= 0 leaves the setting as it is.
+ *   min_tc_frames: trajectories with at least this many frames take the tensor-core kernel, shorter ones the exact
+ *                  fp32 SIMT kernel (default 512).  Must not change between prepare and the rows/block calls that
+ *                  use its workspace.
+ *   max_refs:      upper bound on the reference structures prepare may choose (default and maximum 32). */
+int b200rmsd_allpairs_configure(int min_tc_frames, int max_refs);
+
+/* What prepare found (synchronises `stream`): number of reference structures, number of frames stored as they are
+ * because no reference is near them, covering radius (largest RMSD of a frame to its nearest reference, nm) and the
+ * frame indices of the references (up to ref_frames_cap).  Any pointer may be NULL. */
+int b200rmsd_allpairs_info_dev(const void* workspace, size_t workspace_bytes, int* n_refs, int* n_far,
+                               float* cover_radius, int* ref_frames, int ref_frames_cap, void* stream);
 
 /* Rows [row0, row1) of the matrix:  out[(i-row0)*ld + j], j in [0, n_frames), float32.
  * n_sel must equal the value used in prepare. */

@@ -39,6 +39,8 @@ SIGNATURES = {
     "b200rmsd_center_host": (_i32, [_vp, _i64, _i32, _vp, _i32]),
     "b200rmsd_release_workspaces": (None, []),
     "b200rmsd_allpairs_workspace_bytes": (_sz, [_i64, _i32]),
+    "b200rmsd_allpairs_configure": (_i32, [_i32, _i32]),
+    "b200rmsd_allpairs_info_dev": (_i32, [_vp, _sz, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_f32), _vp, _i32, _vp]),
     "b200rmsd_allpairs_prepare_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _sz, _vp]),
     "b200rmsd_allpairs_block_dev": (_i32, [_vp, _sz, _i64, _i32, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _u32, _vp]),
     "b200rmsd_allpairs_rows_dev": (_i32, [_vp, _sz, _i64, _i32, _i64, _i64, _vp, _i64, _u32, _vp]),
@@ -72,7 +74,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError here == ABI drift, fail loudly
             fn.restype = res
             fn.argtypes = args
-        if L.b200rmsd_abi_version() != 1:
+        if L.b200rmsd_abi_version() != 2:
             raise ImportError("libb200rmsd.so ABI version mismatch")
         _lib = L
     return _lib

@@ -18,8 +18,17 @@ FAST_SOLVE = 2
 _MAX_ROWS_PER_CALL = 65535 * 32
 
 
+def configure(min_tc_frames=None, max_refs=None):
+    """Process-wide settings (``b200rmsd_allpairs_configure``): ``min_tc_frames`` -- trajectories with at least this many
+    frames take the tcgen05 kernel, shorter ones the exact-fp32 SIMT kernel (default 512); ``max_refs`` -- upper bound on
+    the reference structures ``prepare`` may choose (default and maximum 32).  Do not change ``min_tc_frames`` between
+    ``prepare`` and the ``rows``/``block`` calls that use its workspace."""
+    _capi.check(_capi.lib().b200rmsd_allpairs_configure(int(min_tc_frames or 0), int(max_refs or 0)),
+                "b200rmsd_allpairs_configure")
+
+
 class PreparedAllPairs:
-    """Opaque device workspace (centred operands + traces) for one trajectory/selection."""
+    """Opaque device workspace (aligned operands + traces) for one trajectory/selection."""
 
     def __init__(self, workspace, n_frames, n_sel):
         self.workspace = workspace
@@ -29,6 +38,22 @@ class PreparedAllPairs:
     @property
     def device(self):
         return self.workspace.device
+
+    def info(self):
+        """What the prepare step chose: ``n_refs`` reference structures (their frame indices in ``ref_frames``), ``n_far``
+        frames stored as they are because no reference is near them, ``cover_radius`` (largest RMSD of a frame to its
+        nearest reference, nm).  All zero on the SIMT path (fewer than ``min_tc_frames`` frames)."""
+        import ctypes as C
+        torch = _torch()
+        n_refs, n_far, rad = C.c_int(0), C.c_int(0), C.c_float(0)
+        frames = (C.c_int * 32)()
+        with torch.cuda.device(self.device):
+            rc = _capi.lib().b200rmsd_allpairs_info_dev(self.workspace.data_ptr(), self.workspace.numel(), C.byref(n_refs),
+                                                        C.byref(n_far), C.byref(rad), frames, 32,
+                                                        _stream_ptr(torch, self.device))
+        _capi.check(rc, "b200rmsd_allpairs_info_dev")
+        return {"n_refs": n_refs.value, "n_far": n_far.value, "cover_radius": float(rad.value),
+                "ref_frames": [int(frames[i]) for i in range(n_refs.value)]}
 
 
 def prepare(traj: DeviceTrajectory, atom_indices=None) -> PreparedAllPairs:

@@ -17,7 +17,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200rmsd.so")
-SOURCES = ["capi.cu", "one_vs_many.cu", "aux_kernels.cu", "frame_resident.cu", "allpairs.cu", "allpairs_tc144.cu", "cluster_ops.cu"]
+SOURCES = ["capi.cu", "one_vs_many.cu", "aux_kernels.cu", "frame_resident.cu", "allpairs.cu", "allpairs_refs.cu", "allpairs_tc144.cu", "cluster_ops.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "qcp.cuh", "allpairs_layout.cuh", "tc_ptx.cuh", "../../include/b200rmsd.h"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -23,6 +23,9 @@
 
 namespace b200 {
 
+int g_ap_min_tc_frames = 512;
+int g_ap_max_refs = kApMaxRefs;
+
 // one warp per frame
 __global__ void __launch_bounds__(256) allpairs_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames,
                                                                int64_t frame_stride, const int* __restrict__ idx,
@@ -167,6 +170,28 @@ static int ap_sm_count()
 
 extern "C" {
 
+int b200rmsd_allpairs_configure(int min_tc_frames, int max_refs)
+{
+    if (min_tc_frames > 0) g_ap_min_tc_frames = min_tc_frames;
+    if (max_refs > 0) g_ap_max_refs = max_refs < kApMaxRefs ? max_refs : kApMaxRefs;
+    return 0;
+}
+
+int b200rmsd_allpairs_info_dev(const void* workspace, size_t workspace_bytes, int* n_refs, int* n_far, float* cover_radius,
+                               int* ref_frames, int ref_frames_cap, void* stream)
+{
+    if (!workspace || workspace_bytes < 256) return fail(B200RMSD_EINVAL, "allpairs_info: bad arguments");
+    ApHeader h;
+    cudaError_t e = cudaMemcpyAsync(&h, workspace, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(B200RMSD_ECUDA, "allpairs_info: %s", cudaGetErrorString(e));
+    if (n_refs) *n_refs = h.n_refs;
+    if (n_far) *n_far = h.n_far;
+    if (cover_radius) *cover_radius = h.cover_radius;
+    for (int i = 0; ref_frames && i < ref_frames_cap && i < h.n_refs; ++i) ref_frames[i] = h.ref_frame[i];
+    return 0;
+}
+
 size_t b200rmsd_allpairs_workspace_bytes(int64_t n_frames, int n_sel)
 {
     if (n_frames <= 0 || n_sel <= 0) return 256;
@@ -187,31 +212,23 @@ int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atom
     const int sm = ap_sm_count();
     cudaError_t e;
     if (g.tc) {
-        // Align every frame onto frame 0 first (one one-vs-many pass with rotations): the RMSD of a pair does not change
-        // under a rigid motion of either frame, and for frames of one ensemble the aligned frames differ from the
-        // common reference by fluctuations only -- which is what keeps the tensor-core accumulators small
-        // (allpairs_tc144_prepare_kernel).
-        float* ref = (float*)(base + g.ref_off);
-        void* stats = base + g.stats_off;
-        float* rot = (float*)(base + g.rot_off);
-        double* cen = (double*)(base + g.cen_off);
-        if (int rc = b200rmsd_prepare_reference_dev(xyz, idx, ns, 1, 0.f, ref, stats, stream)) return rc;
-        if (int rc = b200rmsd_rmsd_dev(xyz, n_frames, n_atoms, frame_stride, idx, ns, ref, stats, nullptr, 0,
-                                       (float*)(base + g.rmsd_off), rot, cen, nullptr, base + g.scratch_off,
-                                       g.scratch_bytes, stream))
+        // Choose the reference structures and align every frame onto its nearest one: the RMSD of a pair does not change
+        // under a rigid motion of either frame, and a frame differs from a reference of its own basin by fluctuations
+        // only -- which is what keeps the tensor-core accumulators small (allpairs_refs.cu, allpairs_tc144_prepare_kernel).
+        int n_refs = 0;
+        if (int rc = ap_select_references(xyz, n_frames, n_atoms, frame_stride, idx, ns, g, base, g_ap_max_refs, sm, st, &n_refs))
             return rc;
-        e = launch_allpairs_tc144_prepare(xyz, n_frames, frame_stride, idx, ns, g.k_pad, ref, stats,
-                                          (const float*)(base + g.rmsd_off), rot, cen,
-                                          (float*)(base + g.a_hi_off), (float*)(base + g.a_lo_off),
-                                          (float*)(base + g.b_hi_off), (float*)(base + g.b_lo_off),
-                                          (float*)(base + g.traces_off), g.rows_pad, sm, st);
+        e = launch_allpairs_tc144_prepare(xyz, n_frames, frame_stride, idx, ns, g, base, n_refs, sm, st);
     } else {
         int64_t ctas = (int64_t)sm * 8;
         const int64_t need = (n_frames + 7) / 8;
         if (ctas > need) ctas = need;
-        allpairs_prepare_kernel<<<(unsigned)ctas, 256, 0, st>>>(xyz, n_frames, frame_stride, idx, ns, g.k_pad,
-                                                                (float*)(base + g.x_off), (float*)(base + g.traces_off));
-        e = cudaGetLastError();
+        e = cudaMemsetAsync(base, 0, 256, st);  // ApHeader: no references on this path
+        if (e == cudaSuccess) {
+            allpairs_prepare_kernel<<<(unsigned)ctas, 256, 0, st>>>(xyz, n_frames, frame_stride, idx, ns, g.k_pad,
+                                                                    (float*)(base + g.x_off), (float*)(base + g.traces_off));
+            e = cudaGetLastError();
+        }
     }
     return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "allpairs_prepare: %s", cudaGetErrorString(e));
 }
@@ -228,10 +245,8 @@ int b200rmsd_allpairs_block_dev(const void* workspace, size_t workspace_bytes, i
     if (row0 == row1 || col0 == col1) return 0;
     const char* base = (const char*)workspace;
     if (g.tc)
-        return launch_allpairs_tc144_block((const float*)(base + g.a_hi_off), (const float*)(base + g.a_lo_off),
-                                           (const float*)(base + g.b_hi_off), (const float*)(base + g.b_lo_off),
-                                           (const float*)(base + g.traces_off), n_sel, g.k_pad, g.rows_pad, row0, row1,
-                                           col0, col1, out, ld, out_t, ld_t, flags, ap_sm_count(), (cudaStream_t)stream);
+        return launch_allpairs_tc144_block(g, base, n_sel, n_frames, row0, row1, col0, col1, out, ld, out_t, ld_t, flags,
+                                           ap_sm_count(), (cudaStream_t)stream);
     dim3 grid((unsigned)((col1 - col0 + kTile - 1) / kTile), (unsigned)((row1 - row0 + kTile - 1) / kTile));
     if (grid.y > 65535) return fail(B200RMSD_EINVAL, "allpairs_block: at most 65535*32 rows per call");
     allpairs_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)(base + g.x_off),

@@ -6,9 +6,10 @@
 // theobald_rmsd.cpp:217-334; replaces the Python loop of F md.rmsd calls, examples/clustering.ipynb:78-81).
 //
 //   operands   K-major fp32 matrices in tf32 "hi" and "lo" parts (hi = rna_tf32(x), lo = rna_tf32(x-hi)), row 3f+c =
-//              component c of frame f, no padding rows.  A = the frames aligned onto a common reference c (frame 0),
-//              B = their differences from c; six extra K columns add X'_i c^T to every block inside the GEMM, so that
-//              the accumulator holds X'_i D_j^T (fluctuation-sized) until the last K-step -- the tensor core's fp32
+//              component c of frame f, no padding rows.  A = every frame aligned onto its nearest reference structure
+//              (allpairs_refs.cu), B = its difference from that reference; eight extra K columns per reference, in
+//              matrices of their own, add X'_i c_r^T to the blocks whose column frame refers to c_r, so that the
+//              accumulator holds X'_i D_j^T (fluctuation-sized) until the last K-steps -- the tensor core's fp32
 //              accumulation truncates, and the bias is proportional to the running sum (allpairs_tc144_prepare_kernel);
 //   tile       40 i-frames x 48 j-frames.  The A operand (M = 128 TMEM lanes) is brought by FOUR 32-row TMA boxes
 //              starting at rows 120*ti + 30*w, so that each epilogue warp's lane quarter holds 10 whole frames (lanes 30
@@ -72,7 +73,8 @@ struct Tc144Params {
     int tiles_i, tiles_j;    // tile grid
     int n_bj;                // super-blocks per block row
     int n_sel;
-    int nk;                  // K blocks of 32
+    int nk;                  // K blocks of 32 (atoms)
+    const int2* tile_aug;    // per absolute j-tile: first and last augmentation K block (first > last: none)
     int symmetric;           // square block on the diagonal: tiles that hold no pair j >= i are skipped, values mirrored
     unsigned flags;
 };
@@ -99,37 +101,38 @@ __device__ __forceinline__ float sel3(int c, float a0, float a1, float a2) { ret
 // ---------------------------------------------------------------------------------------------
 // prepare: operands and traces.  One warp per frame.
 //
-// The tensor core accumulates in fp32 with truncation: measured on B200 (tools/tc_acc_probe.py) the sum of 300 products
-// comes out ~17 ulp short of its float64 value, always towards zero.  For frames of one ensemble the inner products are
-// large (~N Rg^2 / 3) while the quantity of interest, G_a + G_b - 2 lambda, is N rmsd^2: a 5e-4 bias on M costs 4e-5 nm
-// on a 0.24 nm RMSD (N = 300, Rg = 1 nm), outside the 1e-5 / 1e-4 parity tolerance.  The RMSD of a pair is unchanged by
-// a rigid motion of either frame, so every frame is first aligned onto one common reference c (frame 0, centred):
-// x' = (x - centroid) . R with R, centroid from the one-vs-many kernel.  With d_j = x'_j - c,
+// The tensor core accumulates in fp32 with truncation: measured on B200 (profiles/r01_tc_accumulation_probe.json) the
+// sum of 300 products comes out ~17 ulp short of its float64 value, always towards zero.  For frames of one ensemble the
+// inner products are large (~N Rg^2 / 3) while the quantity of interest, G_a + G_b - 2 lambda, is N rmsd^2: a 5e-4 bias
+// on M costs 4e-5 nm on a 0.24 nm RMSD (N = 300, Rg = 1 nm), outside the 1e-5 / 1e-4 parity tolerance.  The RMSD of a
+// pair is unchanged by a rigid motion of either frame, so every frame is first aligned onto the reference structure it
+// is closest to (its owner c_o, allpairs_refs.cu): x' = (x - centroid) . R.  With d_j = x'_j - c_o(j),
 //
-//     M_ij = sum_k x'_ik x'_jk^T = sum_k x'_ik d_jk^T  +  G_i,     G_i = sum_k x'_ik c_k^T   (3x3, float64 here),
+//     M_ij = sum_k x'_ik x'_jk^T = sum_k x'_ik d_jk^T  +  G_i^(o(j)),     G_i^(r) = sum_k x'_ik c_rk^T   (3x3, float64 here),
 //
 // and the GEMM only has to accumulate X'_i D_j^T, whose entries are fluctuation-sized (~sqrt(N) Rg sigma instead of
-// N Rg^2 / 3: 50 times smaller at sigma = 0.1 nm).  G_i enters the same accumulator through six augmentation columns of
-// K placed in a K-step of their own after the atoms -- A row (i,c) carries the tf32 pieces g1, g2 of G_i[c][0..2], B row
-// (j,q) carries the unit vector e_q twice -- i.e. as the LAST non-zero K-step: one truncation at full magnitude instead
-// of one per accumulation step (a third piece g3 rides in the lo matrix).  The choice is made per column frame: a frame
-// farther from c than half its own size (N rmsd_j^2 >= G_c / 4; iid test data, other basins) keeps b_j = x'_j and a zero
-// in place of e_q, because there X'_i D_j^T and G_i would be two large numbers cancelling -- worse than the plain product.
+// N Rg^2 / 3: 50 times smaller at sigma = 0.1 nm).  G_i^(r) enters the same accumulator through eight augmentation
+// columns per reference, held in matrices of their own: A row (i,c) carries the tf32 pieces g1, g2 of G_i^(r)[c][0..2]
+// (a third piece g3 rides in the lo matrix), B row (j,q) carries the unit vector e_q twice in the columns of ITS owner
+// and zeros elsewhere.  A tile walks the augmentation K blocks of its column frames' owners after the atoms, i.e. G is
+// added in the LAST K-steps: one truncation at full magnitude instead of one per accumulation step.
+// Frames farther from every reference than half its radius of gyration ("far": iid test data, outliers; owner stored as
+// -1-o) keep b_j = x'_j and no unit vectors, because there X'_i D_j^T and G_i would be two large numbers cancelling --
+// worse than the plain product.
 // Centring follows center_generic.h:3-44 (float64 mean, float32 subtraction, float64 trace of the float32 squares);
 // the float32 rotation deforms a frame by ~1e-7 relative, 1e-7 nm of RMSD.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 allpairs_tc144_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames, int64_t frame_stride,
-                              const int* __restrict__ idx, int n_sel, int k_pad, const float* __restrict__ ref,
-                              const RefStats* __restrict__ ref_stats, const float* __restrict__ rmsd_to_ref,
+                              const int* __restrict__ idx, int n_sel, int k_pad, const float* __restrict__ refs,
+                              int64_t ref_stride, int n_refs, const int* __restrict__ owner,
                               const float* __restrict__ rot, const double* __restrict__ centroid,
                               float* __restrict__ a_hi, float* __restrict__ a_lo, float* __restrict__ b_hi,
-                              float* __restrict__ b_lo, float* __restrict__ traces)
+                              float* __restrict__ b_lo, float* __restrict__ aug_a_hi, float* __restrict__ aug_a_lo,
+                              float* __restrict__ aug_b, float* __restrict__ traces)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_warps = (int64_t)gridDim.x * 8;
-    const int k0 = ap_tc144_k0(n_sel);
-    const float near2 = 0.25f * (float)ref_stats->G / (float)n_sel;  // rmsd^2 to c below which b_j = c + d_j
     for (int64_t f = (int64_t)blockIdx.x * 8 + warp; f < n_frames; f += n_warps) {
         const float* fr = xyz + f * frame_stride;
         float R[9];
@@ -138,49 +141,65 @@ allpairs_tc144_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames, i
         const float mx = (float)__ldg(centroid + f * 3), my = (float)__ldg(centroid + f * 3 + 1),
                     mz = (float)__ldg(centroid + f * 3 + 2);
         const int64_t row = ap_tc144_row(f, 0);
-        const float r_ref = __ldg(rmsd_to_ref + f);
-        const bool near = r_ref * r_ref < near2;  // warp-uniform
-        double tr = 0, G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const int raw = __ldg(owner + f);
+        const bool near = raw >= 0;  // warp-uniform
+        const int own = near ? raw : -1 - raw;
+        const float* cown = refs + own * ref_stride;
+        double tr = 0;
         for (int k = lane; k < n_sel; k += 32) {
             const int a = idx ? __ldg(idx + k) : k;
             const float tx = __ldg(fr + 3 * a) - mx, ty = __ldg(fr + 3 * a + 1) - my, tz = __ldg(fr + 3 * a + 2) - mz;
-            float v[3], cr[3];
 #pragma unroll
-            for (int m = 0; m < 3; ++m) {  // row vector x R (rotation_generic.h:40-42)
-                v[m] = fmaf(tz, R[6 + m], fmaf(ty, R[3 + m], tx * R[m]));
-                cr[m] = __ldg(ref + 3 * k + m);
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                tr += (double)(v[c] * v[c]);
-#pragma unroll
-                for (int m = 0; m < 3; ++m) G[3 * c + m] += (double)v[c] * (double)cr[m];
-                const float h = rna_tf32(v[c]);
+            for (int c = 0; c < 3; ++c) {  // row vector x R (rotation_generic.h:40-42)
+                const float v = fmaf(tz, R[6 + c], fmaf(ty, R[3 + c], tx * R[c]));
+                tr += (double)(v * v);
+                const float h = rna_tf32(v);
                 a_hi[(row + c) * k_pad + k] = h;
-                a_lo[(row + c) * k_pad + k] = rna_tf32(v[c] - h);
-                const float d = near ? v[c] - cr[c] : v[c];
+                a_lo[(row + c) * k_pad + k] = rna_tf32(v - h);
+                const float d = near ? v - __ldg(cown + 3 * k + c) : v;
                 const float dh = rna_tf32(d);
                 b_hi[(row + c) * k_pad + k] = dh;
                 b_lo[(row + c) * k_pad + k] = rna_tf32(d - dh);
             }
         }
         tr = warp_sum(tr);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) G[i] = warp_sum(G[i]);
         if (lane == 0) traces[f] = (float)tr;
-        // augmentation columns k0 + 3p + m, p = 0,1: A_hi row c <- piece p of G[c][m] (the third piece in A_lo under
-        // piece 0); B_hi row q <- (q == m) for the frames that are stored as differences
-        if (lane < 18) {
-            const int piece = lane / 9, c = (lane % 9) / 3, m = lane % 3;
-            double g = 0;
+        if (near && lane < 6) {  // B row q: e_q in columns 8*own + q and 8*own + 3 + q
+            const int q = lane % 3;
+            aug_b[(row + q) * kApAugCols + 8 * own + lane] = 1.0f;
+        }
+        __syncwarp();  // the A rows written above are read back below by other lanes of this warp
+        // G^(r) = A_i c_r^T with A_i = hi + lo, exactly the operand the tensor core multiplies
+        for (int r = 0; r < n_refs; ++r) {
+            const float* cr = refs + r * ref_stride;
+            double G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int k = lane; k < n_sel; k += 32) {
+                const double c0 = (double)__ldg(cr + 3 * k), c1 = (double)__ldg(cr + 3 * k + 1),
+                             c2 = (double)__ldg(cr + 3 * k + 2);
 #pragma unroll
-            for (int i = 0; i < 9; ++i) g = (i == 3 * c + m) ? G[i] : g;  // static indexing keeps G in registers
-            const float g1 = rna_tf32((float)g);
-            const float g2 = rna_tf32((float)(g - (double)g1));
-            const float g3 = rna_tf32((float)(g - (double)g1 - (double)g2));
-            a_hi[(row + c) * k_pad + k0 + 3 * piece + m] = piece == 0 ? g1 : g2;
-            if (piece == 0) a_lo[(row + c) * k_pad + k0 + m] = g3;
-            if (c == m && near) b_hi[(row + c) * k_pad + k0 + 3 * piece + m] = 1.0f;
+                for (int c = 0; c < 3; ++c) {
+                    const double v = (double)a_hi[(row + c) * k_pad + k] + (double)a_lo[(row + c) * k_pad + k];
+                    G[3 * c] += v * c0; G[3 * c + 1] += v * c1; G[3 * c + 2] += v * c2;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) G[i] = warp_sum(G[i]);
+            // columns 8r + 3p + m, p = 0,1: A_hi row c <- piece p of G[c][m]; the third piece in A_lo under piece 0
+            if (lane < 18) {
+                const int piece = lane / 9, c = (lane % 9) / 3, m = lane % 3;
+                double g = 0;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) g = (i == 3 * c + m) ? G[i] : g;  // static indexing keeps G in registers
+                // half an fp32 ulp of G towards its sign: G is the last (and by far the largest) term to enter the
+                // accumulator, whose truncation then rounds the finished entry to nearest instead of towards zero --
+                // unbiased, half the worst case (tests/tc_model.py ROUND_BIAS: 8e-6 -> 3e-6 nm at rmsd 0.04 nm)
+                if (g != 0.0) g += copysign(scalbn(1.0, ilogb(g) - 24), g);
+                const float g1 = rna_tf32((float)g);
+                const float g2 = rna_tf32((float)(g - (double)g1));
+                const float g3 = rna_tf32((float)(g - (double)g1 - (double)g2));
+                aug_a_hi[(row + c) * kApAugCols + 8 * r + 3 * piece + m] = piece == 0 ? g1 : g2;
+                if (piece == 0) aug_a_lo[(row + c) * kApAugCols + 8 * r + m] = g3;
+            }
         }
     }
 }
@@ -191,7 +210,8 @@ template <int EPI_WARPS, int NP>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                      const Tc144Params p)
+                      const __grid_constant__ CUtensorMap map_g_a_hi, const __grid_constant__ CUtensorMap map_g_a_lo,
+                      const __grid_constant__ CUtensorMap map_g_b, const Tc144Params p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is not guaranteed to have it
@@ -240,6 +260,20 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                     tma_load_2d(st + 2 * kABytes + kBBytes, &map_b_lo, &full[stage], kb * kK, b_row);
                     if (++stage == kRing) { stage = 0; phase ^= 1u; }
                 }
+                // augmentation K blocks of the references this tile's column frames are stored against (no B_lo part)
+                const int2 aug = __ldg(p.tile_aug + tj);
+                for (int g = aug.x; g <= aug.y; ++g) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    unsigned char* st = smem + stage * kStage;
+                    mbar_arrive_expect_tx(&full[stage], kStage - kBBytes);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        tma_load_2d(st + w * kQuarterBytes, &map_g_a_hi, &full[stage], g * kK, a_row + 30 * w);
+                        tma_load_2d(st + kABytes + w * kQuarterBytes, &map_g_a_lo, &full[stage], g * kK, a_row + 30 * w);
+                    }
+                    tma_load_2d(st + 2 * kABytes, &map_g_b, &full[stage], g * kK, b_row);
+                    if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                }
             }
         }
     } else if (warp == EPI_WARPS + 1) {
@@ -251,26 +285,46 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int64_t t = blockIdx.x; t < p.n_slots; t += gridDim.x) {
-                int ti_unused, tj_unused;
-                if (!tile_of_slot(t, p, ti_unused, tj_unused)) continue;
+                int ti_unused, tj;
+                if (!tile_of_slot(t, p, ti_unused, tj)) continue;
                 mbar_wait(&tempty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
                 for (int kb = 0; kb < p.nk; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
+                    bool continue_mma = true;
                     unsigned char* st = smem + stage * kStage;
                     const uint64_t a_hi = make_sw128_kmajor_desc(st), a_lo = make_sw128_kmajor_desc(st + kABytes);
                     const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * kABytes),
                                    b_lo = make_sw128_kmajor_desc(st + 2 * kABytes + kBBytes);
 #pragma unroll
-                    for (int ks = 0; ks < ((p.flags & 0x200u) ? 0 : kK / 8); ++ks) {  // 0x200: development, skip MMAs
+#ifdef B200RMSD_DEV_SWITCHES
+                    if (p.flags & 0x200u) continue_mma = false;  // development: skip the MMAs (operand delivery alone)
+#endif
+                    for (int ks = 0; ks < (continue_mma ? kK / 8 : 0); ++ks) {
                         const uint64_t off = (uint64_t)(ks * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
                         umma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, (kb | ks) != 0 ? 1u : 0u);
                         umma_tf32(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
                         umma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
                     }
                     umma_commit(&empty[stage]);  // frees this smem stage when the MMAs above have read it
+                    if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                }
+                const int2 aug = __ldg(p.tile_aug + tj);
+                for (int g = aug.x; g <= aug.y; ++g) {  // + X'_i c_r^T for the four references of block g: (g1 + g2 + g3) . e
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    unsigned char* st = smem + stage * kStage;
+                    const uint64_t a_hi = make_sw128_kmajor_desc(st), a_lo = make_sw128_kmajor_desc(st + kABytes);
+                    const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * kABytes);
+#pragma unroll
+                    for (int ks = 0; ks < kK / 8; ++ks) {
+                        const uint64_t off = (uint64_t)(ks * 2);
+                        umma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, 1u);
+                        umma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
+                    }
+                    umma_commit(&empty[stage]);
                     if (++stage == kRing) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(&tfull[acc]);        // accumulator complete
@@ -341,10 +395,13 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                         Gb[u] = Gi;
                         trusted[u] = true;
                     }
+#ifdef B200RMSD_DEV_SWITCHES
                     if (p.flags & 0x100u) {  // development: skip the solve to time the GEMM main loop alone
 #pragma unroll
                         for (int u = 0; u < NP; ++u) res[u] = M[u][0];
-                    } else if (p.flags & B200RMSD_FAST_SOLVE) {  // all-float32 solve (reference-class precision)
+                    } else
+#endif
+                    if (p.flags & B200RMSD_FAST_SOLVE) {  // all-float32 solve (reference-class precision)
                         qcp_msd_f32<NP>(M, Ga, Gb, ok, inv_n, res, trusted);
                     } else {
                         qcp_msd_fast<NP>(M, Ga, Gb, ok, inv_n, res, trusted);
@@ -407,7 +464,10 @@ static Tc144Params tc144_tiling(int64_t row0, int64_t row1, int64_t col0, int64_
     p.tiles_j0 = (int)(col0 / kJFrames);
     p.tiles_j = (int)((col1 + kJFrames - 1) / kJFrames) - p.tiles_j0;
     // a square block on the diagonal: compute each unordered pair once and mirror it (exactly symmetric, half the flops)
-    p.symmetric = (row0 == col0 && row1 == col1 && !has_out_t && !getenv("B200RMSD_NO_SYMMETRIC")) ? 1 : 0;
+    p.symmetric = (row0 == col0 && row1 == col1 && !has_out_t) ? 1 : 0;
+#ifdef B200RMSD_DEV_SWITCHES
+    if (getenv("B200RMSD_NO_SYMMETRIC")) p.symmetric = 0;
+#endif
     p.n_bj = (p.tiles_j + kSupJ - 1) / kSupJ;
     p.n_slots = (int64_t)((p.tiles_i + kSupI - 1) / kSupI) * p.n_bj * (kSupI * kSupJ);
     return p;
@@ -431,64 +491,77 @@ extern "C" long long b200rmsd_debug_allpairs_tiles(long long row0, long long row
 }
 
 cudaError_t launch_allpairs_tc144_prepare(const float* xyz, int64_t n_frames, int64_t frame_stride, const int* idx,
-                                          int n_sel, int k_pad, const float* ref, const void* ref_stats,
-                                          const float* rmsd_to_ref, const float* rot, const double* centroid, float* a_hi,
-                                          float* a_lo, float* b_hi, float* b_lo, float* traces, int64_t rows_pad,
-                                          int sm_count, cudaStream_t st)
+                                          int n_sel, const ApGeometry& g, char* base, int n_refs, int sm_count,
+                                          cudaStream_t st)
 {
-    // K padding, the lo parts of the augmentation columns and the rows past 3F (read by the last tiles' boxes) are zero
-    float* ops[4] = {a_hi, a_lo, b_hi, b_lo};
-    for (float* o : ops) {
-        cudaError_t e = cudaMemsetAsync(o, 0, (size_t)rows_pad * k_pad * 4, st);
+    // K padding, unused augmentation columns and the rows past 3F (read by the last tiles' boxes) are zero
+    const size_t atom_bytes = (size_t)g.rows_pad * g.k_pad * 4, aug_bytes = (size_t)g.rows_pad * kApAugCols * 4;
+    const size_t offs[7] = {g.a_hi_off, g.a_lo_off, g.b_hi_off, g.b_lo_off, g.aug_a_hi_off, g.aug_a_lo_off, g.aug_b_off};
+    for (int i = 0; i < 7; ++i) {
+        cudaError_t e = cudaMemsetAsync(base + offs[i], 0, i < 4 ? atom_bytes : aug_bytes, st);
         if (e != cudaSuccess) return e;
     }
     int64_t ctas = (int64_t)sm_count * 8;
     const int64_t need = (n_frames + 7) / 8;
     if (ctas > need) ctas = need;
-    allpairs_tc144_prepare_kernel<<<(unsigned)ctas, 256, 0, st>>>(xyz, n_frames, frame_stride, idx, n_sel, k_pad, ref,
-                                                                  (const RefStats*)ref_stats, rmsd_to_ref, rot, centroid,
-                                                                  a_hi, a_lo, b_hi, b_lo, traces);
+    allpairs_tc144_prepare_kernel<<<(unsigned)ctas, 256, 0, st>>>(
+        xyz, n_frames, frame_stride, idx, n_sel, g.k_pad, (const float*)(base + g.ref_off), (int64_t)(g.ref_stride / 4),
+        n_refs, (const int*)(base + g.owner_off), (const float*)(base + g.rot_off), (const double*)(base + g.cen_off),
+        (float*)(base + g.a_hi_off), (float*)(base + g.a_lo_off), (float*)(base + g.b_hi_off), (float*)(base + g.b_lo_off),
+        (float*)(base + g.aug_a_hi_off), (float*)(base + g.aug_a_lo_off), (float*)(base + g.aug_b_off),
+        (float*)(base + g.traces_off));
     return cudaGetLastError();
 }
 
-int launch_allpairs_tc144_block(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
-                                const float* traces, int n_sel, int k_pad, int64_t rows_pad, int64_t row0, int64_t row1,
-                                int64_t col0, int64_t col1, float* out, int64_t ld, float* out_t, int64_t ld_t,
-                                unsigned flags, int sm_count, cudaStream_t st)
+int launch_allpairs_tc144_block(const ApGeometry& g, const char* base, int n_sel, int64_t n_frames, int64_t row0,
+                                int64_t row1, int64_t col0, int64_t col1, float* out, int64_t ld, float* out_t,
+                                int64_t ld_t, unsigned flags, int sm_count, cudaStream_t st)
 {
-    CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
-    if (!make_operand_map(&map_a_hi, a_hi, rows_pad, k_pad, 32) || !make_operand_map(&map_a_lo, a_lo, rows_pad, k_pad, 32) ||
-        !make_operand_map(&map_b_hi, b_hi, rows_pad, k_pad, kN) || !make_operand_map(&map_b_lo, b_lo, rows_pad, k_pad, kN))
+    (void)n_frames;
+    CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo, map_g_a_hi, map_g_a_lo, map_g_b;
+    auto op = [&](size_t off) { return (const float*)(base + off); };
+    if (!make_operand_map(&map_a_hi, op(g.a_hi_off), g.rows_pad, g.k_pad, 32) ||
+        !make_operand_map(&map_a_lo, op(g.a_lo_off), g.rows_pad, g.k_pad, 32) ||
+        !make_operand_map(&map_b_hi, op(g.b_hi_off), g.rows_pad, g.k_pad, kN) ||
+        !make_operand_map(&map_b_lo, op(g.b_lo_off), g.rows_pad, g.k_pad, kN) ||
+        !make_operand_map(&map_g_a_hi, op(g.aug_a_hi_off), g.rows_pad, kApAugCols, 32) ||
+        !make_operand_map(&map_g_a_lo, op(g.aug_a_lo_off), g.rows_pad, kApAugCols, 32) ||
+        !make_operand_map(&map_g_b, op(g.aug_b_off), g.rows_pad, kApAugCols, kN))
         return set_error(B200RMSD_ECUDA, "allpairs: cuTensorMapEncodeTiled failed");
     Tc144Params p = tc144_tiling(row0, row1, col0, col1, out_t != nullptr);
-    p.traces = traces;
+    p.traces = op(g.traces_off);
     p.out = out;
     p.ld = ld;
     p.out_t = out_t;
     p.ld_t = ld_t;
     p.n_sel = n_sel;
-    p.nk = k_pad / kK;
-    p.flags = flags;
-    if (const char* dbg = getenv("B200RMSD_TC_DEBUG")) p.flags |= (unsigned)strtoul(dbg, nullptr, 0) & 0xff02u;
+    p.nk = g.k_pad / kK;
+    p.tile_aug = (const int2*)(base + g.tile_aug_off);
+    p.flags = flags & (B200RMSD_DIAG_ZERO | B200RMSD_FAST_SOLVE);
+    int ew = 16, np = 2;
+#ifdef B200RMSD_DEV_SWITCHES
+    if (const char* dbg = getenv("B200RMSD_TC_DEBUG")) p.flags |= (unsigned)strtoul(dbg, nullptr, 0) & 0xff00u;
+    if (const char* cfg = getenv("B200RMSD_TC_EPILOGUE")) sscanf(cfg, "%dx%d", &ew, &np);  // "<warps>x<np>", e.g. 16x1
+#endif
     const size_t smem = (size_t)kRing * kStage + 1024 + 256;
     int64_t ctas = sm_count;
     const int64_t n_tiles = (int64_t)p.tiles_i * p.tiles_j;
     if (ctas > n_tiles) ctas = n_tiles;
     if (ctas < 1) ctas = 1;
-    const char* cfg = getenv("B200RMSD_TC_EPILOGUE");  // development: "<warps>x<np>", e.g. 16x1
-    int ew = 16, np = 2;
-    if (cfg) sscanf(cfg, "%dx%d", &ew, &np);
     cudaError_t e = cudaSuccess;
 #define B200_LAUNCH_TC144(EW, NP)                                                                                          \
     do {                                                                                                                   \
         e = cudaFuncSetAttribute(allpairs_tc144_kernel<EW, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
         if (e == cudaSuccess)                                                                                              \
-            allpairs_tc144_kernel<EW, NP><<<(unsigned)ctas, 64 + 32 * EW, smem, st>>>(map_a_hi, map_a_lo, map_b_hi,       \
-                                                                                       map_b_lo, p);                       \
+            allpairs_tc144_kernel<EW, NP><<<(unsigned)ctas, 64 + 32 * EW, smem, st>>>(                                    \
+                map_a_hi, map_a_lo, map_b_hi, map_b_lo, map_g_a_hi, map_g_a_lo, map_g_b, p);                              \
     } while (0)
+#ifdef B200RMSD_DEV_SWITCHES
     if (ew == 8 && np == 2) B200_LAUNCH_TC144(8, 2);
     else if (ew == 16 && np == 1) B200_LAUNCH_TC144(16, 1);
-    else B200_LAUNCH_TC144(16, 2);
+    else
+#endif
+        B200_LAUNCH_TC144(16, 2);
 #undef B200_LAUNCH_TC144
     if (e != cudaSuccess) return set_error(B200RMSD_ECUDA, "allpairs: %s", cudaGetErrorString(e));
     e = cudaGetLastError();

@@ -345,3 +345,29 @@ def synth_md(n_frames, n_atoms, seed=0, rg=1.5, sigma=0.1, box=5.0):
     R = random_rotations(n_frames, rng)
     X = np.einsum("fni,fij->fnj", X, R) + rng.uniform(-box, box, size=(n_frames, 1, 3))
     return X.astype(np.float32)
+
+
+def synth_md_basins(n_frames, n_atoms, n_basins=3, seed=0, rg=1.0, sigma=0.1, separation=1.4, interleave=False, box=5.0):
+    """Multi-basin MD-like frames: `n_basins` base structures `separation` nm of RMSD apart from the first one (and
+    ~separation*sqrt(2) from each other), per-frame noise sigma, random rigid motion.  Frames of a basin are contiguous
+    (a trajectory that hops) unless interleave=True (concatenated / shuffled runs).  Returns (X float32, basin index)."""
+    rng = np.random.default_rng(seed)
+    base0 = rng.standard_normal((n_atoms, 3)) * rg
+    bases = [base0] + [base0 + rng.standard_normal((n_atoms, 3)) * (separation / np.sqrt(3.0)) for _ in range(n_basins - 1)]
+    which = rng.integers(0, n_basins, n_frames) if interleave else (np.arange(n_frames) * n_basins) // n_frames
+    X = np.stack(bases)[which] + rng.standard_normal((n_frames, n_atoms, 3)) * sigma
+    R = random_rotations(n_frames, rng)
+    X = np.einsum("fni,fij->fnj", X, R) + rng.uniform(-box, box, size=(n_frames, 1, 3))
+    return X.astype(np.float32), which
+
+
+def synth_md_drift(n_frames, n_atoms, seed=0, rg=1.0, step=0.02, sigma=0.01, box=5.0):
+    """A trajectory that drifts: per-atom random walk of `step` nm per frame on top of the base structure (RMSD to frame 0
+    grows like step*sqrt(3 t)), neighbouring frames ~step*sqrt(3) apart, small per-frame noise, random rigid motion."""
+    rng = np.random.default_rng(seed)
+    base = rng.standard_normal((n_atoms, 3)) * rg
+    X = base[None] + np.cumsum(step * rng.standard_normal((n_frames, n_atoms, 3)), 0) + \
+        sigma * rng.standard_normal((n_frames, n_atoms, 3))
+    R = random_rotations(n_frames, rng)
+    X = np.einsum("fni,fij->fnj", X, R) + rng.uniform(-box, box, size=(n_frames, 1, 3))
+    return X.astype(np.float32)

@@ -6,8 +6,9 @@ What it models, and what it was calibrated against:
     ONE truncation (round toward zero) per instruction.  That single assumption reproduces the bias measured on a B200:
     300-term inner products of magnitude ~324 came out 5.3e-4 short (profiles/r01_tc_accumulation_probe.json); the model
     gives 5.8e-4 on the same kind of data;
-  * the operand construction of allpairs_tc144_prepare_kernel: frames aligned onto a common reference c, A = x', B = x' - c
-    for frames near c, the 3x3 matrix X'c^T added through six augmentation columns in a K-step of their own.
+  * the operand construction of allpairs_tc144_prepare_kernel and the reference traversal of allpairs_refs.cu: frames
+    aligned onto their nearest reference c_r, A = x', B = x' - c_r for frames near it, the 3x3 matrix X'c_r^T added
+    through eight augmentation columns per reference in K-steps of their own after the atoms.
 It is a design tool: it says what an operand layout does to the RMSD before a GPU is involved.  It is NOT the oracle and
 nothing in the product depends on it."""
 import numpy as np
@@ -65,78 +66,98 @@ def _align_all(T, c):
     return out, msd
 
 
+ROUND_BIAS = True
+COVER_STOP = 0.25   # nm, kCoverStop of csrc/allpairs_refs.cu
+
+
 def choose_references(T, max_refs):
-    """Greedy farthest-point references: frame 0, then the frame farthest (in RMSD) from all chosen ones, as long as
-    it is not "near" any of them (msd < Rg_c^2 / 4, the per-frame switch of the prepare kernel).  One one-vs-many
-    pass per reference.  Returns (reference frame indices, per-frame nearest reference, aligned frames, msd to it)."""
-    F = len(T)
-    refs = [0]
-    aligned, best = _align_all(T, T[0])
-    owner = np.zeros(F, int)
-    while len(refs) < max_refs:
-        cand = int(np.argmax(best))
-        g_c = float((T[refs[owner[cand]]].astype(np.float64) ** 2).sum()) / T.shape[1]
-        if best[cand] < 0.25 * g_c:
-            break
+    """The traversal of csrc/allpairs_refs.cu (ap_select_references): greedy farthest-point references, every frame owned
+    by its nearest one; stops at max_refs, or when far frames remain but three references in a row captured nothing
+    (iid-like data), or when everything is near and the covering radius is below COVER_STOP / has stopped shrinking.
+    Returns (reference frame indices, per-frame owner, near mask, aligned frames, msd to the owner)."""
+    F, N = len(T), T.shape[1]
+    refs, owner = [], np.zeros(F, int)
+    aligned, best = None, None
+    g = []
+    cand, unproductive, hist = 0, 0, []
+    productive_min = max(2, F // 1000)
+    while True:
+        r = len(refs)
         refs.append(cand)
+        g.append(float((T[cand].astype(np.float64) ** 2).sum()) / N)
         al, msd = _align_all(T, T[cand])
-        closer = msd < best
-        aligned[closer] = al[closer]
-        best[closer] = msd[closer]
-        owner[closer] = len(refs) - 1
-    return refs, owner, aligned, best
+        moved = np.ones(F, bool) if r == 0 else msd < best
+        if r == 0:
+            aligned, best = al, msd
+        else:
+            aligned[moved] = al[moved]
+            best[moved] = msd[moved]
+            owner[moved] = r
+        near = best < 0.25 * np.asarray(g)[owner]
+        radius = float(np.sqrt(best.max()))
+        R = r + 1
+        if R >= max_refs or radius <= 0:
+            break
+        if (~near).any():
+            if R >= 2:
+                unproductive = 0 if int((moved & near).sum()) >= productive_min else unproductive + 1
+            if unproductive >= 3:
+                break
+        else:   # everything is near a reference: refine until the covering radius is small or has stopped shrinking
+            hist.append(radius)
+            if radius <= COVER_STOP or (len(hist) >= 3 and radius > 0.9 * hist[-3]):
+                break
+        cand = int(np.argmax(best))
+    return refs, owner, near, aligned, best
 
 
-def prepare_operands(X, aligned=True, max_refs=1):
+def prepare_operands(X, aligned=True, max_refs=32):
     """The prepare step on frames X (F,N,3) float32 -> dict of (3F, K) operand matrices and traces.
     aligned=False: the plain layout (A = B = centred frames, no augmentation).
-    max_refs=1: what allpairs_tc144_prepare_kernel does today (one reference, frame 0); max_refs>1: the multi-reference
-    plan of DESIGN.md section 8 (six augmentation columns per reference)."""
+    aligned=True: allpairs_tc144_prepare_kernel -- A = frames aligned onto their nearest reference, B = their differences
+    from it (near frames), eight augmentation columns per reference after the atoms."""
     X = np.asarray(X, f32)
     F, N, _ = X.shape
     mu = X.astype(np.float64).mean(1, keepdims=True).astype(f32)
     T = (X - mu).astype(f32)                                   # center_generic.h: float64 mean, float32 subtraction
     if aligned:
-        refs, owner, V, msd = choose_references(T, max_refs)
+        refs, owner, near, V, msd = choose_references(T, max_refs)
     else:
-        refs, owner, V, msd = [], np.zeros(F, int), T, np.full(F, np.inf)
+        refs, owner, near, V = [], np.zeros(F, int), np.zeros(F, bool), T
     R = max(len(refs), 1)
-    k0 = (N + 7) // 8 * 8
-    K = (k0 + 6 * R + 31) // 32 * 32
+    k0 = (N + 31) // 32 * 32
+    K = k0 + (8 * R + 31) // 32 * 32
     A = np.zeros((F, 3, K), f32)
     B = np.zeros((F, 3, K), f32)
-    A_lo_aug = np.zeros((F, 3, K), f32)
     tr = np.empty(F)
     for f in range(F):
         v = V[f]
-        near = False
-        if aligned:
-            c = T[refs[owner[f]]]
-            near = msd[f] < 0.25 * float((c.astype(np.float64) ** 2).sum()) / N
         tr[f] = float(f32((v.astype(np.float64) ** 2).sum()))
         A[f, :, :N] = v.T
-        B[f, :, :N] = ((v - c) if near else v).T
-        for r, rf in enumerate(refs):
-            G = v.astype(np.float64).T @ T[rf].astype(np.float64)  # G[c][m] = sum_k x'_k[c] c_k[m]
-            g1 = rna_tf32(G.astype(f32))
-            g2 = rna_tf32((G - g1).astype(f32))
-            g3 = rna_tf32((G - g1 - g2.astype(np.float64)).astype(f32))
-            o = k0 + 6 * r
-            A[f, :, o:o + 3] = g1
-            A[f, :, o + 3:o + 6] = g2
-            A_lo_aug[f, :, o:o + 3] = g3
-        if near:
-            o = k0 + 6 * owner[f]
-            B[f, :, o:o + 3] = np.eye(3, dtype=f32)
-            B[f, :, o + 3:o + 6] = np.eye(3, dtype=f32)
+        B[f, :, :N] = ((v - T[refs[owner[f]]]) if near[f] else v).T
     a_hi, a_lo = split(A.reshape(3 * F, K))
     b_hi, b_lo = split(B.reshape(3 * F, K))
     a_hi = a_hi.reshape(F, 3, K); a_lo = a_lo.reshape(F, 3, K)
-    if aligned:  # augmentation columns are stored as pieces, not split again
-        a_hi[:, :, k0:k0 + 6 * R] = A[:, :, k0:k0 + 6 * R]
-        a_lo[:, :, k0:k0 + 6 * R] = A_lo_aug[:, :, k0:k0 + 6 * R]
-    return {"a_hi": a_hi.reshape(3 * F, K), "a_lo": a_lo.reshape(3 * F, K), "b_hi": b_hi, "b_lo": b_lo, "traces": tr,
-            "n_atoms": N, "references": refs, "owner": owner}
+    b_hi = b_hi.reshape(F, 3, K)
+    for f in range(F):
+        va = a_hi[f, :, :N].astype(np.float64) + a_lo[f, :, :N]       # the operand the tensor core multiplies
+        for r, rf in enumerate(refs):
+            G = va @ T[rf].astype(np.float64)                         # G[c][m] = sum_k x'_k[c] c_k[m]
+            if ROUND_BIAS:   # half an fp32 ulp of G towards its sign: the accumulator's truncation then rounds to nearest
+                G = G + np.sign(G) * np.exp2(np.floor(np.log2(np.maximum(np.abs(G), 1e-300))) - 24)
+            g1 = rna_tf32(G.astype(f32))
+            g2 = rna_tf32((G - g1).astype(f32))
+            g3 = rna_tf32((G - g1 - g2.astype(np.float64)).astype(f32))
+            o = k0 + 8 * r
+            a_hi[f, :, o:o + 3] = g1
+            a_hi[f, :, o + 3:o + 6] = g2
+            a_lo[f, :, o:o + 3] = g3
+        if near[f]:
+            o = k0 + 8 * owner[f]
+            b_hi[f, :, o:o + 3] = np.eye(3, dtype=f32)
+            b_hi[f, :, o + 3:o + 6] = np.eye(3, dtype=f32)
+    return {"a_hi": a_hi.reshape(3 * F, K), "a_lo": a_lo.reshape(3 * F, K), "b_hi": b_hi.reshape(3 * F, K), "b_lo": b_lo,
+            "traces": tr, "n_atoms": N, "references": refs, "owner": owner, "near": near}
 
 
 def lambda_max(M):

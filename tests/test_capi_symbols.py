@@ -27,7 +27,7 @@ def test_header_symbols_exported():
 def test_abi_version_and_error_string():
     from mdtraj_b200 import _capi
     L = _capi.lib()
-    assert L.b200rmsd_abi_version() == 1
+    assert L.b200rmsd_abi_version() == 2
     assert isinstance(L.b200rmsd_last_error(), bytes)
     assert L.b200rmsd_scratch_bytes(1000, 25000) > 1000 * 7 * 64
     assert L.b200rmsd_allpairs_workspace_bytes(100, 22) >= 100 * 3 * 32 * 4

@@ -57,6 +57,28 @@ def gen(O, kind, F, N, seed):
     return (O.synth_iid if kind == "iid" else O.synth_md)(F, N, seed=seed)
 
 
+@pytest.fixture
+def ap_path():
+    """Select the all-pairs kernel through the public setting (b200rmsd_allpairs_configure): "tc" = tcgen05 for any
+    size, "simt" = exact-fp32 SIMT for any size, None = the default switch at 512 frames."""
+    from mdtraj_b200 import allpairs as AP
+
+    def select(name):
+        AP.configure(min_tc_frames={"tc": 1, "simt": 1 << 30, None: 512}[name])
+    yield select
+    AP.configure(min_tc_frames=512)
+
+
+def unmirrored_matrix(dt, atom_indices=None):
+    """The matrix with EVERY entry computed (two row blocks; a full-matrix call computes each unordered pair once and
+    mirrors it)."""
+    import torch
+    from mdtraj_b200 import allpairs as AP
+    prep = AP.prepare(dt, atom_indices)
+    h = dt.n_frames // 2
+    return torch.cat([AP.rows(prep, 0, h), AP.rows(prep, h, dt.n_frames)])
+
+
 # ------------------------------------------------------------------ C1: ala2 golden
 def test_ala2_rmsd_matches_reference(mdb, golden, ala2):
     t = mdb.Trajectory(ala2.copy())
@@ -347,17 +369,17 @@ def test_allpairs_vs_truth_random(mdb, oracle_mod):
 
 # ------------------------------------------------------------------ tensor-core all-pairs path
 @pytest.mark.parametrize("F,N", [(600, 300), (1001, 97), (520, 22), (2100, 30)])
-def test_allpairs_tensor_core_vs_simt_and_truth(mdb, oracle_mod, monkeypatch, F, N):
+def test_allpairs_tensor_core_vs_simt_and_truth(mdb, oracle_mod, ap_path, F, N):
     """The tcgen05 3xTF32 kernels (F >= 512) against the exact-fp32 SIMT kernel and float64 truth.  F = 2100 spans
     several super-blocks of the tile walk (53 x 44 tiles of 40 x 48 frames) with ragged edges both ways."""
     O = oracle_mod
     X = O.synth_md(F, N, seed=21, rg=1.0, sigma=0.15)
     dt = mdb.DeviceTrajectory.from_host(X)
-    monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
+    ap_path("tc")
     D_tc = mdb.rmsd_matrix(dt)
-    monkeypatch.setenv("B200RMSD_ALLPAIRS", "simt")
+    ap_path("simt")
     D_simt = mdb.rmsd_matrix(dt)
-    monkeypatch.delenv("B200RMSD_ALLPAIRS")
+    ap_path("tc")
     assert D_tc.shape == (F, F) and np.isfinite(D_tc).all()
     assert np.all(np.diag(D_tc) == 0)
     assert_close(D_tc, D_simt, atol=5e-6, what="tcgen05 vs SIMT all-pairs")
@@ -367,35 +389,127 @@ def test_allpairs_tensor_core_vs_simt_and_truth(mdb, oracle_mod, monkeypatch, F,
         m = np.arange(F) != i
         assert_close(D_tc[i][m], truth[m], what=f"tcgen05 row {i} vs truth")
     # all-float32 solve: reference-class precision, still inside the parity tolerance on this data
-    monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
     D_fast = mdb.rmsd_matrix(dt, precise=False)
     assert_close(D_fast, D_simt, what="tcgen05 float32 solve vs SIMT")
     # a row block, as a rank of a sharded run computes it
     from mdtraj_b200 import allpairs as AP
-    monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
     prep = AP.prepare(dt)
     blk = AP.rows(prep, 37, 123).cpu().numpy()
     # full-matrix calls compute each unordered pair once and mirror it (exactly symmetric); row blocks compute
     # every entry: identical to the unmirrored full matrix bit for bit, and to the mirrored one within float32 noise
     assert np.array_equal(D_tc, D_tc.T)
-    monkeypatch.setenv("B200RMSD_NO_SYMMETRIC", "1")
-    D_full = mdb.rmsd_matrix(dt)
-    monkeypatch.delenv("B200RMSD_NO_SYMMETRIC")
+    D_full = unmirrored_matrix(dt).cpu().numpy()
     assert np.array_equal(blk, D_full[37:123])
     assert_close(blk, D_tc[37:123], atol=2e-6, what="row block vs mirrored full matrix")
 
 
-def test_allpairs_tensor_core_window_sweep(mdb, oracle_mod, monkeypatch):
+def _sampled_rows_vs_truth(O, X, D, rows, atom_indices=None):
+    """max |D[i] - float64 truth| over the sampled rows (a frame against itself left out), and the same for the compiled
+    reference / C port run as the notebook does (md.rmsd(traj, traj, i), examples/clustering.ipynb:78-81)."""
+    kind = "reference" if O.ref_available() else "port"
+    F = len(X)
+    e_gpu = e_ref = e_gr = 0.0
+    for i in rows:
+        truth = O.truth_rmsd(X, X, i, atom_indices=atom_indices)
+        ref = O.rmsd(X, X, i, atom_indices=atom_indices, impl=kind)
+        m = np.arange(F) != i
+        e_gpu = max(e_gpu, float(np.abs(D[i][m] - truth[m]).max()))
+        e_ref = max(e_ref, float(np.abs(ref[m] - truth[m]).max()))
+        e_gr = max(e_gr, float(np.abs(D[i][m] - ref[m]).max()))
+    return e_gpu, e_ref, e_gr
+
+
+@pytest.mark.parametrize("n_basins,interleave", [(2, False), (3, False), (3, True)])
+def test_allpairs_multi_basin(mdb, oracle_mod, n_basins, interleave):
+    """Clustering input: MD-like frames in 2-3 basins 1.4 nm apart, 300 atoms, F = 2400 (round 1 aligned everything onto
+    frame 0 and was 4.6e-5 nm off inside the other basins).  Every sampled row -- at least two per basin -- within
+    1e-5 nm of the float64 truth AND of the reference's md.rmsd(traj, traj, i); one reference structure per basin."""
+    from mdtraj_b200 import allpairs as AP
+    O = oracle_mod
+    F, N = 2400, 300
+    X, which = O.synth_md_basins(F, N, n_basins, seed=31 + n_basins, rg=1.0, sigma=0.1, separation=1.4, interleave=interleave)
+    dt = mdb.DeviceTrajectory.from_host(X)
+    prep = AP.prepare(dt)
+    info = prep.info()
+    assert n_basins <= info["n_refs"] <= n_basins + 2 and info["n_far"] == 0 and info["cover_radius"] < 0.3, info
+    assert sorted(set(which[info["ref_frames"][:n_basins]])) == list(range(n_basins)), "one reference per basin first"
+    D = AP.rows(prep, 0, F).cpu().numpy()
+    rows = [int(np.flatnonzero(which == b)[k]) for b in range(n_basins) for k in (0, 7, -1)]
+    e_gpu, e_ref, e_gr = _sampled_rows_vs_truth(O, X, D, rows)
+    assert e_gpu < 1e-5 and e_gr < 1e-5, (e_gpu, e_ref, e_gr)
+    assert e_gpu < 4e-6, f"multi-reference operands should be in the 1e-6 class: {e_gpu:.2e} (reference: {e_ref:.2e})"
+    assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+    # the same numbers through the public call, with an atom selection, and from a row block of a sharded run
+    idx = np.arange(0, N, 2)
+    Ds = mdb.rmsd_matrix(dt, atom_indices=idx)
+    e_gpu, e_ref, e_gr = _sampled_rows_vs_truth(O, X, Ds, rows[:3], atom_indices=idx)
+    assert e_gpu < 1e-5 and e_gr < 1e-5, (e_gpu, e_ref, e_gr)
+    blk = AP.rows(prep, 1000, 1100).cpu().numpy()
+    assert np.abs(blk - D[1000:1100]).max() < 2e-6
+
+
+def test_allpairs_single_reference_would_fail_multi_basin(mdb, oracle_mod):
+    """The same input with the traversal capped at ONE reference reproduces round 1's error class inside the second
+    basin (> 1e-5 nm): the test above is green because of the references, not because the data is easy."""
+    from mdtraj_b200 import allpairs as AP
+    O = oracle_mod
+    X, which = O.synth_md_basins(2400, 300, 2, seed=33, rg=1.0, sigma=0.1, separation=1.4)
+    dt = mdb.DeviceTrajectory.from_host(X)
+    AP.configure(max_refs=1)
+    try:
+        prep = AP.prepare(dt)
+        assert prep.info()["n_refs"] == 1
+        D = AP.rows(prep, 0, 2400).cpu().numpy()
+    finally:
+        AP.configure(max_refs=32)
+    second = np.flatnonzero(which == 1)
+    i = int(second[3])
+    truth = O.truth_rmsd(X, X, i)
+    m = second[second != i]
+    assert np.abs(D[i][m] - truth[m]).max() > 1e-5
+
+
+def test_allpairs_drifting_trajectory(mdb, oracle_mod):
+    """A trajectory that drifts 0.8 nm away from frame 0 with neighbouring frames 0.02 nm apart: every frame is 'near'
+    frame 0, but the error of the difference operands grows like delta^2 / rmsd_ij, so the traversal keeps adding
+    references along the path until the covering radius is below 0.25 nm.  Neighbouring-frame RMSDs (the small ones, where
+    float32 inner products are weakest) must stay within tolerance of the float64 truth or beat the reference."""
+    from mdtraj_b200 import allpairs as AP
+    O = oracle_mod
+    F, N = 2000, 300
+    X = O.synth_md_drift(F, N, seed=2, step=0.01)
+    dt = mdb.DeviceTrajectory.from_host(X)
+    prep = AP.prepare(dt)
+    info = prep.info()
+    assert 3 <= info["n_refs"] <= 32 and info["n_far"] == 0 and info["cover_radius"] <= 0.3, info
+    D = AP.rows(prep, 0, F).cpu().numpy()
+    e_gpu, e_ref, e_gr = _sampled_rows_vs_truth(O, X, D, [3, 700, 1400, 1998])
+    assert e_gpu <= max(1e-5, 1.5 * e_ref), (e_gpu, e_ref, e_gr)
+
+
+def test_allpairs_iid_frames_stop_the_traversal(mdb, oracle_mod):
+    """iid frames are far from everything: references capture nothing, the traversal stops after four, all frames keep
+    plain operands and the numbers stay in the 1e-6 class (large RMSDs, no cancellation)."""
+    from mdtraj_b200 import allpairs as AP
+    O = oracle_mod
+    X = O.synth_iid(1500, 300, seed=5)
+    prep = AP.prepare(mdb.DeviceTrajectory.from_host(X))
+    info = prep.info()
+    assert info["n_refs"] == 4 and info["n_far"] == 1500 - 4, info
+    D = AP.rows(prep, 0, 1500).cpu().numpy()
+    e_gpu, e_ref, e_gr = _sampled_rows_vs_truth(O, X, D, [0, 777, 1499])
+    assert e_gpu < 3e-6 and e_gr < 1e-5, (e_gpu, e_ref, e_gr)
+
+
+def test_allpairs_tensor_core_window_sweep(mdb, oracle_mod, ap_path):
     """Row/column windows that start and end anywhere relative to the 40- and 48-frame tile grids, incl. diagonal
     squares off the origin (symmetric mode with different i- and j-grid origins): every entry equals the full matrix."""
     import torch
     from mdtraj_b200 import allpairs as AP
-    monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
+    ap_path("tc")
     X = oracle_mod.synth_md(1300, 40, seed=44, rg=0.8, sigma=0.1)
     dt = mdb.DeviceTrajectory.from_host(X)
-    monkeypatch.setenv("B200RMSD_NO_SYMMETRIC", "1")
-    full = mdb.rmsd_matrix_device(dt)
-    monkeypatch.delenv("B200RMSD_NO_SYMMETRIC")
+    full = unmirrored_matrix(dt)
     prep = AP.prepare(dt)
     for (r0, r1, c0, c1) in [(0, 1300, 0, 1300), (50, 1251, 50, 1251), (47, 1001, 47, 1001), (960, 1300, 960, 1300),
                              (1, 2, 0, 1300), (0, 1300, 1299, 1300), (39, 41, 47, 49), (1000, 1300, 0, 500),
@@ -412,11 +526,11 @@ def test_allpairs_tensor_core_window_sweep(mdb, oracle_mod, monkeypatch):
         assert (out[:, :c0] == -1).all() and (out[:, c1:] == -1).all(), "wrote outside the column window"
 
 
-def test_allpairs_tensor_core_degenerate_geometries(mdb, oracle_mod, monkeypatch):
+def test_allpairs_tensor_core_degenerate_geometries(mdb, oracle_mod, ap_path):
     """Double largest root of the QCP quartic -- atoms on a line, two-atom selections -- where Newton alone lands on
     the wrong root (tests/test_qcp_host.py); the epilogue's certificate sends these pairs to the closed form."""
     O = oracle_mod
-    monkeypatch.setenv("B200RMSD_ALLPAIRS", "tc")
+    ap_path("tc")
     rng = np.random.default_rng(7)
     F = 640
     line = rng.standard_normal((30, 1)) * np.array([[1.0, 0.0, 0.0]]) + 0.05 * rng.standard_normal((F, 30, 3))
@@ -582,17 +696,15 @@ def test_superpose_and_center_properties_at_scale(mdb, F, N, stride):
     assert (pre - fly)[1:].abs().max().item() < 1e-5
 
 
-def test_allpairs_block_api(mdb, oracle_mod, monkeypatch):
+def test_allpairs_block_api(mdb, oracle_mod, ap_path):
     """b200rmsd_allpairs_block_dev: rectangular blocks, transposed copies and diagonal squares on both kernels."""
     import torch
     from mdtraj_b200 import allpairs as AP
     X = oracle_mod.synth_md(700, 64, seed=33, rg=0.8, sigma=0.1)
     dt = mdb.DeviceTrajectory.from_host(X)
     for path in ("tc", "simt"):
-        monkeypatch.setenv("B200RMSD_ALLPAIRS", path)
-        monkeypatch.setenv("B200RMSD_NO_SYMMETRIC", "1")
-        full = mdb.rmsd_matrix_device(dt)
-        monkeypatch.delenv("B200RMSD_NO_SYMMETRIC")
+        ap_path(path)
+        full = unmirrored_matrix(dt)
         prep = AP.prepare(dt)
         out = torch.zeros((190, 700), dtype=torch.float32, device=dt.device)
         out_t = torch.zeros((251, 190), dtype=torch.float32, device=dt.device)

@@ -221,26 +221,32 @@ def test_allpairs_tile_walk_covers_every_pair_once():
 
 def test_allpairs_workspace_geometry():
     """b200rmsd_allpairs_workspace_bytes (csrc/allpairs_layout.cuh: ap_geometry): the tensor-core path (F >= 512) holds four
-    tf32 operand matrices of (3F + 160) rows x K floats, K = atoms rounded up to 8, plus 6 augmentation columns, rounded up
-    to 32 -- and the alignment pass's buffers; the SIMT path one (F,3,K32) copy.  Sizes must grow monotonically and stay
-    256-byte granular (the prepare entry point rejects unaligned workspaces)."""
+    tf32 operand matrices of (3F + 160) rows x K floats, K = atoms rounded up to 32, three augmentation matrices of 256
+    columns (8 per reference structure, at most 32 references), the references themselves and the traversal's per-frame
+    buffers; the SIMT path one (F,3,K32) copy.  Sizes must grow monotonically and stay 256-byte granular (the prepare entry
+    point rejects unaligned workspaces)."""
     from mdtraj_b200 import _capi
     L = _capi.lib()
     wb = L.b200rmsd_allpairs_workspace_bytes
     assert wb(0, 10) == 256 and wb(10, 0) == 256
     for n_sel in (1, 2, 22, 299, 300, 301, 314, 315, 1000, 4097):
-        k0 = (n_sel + 7) // 8 * 8
-        k_pad = (k0 + 6 + 31) // 32 * 32
-        assert k_pad >= n_sel + 6 and k_pad % 32 == 0 and k0 % 8 == 0 and k0 >= n_sel   # augmentation in its own K-step
+        k_pad = (n_sel + 31) // 32 * 32
         prev = 0
         for F in (512, 513, 1000, 20000, 100000):
             n = wb(F, n_sel)
             rows = (3 * F + 160 + 7) // 8 * 8
-            operands = 4 * rows * k_pad * 4
+            operands = 4 * rows * k_pad * 4 + 3 * rows * 256 * 4
+            refs = 32 * ((n_sel + 3) // 4 * 4 * 12 + 256)
             assert n % 256 == 0 and n > prev
-            assert operands <= n <= operands + F * 256 + (1 << 20) + 16 * F * ((n_sel + 4095) // 4096 + 1) * 4 * 2, (F, n_sel, n)
+            assert operands + refs <= n <= operands + refs + F * 256 + (1 << 20) + 16 * F * ((n_sel + 4095) // 4096 + 1) * 4 * 2, \
+                (F, n_sel, n)
             prev = n
         small = wb(511, n_sel)   # SIMT path below 512 frames
         assert small % 256 == 0 and small >= 511 * 3 * ((n_sel + 31) // 32 * 32) * 4
-    # C4: 100k frames x 300 atoms -> four 300160 x 320 float matrices (1.54 GB) + ~10 MB
-    assert 1.53e9 < wb(100000, 300) < 1.56e9
+    # C4: 100k frames x 300 atoms -> four 300160 x 320 float matrices (1.54 GB) + three 300160 x 256 (0.92 GB) + ~20 MB
+    assert 2.45e9 < wb(100000, 300) < 2.50e9
+    # the kernel switch is a public setting, not an environment variable
+    assert L.b200rmsd_allpairs_configure(1 << 30, 0) == 0
+    assert 3.8e8 < wb(100000, 300) < 3.9e8             # SIMT layout: one (F,3,320) float copy + traces
+    assert L.b200rmsd_allpairs_configure(512, 0) == 0
+    assert 2.45e9 < wb(100000, 300) < 2.50e9

@@ -25,6 +25,10 @@ def main():
     res = {"F": F, "N": N}
     for name, dt in (("iid", mdb.DeviceTrajectory.synthetic_iid(F, N, 1, dev)), ("md", md_like(F, N, dev))):
         prep = AP.prepare(dt)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(); prep = AP.prepare(dt); p1.record(); torch.cuda.synchronize()
+        res[name + "_prepare_ms"] = p0.elapsed_time(p1); res[name + "_info"] = prep.info()
         out = torch.empty((F, F), dtype=torch.float32, device=dev)
         for _ in range(2):
             AP.rows(prep, 0, F, out=out)
