@@ -17,9 +17,12 @@
  *   - "_dev" entry points take DEVICE pointers, run asynchronously on `stream`
  *     (a cudaStream_t passed as void*; NULL = default stream) of the calling thread's
  *     current device, and never allocate.  Scratch is caller-provided.
- *   - "_host" entry points take HOST pointers (pageable or pinned), stage through an
- *     internal per-device workspace, pipeline H2D copies against kernels, and return
- *     when the results are in the caller's host buffers.
+ *   - "_host" entry points take HOST pointers, stage through an internal per-device
+ *     workspace, pipeline H2D copies against kernels, and return when the results are in
+ *     the caller's host buffers.  Pageable memory (any numpy array) is staged through
+ *     page-locked buffers by a pool of memcpy threads; page-locked memory is DMA'd directly.
+ *     After a failed in-place call (superpose_host, center_host) the contents of xyz are
+ *     undefined; no transfer is in flight any more when an error is returned.
  *   - staged trajectory layout ("padded atom-major"): float32, frame f starts at
  *     xyz + f*frame_stride, holds n_atoms x 3 floats followed by zeros up to
  *     n_pad = 4*ceil(n_atoms/4) atoms; frame_stride >= 3*n_pad and frame_stride % 4 == 0;
@@ -243,6 +246,28 @@ int b200rmsd_superpose_host(float* xyz, int64_t n_frames, int n_atoms, const flo
 /* _center_inplace_atom_major on a host array (n_frames, n_atoms, 3), in place; traces
  * (n_frames) may be NULL.  Replaces: _rmsd.pyx:487-491. */
 int b200rmsd_center_host(float* xyz, int64_t n_frames, int n_atoms, float* traces, int device);
+
+/* The same three calls over SEVERAL devices from one process: the frames are cut into chunks that are handed out
+ * dynamically to the listed devices (one host thread each; frames are independent, so there is no exchange between
+ * devices -- BASELINE north_star: "a trivial frame split with a host gather").  `devices`: n_devices distinct CUDA
+ * device indices.  The single-device entry points above are the n_devices = 1 case.  Results are identical to the
+ * single-device call bit for bit (each frame is computed by the same kernel whichever device takes its chunk). */
+int b200rmsd_rmsd_host_multi(const float* target, int64_t n_frames, int n_atoms_target, const float* ref_frame,
+                             int n_atoms_ref, const int32_t* idx, const int32_t* ref_idx, int n_sel, int superpose,
+                             int precentered, const float* traces, float ref_trace, float* out, const int* devices,
+                             int n_devices);
+int b200rmsd_superpose_host_multi(float* xyz, int64_t n_frames, int n_atoms, const float* ref_frame, int n_atoms_ref,
+                                  const int32_t* idx, const int32_t* ref_idx, int n_sel, float* out_rot, float* out_rmsd,
+                                  unsigned* n_degenerate, const int* devices, int n_devices);
+int b200rmsd_center_host_multi(float* xyz, int64_t n_frames, int n_atoms, float* traces, const int* devices,
+                               int n_devices);
+
+/* Process-wide settings of the host pipeline; a value <= 0 leaves the setting as it is.
+ *   copy_threads:    threads of the memcpy pool that stages pageable host memory through page-locked buffers (default:
+ *                    all hardware threads but one, at most 24; takes effect before the pool's first use);
+ *   chunk_mb:        MB of padded coordinates per chunk when the caller's memory is page-locked (default 64);
+ *   staged_chunk_mb: the same for pageable memory (default 16: three staging lanes stay inside a 60 MB host L3). */
+int b200rmsd_host_configure(int copy_threads, int chunk_mb, int staged_chunk_mb);
 
 /* Release the internal per-device workspaces of the host API. */
 void b200rmsd_release_workspaces(void);

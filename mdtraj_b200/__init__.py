@@ -14,7 +14,8 @@ mdtraj is rebuilt.  Hand-written CUDA behind a C ABI (``include/b200rmsd.h``,
 """
 from ._rmsd import (TypeCastPerformanceWarning, _center_inplace_atom_major, current_device,  # noqa: F401
                     getMultipleAlignDisplaceRMSDs_atom_major, getMultipleRMSDs_atom_major,
-                    getMultipleRMSDs_axis_major, rmsd, rmsf, set_device, set_inplace_centering, superpose_atom_major)
+                    getMultipleRMSDs_axis_major, rmsd, rmsf, set_device, set_devices, set_host_pipeline, set_inplace_centering,
+                    superpose_atom_major)
 from .trajectory import Trajectory  # noqa: F401
 
 __version__ = "0.1.0"

@@ -28,7 +28,7 @@ from . import _capi
 __all__ = [
     "rmsd", "rmsf", "_center_inplace_atom_major", "getMultipleRMSDs_atom_major", "getMultipleRMSDs_axis_major",
     "superpose_atom_major", "getMultipleAlignDisplaceRMSDs_atom_major", "set_inplace_centering", "set_device",
-    "current_device", "TypeCastPerformanceWarning",
+    "set_devices", "set_host_pipeline", "current_device", "current_devices", "TypeCastPerformanceWarning",
 ]
 
 
@@ -36,7 +36,7 @@ class TypeCastPerformanceWarning(RuntimeWarning):
     """Same role as mdtraj.utils.validation.TypeCastPerformanceWarning (validation.py:36)."""
 
 
-_state = {"inplace": False, "device": None}
+_state = {"inplace": False, "device": None, "devices": None}
 
 
 def set_inplace_centering(flag: bool) -> None:
@@ -49,10 +49,42 @@ def set_device(index) -> None:
     _state["device"] = None if index is None else int(index)
 
 
+def set_devices(indices) -> None:
+    """CUDA devices the host-array entry points spread their frames over (``b200rmsd_*_host_multi``).  ``None`` restores
+    the default: the one device of ``set_device`` / ``$MDTRAJ_B200_DEVICE`` / ``$LOCAL_RANK`` when any of those is set (one
+    process per GPU under torchrun), otherwise every visible device."""
+    _state["devices"] = None if indices is None else [int(i) for i in indices]
+
+
+def set_host_pipeline(copy_threads=None, chunk_mb=None, staged_chunk_mb=None) -> None:
+    """Settings of the host-array pipeline (``b200rmsd_host_configure``): threads of the memcpy pool that stages pageable
+    memory through page-locked buffers (before its first use), MB of coordinates per chunk for page-locked (default 64)
+    and for pageable (default 16) caller memory."""
+    _capi.check(_capi.lib().b200rmsd_host_configure(int(copy_threads or 0), int(chunk_mb or 0), int(staged_chunk_mb or 0)),
+                "b200rmsd_host_configure")
+
+
 def current_device() -> int:
     if _state["device"] is not None:
         return _state["device"]
+    if _state["devices"]:
+        return _state["devices"][0]
     return int(os.environ.get("MDTRAJ_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+_n_visible = None
+
+
+def current_devices():
+    """Devices a host-array call runs on, as an int32 array (see ``set_devices``)."""
+    global _n_visible
+    if _state["devices"]:
+        return np.asarray(_state["devices"], dtype=np.int32)
+    if _state["device"] is not None or "MDTRAJ_B200_DEVICE" in os.environ or "LOCAL_RANK" in os.environ:
+        return np.asarray([current_device()], dtype=np.int32)
+    if _n_visible is None:
+        _n_visible = max(1, int(_capi.device_info(0)["n_devices"]))
+    return np.arange(_n_visible, dtype=np.int32)
 
 
 # ---------------------------------------------------------------------------
@@ -154,7 +186,7 @@ def rmsd(target, reference, frame=0, atom_indices=None, ref_atom_indices=None, p
     ref_frame = _as_f32c(rxyz[frame])
     out = np.zeros(n_frames, dtype=np.float32)
     L = _capi.lib()
-    dev = current_device()
+    devs = current_devices()
 
     use_traces = False
     traces = None
@@ -182,11 +214,11 @@ def rmsd(target, reference, frame=0, atom_indices=None, ref_atom_indices=None, p
         ridx = _i32(ref_atom_indices)
         idx = np.arange(len(ridx), dtype=np.int32)
 
-    rc = L.b200rmsd_rmsd_host(
+    rc = L.b200rmsd_rmsd_host_multi(
         t32.ctypes.data, n_frames, t32.shape[1], ref_frame.ctypes.data, ref_frame.shape[0],
         _capi.np_ptr(idx), _capi.np_ptr(ridx), 0 if idx is None else len(idx), int(bool(superpose)),
-        int(use_traces), _capi.np_ptr(traces), ref_trace, out.ctypes.data, dev)
-    _capi.check(rc, "b200rmsd_rmsd_host")
+        int(use_traces), _capi.np_ptr(traces), ref_trace, out.ctypes.data, devs.ctypes.data, len(devs))
+    _capi.check(rc, "b200rmsd_rmsd_host_multi")
 
     if atom_indices_is_none and superpose and target is reference and 0 <= (frame % rxyz.shape[0]) < n_frames:
         # the reference's same-pointer shortcut (theobald_rmsd_sse.h:256-262): a frame against itself,
@@ -196,11 +228,11 @@ def rmsd(target, reference, frame=0, atom_indices=None, ref_atom_indices=None, p
     if _state["inplace"] and superpose and not use_traces and atom_indices_is_none:
         # reproduce the documented side effect (_rmsd.pyx:71): centre the live arrays
         if txyz.dtype == np.float32 and txyz.flags.c_contiguous:
-            _capi.check(L.b200rmsd_center_host(txyz.ctypes.data, n_frames, txyz.shape[1], None, dev),
-                        "b200rmsd_center_host")
+            _capi.check(L.b200rmsd_center_host_multi(txyz.ctypes.data, n_frames, txyz.shape[1], None, devs.ctypes.data,
+                                                     len(devs)), "b200rmsd_center_host_multi")
         if rxyz is not txyz and rxyz.dtype == np.float32 and rxyz[frame].flags.c_contiguous:
             fr = rxyz[frame]
-            _capi.check(L.b200rmsd_center_host(fr.ctypes.data, 1, fr.shape[0], None, dev), "b200rmsd_center_host")
+            _capi.check(L.b200rmsd_center_host(fr.ctypes.data, 1, fr.shape[0], None, int(devs[0])), "b200rmsd_center_host")
     return out
 
 
@@ -218,8 +250,9 @@ def _center_inplace_atom_major(xyz):
     assert xyz.shape[2] == 3
     traces = np.empty(xyz.shape[0], dtype=np.float32)
     if xyz.shape[0] and xyz.shape[1]:
-        _capi.check(_capi.lib().b200rmsd_center_host(xyz.ctypes.data, xyz.shape[0], xyz.shape[1], traces.ctypes.data,
-                                                     current_device()), "b200rmsd_center_host")
+        devs = current_devices()
+        _capi.check(_capi.lib().b200rmsd_center_host_multi(xyz.ctypes.data, xyz.shape[0], xyz.shape[1], traces.ctypes.data,
+                                                           devs.ctypes.data, len(devs)), "b200rmsd_center_host_multi")
     return traces
 
 
@@ -253,7 +286,9 @@ def getMultipleRMSDs_atom_major(xyz1, xyz2, g1, g2, frame, parallel=True):
                                         None, None, 0, 1, 1, g2.ctypes.data, float(g1[frame]), out.ctypes.data,
                                         current_device())
     _capi.check(rc, "b200rmsd_rmsd_host")
-    if xyz1 is xyz2 and np.shares_memory(g1, g2) or (xyz1.ctypes.data == xyz2.ctypes.data and g1[frame] == g2[frame]):
+    same_memory = (xyz1 is xyz2 and np.shares_memory(g1, g2)) or \
+        (xyz1.ctypes.data == xyz2.ctypes.data and frame < g2.shape[0] and g1[frame] == g2[frame])
+    if same_memory and -xyz2.shape[0] <= frame < xyz2.shape[0]:
         out[frame] = 0.0  # same-pointer shortcut, theobald_rmsd_sse.h:256-262
     return out
 
@@ -273,7 +308,8 @@ def getMultipleRMSDs_axis_major(xyz1, xyz2, g1, g2, frame, parallel=True):
     a2 = np.ascontiguousarray(np.transpose(xyz2, (0, 2, 1)))
     g1 = _as_f32c(g1)
     out = getMultipleRMSDs_atom_major(a1, a2, g1[frame:frame + 1], g2, 0)
-    if xyz1.ctypes.data == xyz2.ctypes.data and float(g1[frame]) == float(np.asarray(g2)[frame]):
+    if xyz1.ctypes.data == xyz2.ctypes.data and frame < xyz2.shape[0] and \
+            float(g1[frame]) == float(np.asarray(g2)[frame]):
         out[frame] = 0.0
     return out
 

@@ -17,8 +17,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200rmsd.so")
-SOURCES = ["capi.cu", "one_vs_many.cu", "aux_kernels.cu", "frame_resident.cu", "allpairs.cu", "allpairs_refs.cu", "allpairs_tc144.cu", "cluster_ops.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "qcp.cuh", "allpairs_layout.cuh", "tc_ptx.cuh", "../../include/b200rmsd.h"]
+SOURCES = ["capi.cu", "host_pipeline.cu", "one_vs_many.cu", "aux_kernels.cu", "frame_resident.cu", "allpairs.cu", "allpairs_refs.cu", "allpairs_tc144.cu", "cluster_ops.cu"]
+HEADERS = ["host_pipeline.cu", "allpairs_refs.cu", "common.cuh", "kernels.cuh", "qcp.cuh", "allpairs_layout.cuh", "tc_ptx.cuh", "../../include/b200rmsd.h"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -41,11 +41,16 @@ def needs_build() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, dev: bool = False) -> str:
+    """dev=True adds -DB200RMSD_DEV_SWITCHES: the B200RMSD_* environment overrides (kernel / geometry selection, isolation
+    runs) the sweeps under tools/ use.  A release build (the default, what the tests and the bench run) never reads the
+    environment."""
+    if not force and not dev and not needs_build():
         return LIB
-    cmd = [nvcc_path(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+    cmd = [nvcc_path(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-pthread",
            "-ccbin", "/usr/bin/g++", "-o", LIB, *sources()]
+    if dev:
+        cmd[1:1] = ["-DB200RMSD_DEV_SWITCHES"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -57,4 +62,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, dev="--dev" in sys.argv))

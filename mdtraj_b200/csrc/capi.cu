@@ -1,8 +1,5 @@
-// capi.cu -- extern "C" entry points declared in include/b200rmsd.h.
-//
-// Device API: thin argument checking + kernel configuration.  Host API: chunked,
-// double-buffered H2D -> kernel -> D2H pipeline over two streams with a per-device
-// workspace, so PCIe transfers of chunk c+1 overlap the kernels of chunk c.
+// capi.cu -- extern "C" device entry points declared in include/b200rmsd.h: thin argument checking + kernel
+// configuration.  The host-array entry points live in host_pipeline.cu, the all-pairs ones in allpairs.cu.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -71,10 +68,17 @@ int current_sm_count(int* sm)
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// development overrides (kernel / geometry selection for the sweeps under tools/): compiled in only with
+// -DB200RMSD_DEV_SWITCHES (python -m mdtraj_b200.build --dev); a release build never reads the environment
 inline int env_int(const char* name, int dflt)
 {
+#ifdef B200RMSD_DEV_SWITCHES
     const char* s = getenv(name);
     return s && *s ? atoi(s) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
 }
 
 // choose segmenting / ring geometry of the TMA kernel for n_atoms
@@ -370,309 +374,6 @@ int b200rmsd_rot_msd_dev(const float* a_frame, const float* b_xyz, int64_t n_fra
     if (int rc = current_sm_count(&sm)) return rc;
     CU(launch_rot_msd(a_frame, b_xyz, n_frames, n_atoms, frame_stride, rot, transpose, rot_out, out_rmsd, sm, (cudaStream_t)stream));
     return 0;
-}
-
-}  // extern "C"
-
-// ===========================================================================
-// Host API: per-device workspace + chunked pipeline
-// ===========================================================================
-namespace {
-
-struct Workspace {
-    bool init = false;
-    cudaStream_t stream[2] = {nullptr, nullptr};
-    cudaEvent_t ref_ready = nullptr;
-    // two chunk slots
-    float* xyz[2] = {nullptr, nullptr};
-    size_t xyz_bytes = 0;
-    float* out[2] = {nullptr, nullptr};   // rmsd per chunk
-    float* rot[2] = {nullptr, nullptr};
-    float* trc[2] = {nullptr, nullptr};
-    void* scratch[2] = {nullptr, nullptr};
-    size_t per_frame_cap = 0;             // frames the small per-frame buffers can hold
-    size_t scratch_bytes = 0;
-    // reference
-    float* ref_raw = nullptr;             // full reference frame as uploaded
-    float* ref_sel = nullptr;             // prepared (centred / packed)
-    size_t ref_cap = 0;                   // in atoms
-    int32_t* idx = nullptr;
-    int32_t* ref_idx = nullptr;
-    size_t idx_cap = 0;
-    RefStats* stats = nullptr;
-    unsigned* degen = nullptr;
-    std::mutex mu;
-    void reset()
-    {
-        init = false;
-        ref_ready = nullptr;
-        for (int i = 0; i < 2; ++i) { stream[i] = nullptr; xyz[i] = out[i] = rot[i] = trc[i] = nullptr; scratch[i] = nullptr; }
-        xyz_bytes = per_frame_cap = scratch_bytes = ref_cap = idx_cap = 0;
-        ref_raw = ref_sel = nullptr; idx = ref_idx = nullptr; stats = nullptr; degen = nullptr;
-    }
-};
-Workspace g_ws[64];
-
-template <class T>
-cudaError_t regrow(T*& p, size_t bytes)
-{
-    if (p) cudaFree(p);
-    p = nullptr;
-    return cudaMalloc((void**)&p, bytes);
-}
-
-int ws_prepare(Workspace& w, size_t chunk_bytes, size_t chunk_frames, size_t scratch_bytes, size_t ref_atoms,
-               size_t n_idx)
-{
-    if (!w.init) {
-        for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithFlags(&w.stream[i], cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&w.ref_ready, cudaEventDisableTiming));
-        CU(cudaMalloc((void**)&w.stats, sizeof(RefStats)));
-        CU(cudaMalloc((void**)&w.degen, sizeof(unsigned)));
-        w.init = true;
-    }
-    if (chunk_bytes > w.xyz_bytes) {
-        for (int i = 0; i < 2; ++i)
-            if (regrow(w.xyz[i], chunk_bytes) != cudaSuccess) return fail(B200RMSD_ENOMEM, "workspace: %zu bytes", chunk_bytes);
-        w.xyz_bytes = chunk_bytes;
-    }
-    if (chunk_frames > w.per_frame_cap) {
-        for (int i = 0; i < 2; ++i) {
-            if (regrow(w.out[i], chunk_frames * sizeof(float)) != cudaSuccess ||
-                regrow(w.rot[i], chunk_frames * 9 * sizeof(float)) != cudaSuccess ||
-                regrow(w.trc[i], chunk_frames * sizeof(float)) != cudaSuccess)
-                return fail(B200RMSD_ENOMEM, "workspace: per-frame buffers");
-        }
-        w.per_frame_cap = chunk_frames;
-    }
-    if (scratch_bytes > w.scratch_bytes) {
-        for (int i = 0; i < 2; ++i)
-            if (regrow(w.scratch[i], scratch_bytes) != cudaSuccess) return fail(B200RMSD_ENOMEM, "workspace: scratch");
-        w.scratch_bytes = scratch_bytes;
-    }
-    if (ref_atoms > w.ref_cap) {
-        const size_t b = (ref_atoms + 4) * 3 * sizeof(float);
-        if (regrow(w.ref_raw, b) != cudaSuccess || regrow(w.ref_sel, b) != cudaSuccess)
-            return fail(B200RMSD_ENOMEM, "workspace: reference");
-        w.ref_cap = ref_atoms;
-    }
-    if (n_idx > w.idx_cap) {
-        if (regrow(w.idx, n_idx * sizeof(int32_t)) != cudaSuccess || regrow(w.ref_idx, n_idx * sizeof(int32_t)) != cudaSuccess)
-            return fail(B200RMSD_ENOMEM, "workspace: index lists");
-        w.idx_cap = n_idx;
-    }
-    return 0;
-}
-
-// frames per chunk: ~B200RMSD_CHUNK_MB (default 64 MB) of padded coordinates
-int64_t frames_per_chunk(int64_t n_frames, int n_pad)
-{
-    const size_t frame_bytes = (size_t)n_pad * 12;
-    const size_t target = (size_t)env_int("B200RMSD_CHUNK_MB", 64) << 20;
-    int64_t fpc = (int64_t)std::max<size_t>(1, target / frame_bytes);
-    return std::min<int64_t>(fpc, std::max<int64_t>(n_frames, 1));
-}
-
-// H2D of frames [f0, f0+nf) into the padded device layout
-cudaError_t upload_chunk(float* dst, const float* src_host, int64_t f0, int64_t nf, int n_atoms, int n_pad, cudaStream_t st)
-{
-    const float* src = src_host + (size_t)f0 * n_atoms * 3;
-    if (n_pad == n_atoms) return cudaMemcpyAsync(dst, src, (size_t)nf * n_atoms * 12, cudaMemcpyHostToDevice, st);
-    cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)nf * n_pad * 12, st);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy2DAsync(dst, (size_t)n_pad * 12, src, (size_t)n_atoms * 12, (size_t)n_atoms * 12, (size_t)nf,
-                             cudaMemcpyHostToDevice, st);
-}
-cudaError_t download_chunk(float* dst_host, const float* src, int64_t f0, int64_t nf, int n_atoms, int n_pad, cudaStream_t st)
-{
-    float* dst = dst_host + (size_t)f0 * n_atoms * 3;
-    if (n_pad == n_atoms) return cudaMemcpyAsync(dst, src, (size_t)nf * n_atoms * 12, cudaMemcpyDeviceToHost, st);
-    return cudaMemcpy2DAsync(dst, (size_t)n_atoms * 12, src, (size_t)n_pad * 12, (size_t)n_atoms * 12, (size_t)nf,
-                             cudaMemcpyDeviceToHost, st);
-}
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = false;
-    explicit DeviceGuard(int dev)
-    {
-        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
-    }
-    ~DeviceGuard()
-    {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
-}  // namespace
-
-extern "C" {
-
-int b200rmsd_rmsd_host(const float* target, int64_t n_frames, int n_atoms_target, const float* ref_frame,
-                       int n_atoms_ref, const int32_t* idx, const int32_t* ref_idx, int n_sel, int superpose,
-                       int precentered, const float* traces, float ref_trace, float* out, int device)
-{
-    if (!target || !ref_frame || !out || n_frames < 0 || n_atoms_target <= 0 || n_atoms_ref <= 0)
-        return fail(B200RMSD_EINVAL, "rmsd_host: bad arguments");
-    if ((idx == nullptr) != (ref_idx == nullptr)) return fail(B200RMSD_EINVAL, "rmsd_host: idx and ref_idx must both be given or both NULL");
-    if (!idx && n_atoms_target != n_atoms_ref) return fail(B200RMSD_EINVAL, "rmsd_host: atom counts differ and no index lists given");
-    if (idx && n_sel <= 0) return fail(B200RMSD_EINVAL, "rmsd_host: empty selection");
-    if (precentered && (!traces || idx)) return fail(B200RMSD_EINVAL, "rmsd_host: precentered needs traces and no index lists");
-    if (device < 0 || device >= 64) return fail(B200RMSD_EINVAL, "rmsd_host: device %d", device);
-    if (n_frames == 0) return 0;
-    DeviceGuard guard(device);
-    if (!guard.ok) return fail(B200RMSD_ENODEVICE, "rmsd_host: cannot select CUDA device %d", device);
-    int sm = 0;
-    if (int rc = current_sm_count(&sm)) return rc;
-
-    Workspace& w = g_ws[device];
-    std::lock_guard<std::mutex> lk(w.mu);
-    const int n_pad = (n_atoms_target + 3) / 4 * 4;
-    const int64_t fpc = frames_per_chunk(n_frames, n_pad);
-    const int n_use = idx ? n_sel : n_atoms_target;
-    if (int rc = ws_prepare(w, (size_t)fpc * n_pad * 12, (size_t)fpc, b200rmsd_scratch_bytes(fpc, n_atoms_target),
-                            (size_t)std::max(n_atoms_ref, n_use), idx ? (size_t)n_sel : 0))
-        return rc;
-
-    cudaStream_t s0 = w.stream[0];
-    CU(cudaMemcpyAsync(w.ref_raw, ref_frame, (size_t)n_atoms_ref * 12, cudaMemcpyHostToDevice, s0));
-    if (idx) {
-        CU(cudaMemcpyAsync(w.idx, idx, (size_t)n_sel * 4, cudaMemcpyHostToDevice, s0));
-        CU(cudaMemcpyAsync(w.ref_idx, ref_idx, (size_t)n_sel * 4, cudaMemcpyHostToDevice, s0));
-    }
-    // superpose: centred packed reference; no-superpose: packed raw reference (do_center = 0)
-    CU(launch_prepare_ref(w.ref_raw, idx ? w.ref_idx : nullptr, n_use, (superpose && !precentered) ? 1 : 0, ref_trace,
-                          w.ref_sel, w.stats, s0));
-    CU(cudaEventRecord(w.ref_ready, s0));
-    CU(cudaStreamWaitEvent(w.stream[1], w.ref_ready, 0));
-
-    int slot = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += fpc, slot ^= 1) {
-        const int64_t nf = std::min(fpc, n_frames - f0);
-        cudaStream_t st = w.stream[slot];
-        CU(upload_chunk(w.xyz[slot], target, f0, nf, n_atoms_target, n_pad, st));
-        int rc;
-        if (superpose) {
-            if (precentered) CU(cudaMemcpyAsync(w.trc[slot], traces + f0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
-            rc = b200rmsd_rmsd_dev(w.xyz[slot], nf, n_atoms_target, (int64_t)n_pad * 3, idx ? w.idx : nullptr, n_sel,
-                                   w.ref_sel, w.stats, precentered ? w.trc[slot] : nullptr,
-                                   precentered ? B200RMSD_PRECENTERED : 0u, w.out[slot], nullptr, nullptr, nullptr,
-                                   w.scratch[slot], w.scratch_bytes, st);
-        } else {
-            rc = b200rmsd_rmsd_nosuperpose_dev(w.xyz[slot], nf, n_atoms_target, (int64_t)n_pad * 3,
-                                               idx ? w.idx : nullptr, n_sel, w.ref_sel, w.out[slot], st);
-        }
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(out + f0, w.out[slot], (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CU(cudaStreamSynchronize(w.stream[0]));
-    CU(cudaStreamSynchronize(w.stream[1]));
-    return 0;
-}
-
-int b200rmsd_superpose_host(float* xyz, int64_t n_frames, int n_atoms, const float* ref_frame, int n_atoms_ref,
-                            const int32_t* idx, const int32_t* ref_idx, int n_sel, float* out_rot, float* out_rmsd,
-                            unsigned* n_degenerate, int device)
-{
-    if (!xyz || !ref_frame || n_frames < 0 || n_atoms <= 0 || n_atoms_ref <= 0) return fail(B200RMSD_EINVAL, "superpose_host: bad arguments");
-    if ((idx == nullptr) != (ref_idx == nullptr)) return fail(B200RMSD_EINVAL, "superpose_host: idx and ref_idx must both be given or both NULL");
-    if (!idx && n_atoms != n_atoms_ref) return fail(B200RMSD_EINVAL, "superpose_host: atom counts differ and no index lists given");
-    if (idx && n_sel <= 0) return fail(B200RMSD_EINVAL, "superpose_host: empty selection");
-    if (device < 0 || device >= 64) return fail(B200RMSD_EINVAL, "superpose_host: device %d", device);
-    if (n_degenerate) *n_degenerate = 0;
-    if (n_frames == 0) return 0;
-    DeviceGuard guard(device);
-    if (!guard.ok) return fail(B200RMSD_ENODEVICE, "superpose_host: cannot select CUDA device %d", device);
-    int sm = 0;
-    if (int rc = current_sm_count(&sm)) return rc;
-
-    Workspace& w = g_ws[device];
-    std::lock_guard<std::mutex> lk(w.mu);
-    const int n_pad = (n_atoms + 3) / 4 * 4;
-    const int64_t fpc = frames_per_chunk(n_frames, n_pad);
-    const int n_use = idx ? n_sel : n_atoms;
-    if (int rc = ws_prepare(w, (size_t)fpc * n_pad * 12, (size_t)fpc, b200rmsd_scratch_bytes(fpc, n_atoms),
-                            (size_t)std::max(n_atoms_ref, n_use), idx ? (size_t)n_sel : 0))
-        return rc;
-
-    cudaStream_t s0 = w.stream[0];
-    CU(cudaMemsetAsync(w.degen, 0, sizeof(unsigned), s0));
-    CU(cudaMemcpyAsync(w.ref_raw, ref_frame, (size_t)n_atoms_ref * 12, cudaMemcpyHostToDevice, s0));
-    if (idx) {
-        CU(cudaMemcpyAsync(w.idx, idx, (size_t)n_sel * 4, cudaMemcpyHostToDevice, s0));
-        CU(cudaMemcpyAsync(w.ref_idx, ref_idx, (size_t)n_sel * 4, cudaMemcpyHostToDevice, s0));
-    }
-    CU(launch_prepare_ref(w.ref_raw, idx ? w.ref_idx : nullptr, n_use, 1, 0.f, w.ref_sel, w.stats, s0));
-    CU(cudaEventRecord(w.ref_ready, s0));
-    CU(cudaStreamWaitEvent(w.stream[1], w.ref_ready, 0));
-
-    int slot = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += fpc, slot ^= 1) {
-        const int64_t nf = std::min(fpc, n_frames - f0);
-        cudaStream_t st = w.stream[slot];
-        CU(upload_chunk(w.xyz[slot], xyz, f0, nf, n_atoms, n_pad, st));
-        int rc = b200rmsd_superpose_dev(w.xyz[slot], nf, n_atoms, (int64_t)n_pad * 3, idx ? w.idx : nullptr, n_sel,
-                                        w.ref_sel, w.stats, w.out[slot], w.rot[slot], w.degen, w.scratch[slot],
-                                        w.scratch_bytes, st);
-        if (rc) return rc;
-        CU(download_chunk(xyz, w.xyz[slot], f0, nf, n_atoms, n_pad, st));
-        if (out_rot) CU(cudaMemcpyAsync(out_rot + f0 * 9, w.rot[slot], (size_t)nf * 36, cudaMemcpyDeviceToHost, st));
-        if (out_rmsd) CU(cudaMemcpyAsync(out_rmsd + f0, w.out[slot], (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CU(cudaStreamSynchronize(w.stream[0]));
-    CU(cudaStreamSynchronize(w.stream[1]));
-    if (n_degenerate) CU(cudaMemcpy(n_degenerate, w.degen, sizeof(unsigned), cudaMemcpyDeviceToHost));
-    return 0;
-}
-
-int b200rmsd_center_host(float* xyz, int64_t n_frames, int n_atoms, float* traces, int device)
-{
-    if (!xyz || n_frames < 0 || n_atoms <= 0) return fail(B200RMSD_EINVAL, "center_host: bad arguments");
-    if (device < 0 || device >= 64) return fail(B200RMSD_EINVAL, "center_host: device %d", device);
-    if (n_frames == 0) return 0;
-    DeviceGuard guard(device);
-    if (!guard.ok) return fail(B200RMSD_ENODEVICE, "center_host: cannot select CUDA device %d", device);
-    int sm = 0;
-    if (int rc = current_sm_count(&sm)) return rc;
-    Workspace& w = g_ws[device];
-    std::lock_guard<std::mutex> lk(w.mu);
-    const int n_pad = (n_atoms + 3) / 4 * 4;
-    const int64_t fpc = frames_per_chunk(n_frames, n_pad);
-    if (int rc = ws_prepare(w, (size_t)fpc * n_pad * 12, (size_t)fpc, 256, 4, 0)) return rc;
-    int slot = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += fpc, slot ^= 1) {
-        const int64_t nf = std::min(fpc, n_frames - f0);
-        cudaStream_t st = w.stream[slot];
-        CU(upload_chunk(w.xyz[slot], xyz, f0, nf, n_atoms, n_pad, st));
-        CU(launch_center_trace(w.xyz[slot], nf, n_atoms, (int64_t)n_pad * 3, w.trc[slot], sm, st));
-        CU(download_chunk(xyz, w.xyz[slot], f0, nf, n_atoms, n_pad, st));
-        if (traces) CU(cudaMemcpyAsync(traces + f0, w.trc[slot], (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CU(cudaStreamSynchronize(w.stream[0]));
-    CU(cudaStreamSynchronize(w.stream[1]));
-    return 0;
-}
-
-void b200rmsd_release_workspaces(void)
-{
-    for (int d = 0; d < 64; ++d) {
-        Workspace& w = g_ws[d];
-        std::lock_guard<std::mutex> lk(w.mu);
-        if (!w.init) continue;
-        int prev = -1;
-        cudaGetDevice(&prev);
-        if (cudaSetDevice(d) == cudaSuccess) {
-            for (int i = 0; i < 2; ++i) {
-                cudaFree(w.xyz[i]); cudaFree(w.out[i]); cudaFree(w.rot[i]); cudaFree(w.trc[i]); cudaFree(w.scratch[i]);
-                w.xyz[i] = w.out[i] = w.rot[i] = w.trc[i] = nullptr; w.scratch[i] = nullptr;
-                cudaStreamDestroy(w.stream[i]);
-            }
-            cudaFree(w.ref_raw); cudaFree(w.ref_sel); cudaFree(w.idx); cudaFree(w.ref_idx); cudaFree(w.stats); cudaFree(w.degen);
-            cudaEventDestroy(w.ref_ready);
-        }
-        if (prev >= 0) cudaSetDevice(prev);
-        w.reset();
-    }
 }
 
 }  // extern "C"

@@ -600,6 +600,10 @@ long long* fr_trace_buffer(size_t n_frames_cta)
 {
     static long long* buf = nullptr;
     static size_t cap = 0;
+#ifndef B200RMSD_DEV_SWITCHES
+    (void)buf; (void)cap; (void)n_frames_cta;
+    return nullptr;
+#else
     if (!getenv("B200RMSD_FUSED_TRACE")) return nullptr;
     if (cap < n_frames_cta * 8) {
         if (buf) cudaFree(buf);
@@ -609,6 +613,7 @@ long long* fr_trace_buffer(size_t n_frames_cta)
     cudaMemset(buf, 0, cap * sizeof(long long));
     cudaMemcpyToSymbol(g_fr_trace, &buf, sizeof(buf));
     return buf;
+#endif
 }
 
 // development / test hook (no device needed): the geometry fused_config picks; out = {G, nbuf, fpb, team_warps, lanes,

@@ -510,7 +510,9 @@ bool launch_ovm_group(OvmParams& p, bool precentered, int sm_count, cudaStream_t
     if (sel && frame_bytes > 3072 && (size_t)p.n_atoms * 64 < frame_bytes) return false;
     const size_t sel_bytes = sel ? align_up((size_t)((p.n_atoms + 3) / 4) * 48, 16) + (size_t)p.n_atoms * 4 + 128 : 0;
     size_t max_bytes = 8448;  // 704 atoms: measured 0.97-1.05x of HBM peak up to here, the chunked kernel wins from ~800 atoms
+#ifdef B200RMSD_DEV_SWITCHES
     if (const char* mb = getenv("B200RMSD_GROUP_MAX_BYTES")) max_bytes = (size_t)atol(mb);  // development override
+#endif
     if (p.frame_stride != (int64_t)p.total_units * 12 || frame_bytes > max_bytes || p.n_seg > 1) return false;
     const size_t budget = 232448;
     auto per_warp_bytes = [&](int warps) {
@@ -527,6 +529,7 @@ bool launch_ovm_group(OvmParams& p, bool precentered, int sm_count, cudaStream_t
         for (warps = kWarpsPerCta - 1; warps >= 4; --warps)
             if (per_warp_bytes(warps) / (2 * frame_bytes) >= 2) { Lsel = 16; stages = 2; break; }
     }
+#ifdef B200RMSD_DEV_SWITCHES
     if (const char* force = getenv("B200RMSD_GROUP_LANES")) {  // development override
         const int L = atoi(force);
         if (L == 2 || L == 4 || L == 8 || L == 16) {
@@ -541,6 +544,7 @@ bool launch_ovm_group(OvmParams& p, bool precentered, int sm_count, cudaStream_t
             stages = (int)std::min<size_t>(4, per_warp_bytes(w) / (2 * frame_bytes));
         }
     }
+#endif
     if (Lsel == 0) return false;
     p.stages = stages;
     switch (Lsel) {

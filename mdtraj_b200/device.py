@@ -31,12 +31,14 @@ def _stream_ptr(torch, device):
 
 
 class _Scratch:
-    """Grow-only per-device scratch tensor for the _dev entry points."""
+    """Grow-only scratch tensor for the _dev entry points, one per (device, stream): calls issued on different streams
+    may run concurrently and must not share partial-sum buffers."""
     _buf = {}
 
     @classmethod
     def get(cls, torch, device, nbytes):
-        key = (device.index if device.index is not None else torch.cuda.current_device())
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        key = (index, torch.cuda.current_stream(device).cuda_stream)
         buf = cls._buf.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
@@ -246,6 +248,14 @@ class DeviceTrajectory:
                                           prep.stats.data_ptr(), out.data_ptr(), rot.data_ptr(), degen.data_ptr(),
                                           scratch.data_ptr(), scratch.numel(), _stream_ptr(torch, self.device))
         _capi.check(rc, "b200rmsd_superpose_dev")
+        # overflow / underflow guard of trajectory.py:1162-1169 (rotated centred frame 0 all zeros), evaluated after the
+        # re-translation: every atom of frame 0 on one point
+        if F and not bool((self._xyz[0, : self.n_atoms] - self._xyz[0, :1]).any().item()):
+            raise OverflowError(
+                "Encounted a potential overflow/underflow error during superpose() due to the magnitude of your `_xyz`"
+                "coordinates. To circumvent this, (1) reload your trajectory and (2) divide and/or multiply your"
+                "`_xyz` dataset by multiples of 10 before running superpose again. Then, (3) revert that "
+                "multiplication/division after the calculations.")
         self._rmsd_traces = None  # xyz changed (trajectory.py:1029)
         self.last_superpose_rmsd = out
         self.n_degenerate_rotations = degen

@@ -73,13 +73,16 @@ def superpose_host(self, reference, frame=0, atom_indices=None, ref_atom_indices
     ref_frame = np.array(rxyz[frame], dtype=np.float32, order="C", copy=True)  # reference never mutated (:1129)
     degen = _capi.C.c_uint(0)
     if n_frames:
-        rc = _capi.lib().b200rmsd_superpose_host(
+        devs = _rmsd.current_devices()
+        rc = _capi.lib().b200rmsd_superpose_host_multi(
             work.ctypes.data, n_frames, n_atoms, ref_frame.ctypes.data, ref_frame.shape[0], _capi.np_ptr(idx),
             _capi.np_ptr(ridx), 0 if idx is None else len(idx), None, None, _capi.C.byref(degen),
-            _rmsd.current_device())
-        _capi.check(rc, "b200rmsd_superpose_host")
-        # same guard as trajectory.py:1162-1169
-        if not np.any(work[0]):
+            devs.ctypes.data, len(devs))
+        _capi.check(rc, "b200rmsd_superpose_host_multi")
+        # The guard of trajectory.py:1162-1169 fires when the ROTATED, CENTRED first frame is all zeros, i.e. before the
+        # reference centroid is added back (:1171).  The kernel has already re-translated, so the same condition reads:
+        # every atom of frame 0 sits on one point (x' = 0 . R + o).
+        if not np.any(work[0] - work[0, :1]):
             raise OverflowError(
                 "Encounted a potential overflow/underflow error during superpose() due to the magnitude of your `_xyz`"
                 "coordinates. To circumvent this, (1) reload your trajectory and (2) divide and/or multiply your"

@@ -794,3 +794,90 @@ def test_rmsd_matrix_into_host_buffer(mdb):
         assert np.all(np.diag(got) == 0.0)
     with pytest.raises(ValueError):
         mdb.rmsd_matrix(dt, out=np.empty((F, F), dtype=np.float64))
+
+
+# ------------------------------------------------------------------ host pipeline: pageable staging, lanes, several devices
+@pytest.fixture
+def small_chunks(mdb):
+    """1 MB chunks: a few thousand frames already exercise the three-lane pipeline, the finalizer thread and the memcpy
+    pool (default 64 MB)."""
+    mdb.set_host_pipeline(chunk_mb=1, staged_chunk_mb=1)
+    yield
+    mdb.set_host_pipeline(chunk_mb=64, staged_chunk_mb=16)
+
+
+@pytest.mark.parametrize("N", [100, 22, 301])
+def test_host_pipeline_pageable_pinned_and_chunking_agree(mdb, oracle_mod, small_chunks, N):
+    """md.rmsd / superpose / centring on host arrays: pageable input (staged through page-locked lanes by the memcpy
+    pool), page-locked input (DMA'd directly) and a single-chunk run give bit-identical results, for frame sizes with
+    and without padding atoms (N % 4 != 0 takes the row-wise staging copy)."""
+    import torch
+    O = oracle_mod
+    F = 9000 if N > 30 else 40000
+    X = O.synth_md(F, N, seed=70 + N)
+    ref = mdb.Trajectory(X[:3].copy())
+    idx = np.arange(0, N, 3)
+    pinned = torch.empty((F, N, 3), dtype=torch.float32).pin_memory()
+    pinned.copy_(torch.from_numpy(X))
+    got = {}
+    for name, arr in (("pageable", X.copy()), ("pinned", pinned.numpy())):
+        t = mdb.Trajectory.__new__(mdb.Trajectory)
+        t.topology, t._xyz, t._rmsd_traces = None, arr, None
+        got[name] = (mdb.rmsd(t, ref, 1), mdb.rmsd(t, ref, 2, atom_indices=idx))
+    mdb.set_host_pipeline(chunk_mb=1024, staged_chunk_mb=1024)
+    one = mdb.rmsd(mdb.Trajectory(X.copy()), ref, 1)
+    mdb.set_host_pipeline(chunk_mb=1, staged_chunk_mb=1)
+    assert np.array_equal(got["pageable"][0], got["pinned"][0]) and np.array_equal(got["pageable"][0], one)
+    assert np.array_equal(got["pageable"][1], got["pinned"][1])
+    want = O.rmsd(X, X[:3], 1, impl="reference" if O.ref_available() else "port")
+    m = np.arange(F) != 1   # the reference frame against itself: noise floor here, exactly 0 in the reference (same memory)
+    assert_three_way(one[m], want[m], O.truth_rmsd_batch(X, X[1])[m], "host pipeline vs oracle")
+    # in-place operations: superposed coordinates and traces come back through the finalizer
+    a, b = mdb.Trajectory(X.copy()), mdb.Trajectory(pinned.numpy().copy())
+    tp = mdb.Trajectory.__new__(mdb.Trajectory)
+    tp.topology, tp._xyz, tp._rmsd_traces = None, pinned.numpy(), None
+    a.superpose(ref, 0, atom_indices=idx)
+    tp.superpose(ref, 0, atom_indices=idx)
+    mdb.set_host_pipeline(chunk_mb=1024, staged_chunk_mb=1024)
+    b.superpose(ref, 0, atom_indices=idx)
+    mdb.set_host_pipeline(chunk_mb=1, staged_chunk_mb=1)
+    assert np.array_equal(a.xyz, b.xyz) and np.array_equal(a.xyz, tp.xyz)
+    c = mdb.Trajectory(X.copy())
+    c.center_coordinates()
+    Xc = X.copy()
+    tr = O.center_and_trace(Xc, "reference" if O.ref_available() else "port")
+    assert np.abs(c.xyz - Xc).max() <= 2e-6 and np.allclose(c._rmsd_traces, tr, rtol=1e-6)
+
+
+def test_host_pipeline_several_devices(mdb, oracle_mod, small_chunks):
+    """b200rmsd_*_host_multi: chunks handed out dynamically to every visible device from one process; the result does not
+    depend on which device took which chunk.  Needs >= 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    O = oracle_mod
+    X = O.synth_md(30000, 100, seed=91)
+    ref = mdb.Trajectory(X[:1].copy())
+    try:
+        mdb.set_devices([0])
+        one = mdb.rmsd(mdb.Trajectory(X.copy()), ref, 0)
+        s1 = mdb.Trajectory(X.copy()); s1.superpose(ref, 0)
+        mdb.set_devices(list(range(torch.cuda.device_count())))
+        many = mdb.rmsd(mdb.Trajectory(X.copy()), ref, 0)
+        s2 = mdb.Trajectory(X.copy()); s2.superpose(ref, 0)
+    finally:
+        mdb.set_devices(None)
+    assert np.array_equal(one, many) and np.array_equal(s1.xyz, s2.xyz)
+
+
+def test_host_pipeline_error_paths(mdb):
+    """Bad device lists are rejected before anything is launched; a failed call leaves no transfer in flight."""
+    from mdtraj_b200 import _capi
+    L = _capi.lib()
+    X = np.zeros((10, 8, 3), np.float32); out = np.zeros(10, np.float32)
+    for devs in ([99], [0, 0], []):
+        d = np.asarray(devs, np.int32)
+        rc = L.b200rmsd_rmsd_host_multi(X.ctypes.data, 10, 8, X[0].ctypes.data, 8, None, None, 0, 1, 0, None, 0.0,
+                                        out.ctypes.data, d.ctypes.data if len(devs) else None, len(devs))
+        assert rc == _capi.EINVAL or rc == _capi.ENODEVICE, (devs, rc)
+        assert L.b200rmsd_last_error()
