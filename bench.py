@@ -1,23 +1,36 @@
 #!/usr/bin/env python
 """bench.py -- frame-pair RMSDs per second on B200 (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--only NAME] [--no-subs]
 
-A "step" is one pass of the hot path over one batch of synthetic input.  Default workload =
-BASELINE.json configs[1]: one-vs-many md.rmsd, 1,000,000 frames x 1,000 atoms, precentered=False,
-reference = frame 0.  With N > 1 (torchrun, one rank per GPU) every rank owns its own 1M-frame shard
-(frames are independent: no data-path collective, weak scaling) and `value` is the aggregate.
+A "step" is one pass of the hot path over one batch of synthetic input.  The HEADLINE (top-level keys of the JSON line)
+is BASELINE.json configs[1]: one-vs-many md.rmsd, 1,000,000 frames x 1,000 atoms, precentered=False, reference = frame
+0.  With N > 1 (torchrun, one rank per GPU) every rank owns its own 1M-frame shard (frames are independent: no data-path
+collective, weak scaling) and `value` is the aggregate.
 
-  value      device-resident throughput: inputs already in HBM, CUDA-event timed, max over ranks
-  e2e        the same metric through the public API mdb.rmsd(host_traj, ...) with PINNED HOST buffers:
-             H2D of every frame and D2H of the result inside the timed region
-  roofline   dominant kernel (ovm_tma_kernel): algorithmic bytes 12*N per frame / CUDA-event launch time
-  cpu_baseline  the compiled reference (oracle/_ref) on this box's host cores, bounded sample
-  parity     GPU path vs the CPU reference vs the float64 truth on a sample of the same shape (outside the timed region)
+The same line carries, under "sub", one record per remaining BASELINE config, each with its own timed region, roofline,
+end-to-end number, CPU baseline and parity block:
+  superpose      configs[2]  Trajectory.superpose, 200k x 5,000 atoms, every 5th atom aligned        (N = 1 only)
+  allpairs_20k   configs[3]  shape at F = 20,000: all-pairs matrix incl. e2e / parity / CPU baseline   (N = 1 only)
+  allpairs_100k  configs[3]  at full size, 100k x 100k x 300 atoms: ONE GPU at N = 1; at N > 1 the frames are
+                 NCCL-broadcast, row blocks sharded, every unordered block pair computed once and the transposed blocks
+                 exchanged over NVLink (distributed.rmsd_matrix_sharded) -- strong scaling, the one step of the path with
+                 a collective, inside its timed region
+  ovm25k         configs[4]  per-GPU shard: 62,500 frames x 25,000 atoms (weak scaling)
 
---impl reference times the reference's own CPU implementation (oracle/_ref = its C++ sources compiled
-in place + our OpenMP loop shell; falls back to the C port oracle/liboracle.so if _ref was never built).
-Other workloads (superpose, allpairs, ovm25k, ala2) exist for profiling; the driver uses the default.
+  value      device-resident throughput: inputs already in HBM, CUDA-event timed, barrier + synchronize both sides,
+             max over ranks
+  e2e        the same metric through the public API (mdb.rmsd(host Trajectory) etc.) on PAGEABLE numpy input -- what a
+             user of mdtraj holds -- with H2D of every frame and D2H of the result inside the timed region;
+             e2e_pinned: the same with page-locked input
+  roofline   dominant kernel: algorithmic bytes (or issued tensor flops) / CUDA-event launch time, against
+             MEASURED_PEAKS.json (HBM) or a TF32 GEMM measured in this run (tensor)
+  cpu_baseline  the compiled reference (oracle/_ref) on this box's host cores, all of them, bounded sample
+  parity     GPU path vs the CPU reference vs the float64 truth on samples of the same shape (outside the timed region)
+
+--impl reference times the reference's own CPU implementation (oracle/_ref = its C++ sources compiled in place + our
+OpenMP loop shell; the C port oracle/liboracle.so if _ref was never built) with every host thread this process may use,
+on rank 0 only.
 """
 from __future__ import annotations
 
@@ -40,12 +53,14 @@ WORKLOADS = {
     "ovm": (1_000_000, 1000, "one-vs-many md.rmsd: synthetic 1M frames x 1,000 atoms, precentered=False (BASELINE configs[1])"),
     "ovm25k": (62_500, 25_000, "one-vs-many md.rmsd: 62,500 frames x 25,000 atoms per GPU (BASELINE configs[4] per-GPU shard)"),
     "superpose": (200_000, 5000, "Trajectory.superpose: 200k frames x 5,000 atoms, atom_indices=arange(0,5000,5) (BASELINE configs[2])"),
-    "allpairs": (20_000, 300, "all-pairs RMSD matrix: 20k x 20k frames x 300 atoms (BASELINE configs[3] shape, reduced F)"),
+    "allpairs_20k": (20_000, 300, "all-pairs RMSD matrix: 20k x 20k frames x 300 atoms (BASELINE configs[3] shape, reduced F)"),
+    "allpairs_100k": (100_000, 300, "all-pairs RMSD matrix: 100k x 100k frames x 300 atoms (BASELINE configs[3])"),
     "ala2": (100, 22, "md.rmsd 100 frames x 22 atoms (BASELINE configs[0] shape, synthetic)"),
 }
+TOL = "1e-5 nm abs or 1e-4 rel"
 
 
-def peaks():
+def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as fh:
@@ -54,16 +69,13 @@ def peaks():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
-def tf32_peak():
-    """Dense TF32 tensor peak in TFLOP/s.  MEASURED_PEAKS.json carries the cuBLAS bf16 number only; kind::tf32
-    issues at exactly half the kind::f16 rate (K=8 vs K=16 per instruction at the same cycle count), so the
-    measured bf16 burst figure / 2 is used and labelled as such."""
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as fh:
-            p = json.load(fh)
-        return float(p["bf16_tflops"]) / 2.0, "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 = half the bf16 rate; of measured)"
-    return 1590.0 / 2.0, "B200_PROFILING.md fallback 1.59 PFLOP/s bf16 / 2 (of fallback)"
+def ncu_fact(key):
+    """Per-launch facts of the dominant kernels from the committed ncu captures (profiles/ncu_traffic.json)."""
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(tpath):
+        return None
+    with open(tpath) as fh:
+        return json.load(fh).get(key)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -112,18 +124,27 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(workload, steps, warmup, sample_frames=None):
-    """Time the reference CPU path on a bounded sample of `workload`.  Returns (value, info)."""
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(workload, steps, warmup):
+    """Time the reference CPU path on a bounded sample of `workload` with every host thread this process may use
+    (torchrun exports OMP_NUM_THREADS=1 to its ranks: the thread count is set explicitly, like mdtraj's own
+    `parallel=True` default uses all cores, _rmsd.pyx:136-141).  Returns the cpu_baseline record."""
     from oracle import oracle as O
     F_full, N, _ = WORKLOADS[workload]
     kind = "reference" if O.ref_available() else "port"
     threads = 1
     if kind == "reference":
         L = O.ref_lib()
+        L.refloops_set_threads(host_threads())
         threads = int(L.refloops_max_threads())
-    if workload == "allpairs":
-        F = 20_000 if sample_frames is None else sample_frames
-        rows = 8
+    if workload.startswith("allpairs"):
+        F, rows = 20_000, 8
         X = O.synth_iid(F, N, seed=4)
         tr = O.center_and_trace(X, kind)
 
@@ -133,7 +154,7 @@ def cpu_reference_run(workload, steps, warmup, sample_frames=None):
         units = rows * F
         sample = f"{rows} rows of md.rmsd(t,t,i,precentered=True) at F={F}, N={N} after center_coordinates()"
     elif workload == "superpose":
-        F = 2000 if sample_frames is None else sample_frames
+        F = 2000
         X = O.synth_iid(F, N, seed=4)
         idx = np.arange(0, N, 5)
 
@@ -142,8 +163,7 @@ def cpu_reference_run(workload, steps, warmup, sample_frames=None):
         units = F
         sample = f"Trajectory.superpose restated (numpy glue + reference C kernels) on {F} x {N}, 1000-atom subset"
     else:
-        budget_bytes = 1.2e9
-        F = int(min(F_full, max(64, budget_bytes // (N * 12)))) if sample_frames is None else sample_frames
+        F = int(min(F_full, max(64, 1.2e9 // (N * 12))))
         X = O.synth_iid(F, N, seed=4)
 
         def step():
@@ -156,47 +176,43 @@ def cpu_reference_run(workload, steps, warmup, sample_frames=None):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    info = {"value": units / dt, "unit": "rmsd/s", "cores": threads, "kind": kind, "sample": sample,
+    return {"value": units / dt, "unit": "rmsd/s", "cores": threads, "kind": kind, "sample": sample,
             "host_cpus": os.cpu_count(), "ms_per_step": dt * 1e3}
-    return units / dt, info
+
+
+def _verdict(got, ref, truth, what, kind):
+    got, ref, truth = (np.asarray(v, dtype=np.float64) for v in (got, ref, truth))
+    e_gr, e_gt, e_rt = np.abs(got - ref), np.abs(got - truth), np.abs(ref - truth)
+    ok = bool(np.all((e_gr <= np.maximum(1e-5, 1e-4 * np.abs(ref))) | (e_gt <= np.maximum(1e-5, e_rt))))
+    return {"what": what, "n": int(got.size), "max_abs_gpu_vs_ref": float(e_gr.max()), "max_abs_gpu_vs_truth": float(e_gt.max()),
+            "max_abs_ref_vs_truth": float(e_rt.max()), "tolerance": TOL, "checker": kind, "pass": ok}
 
 
 def parity_block(workload, mdb):
-    """GPU path (through the public host API) against the CPU reference and the float64 truth on a sample of the
-    workload's shape (SURVEY.md section 8(d) "parity checks in the bench").  The oracle is the checker here, never the
-    thing measured.  Tolerance: 1e-5 nm absolute or 1e-4 relative (BASELINE.json north_star)."""
+    """GPU path (through the public host API) against the CPU reference and the float64 truth on samples of the
+    workload's shape.  The oracle is the checker here, never the thing measured.  Tolerance:
+    1e-5 nm absolute or 1e-4 relative (BASELINE.json north_star), or at least as close to the truth as the reference."""
     from oracle import oracle as O
     F_full, N, _ = WORKLOADS[workload]
     kind = "reference" if O.ref_available() else "port"
-    tol_abs, tol_rel = 1e-5, 1e-4
-
-    def verdict(got, ref, truth, what, n):
-        got, ref, truth = (np.asarray(v, dtype=np.float64) for v in (got, ref, truth))
-        e_gr, e_gt, e_rt = np.abs(got - ref), np.abs(got - truth), np.abs(ref - truth)
-        ok = bool(np.all((e_gr <= np.maximum(tol_abs, tol_rel * np.abs(ref))) | (e_gt <= np.maximum(tol_abs, e_rt))))
-        return {"what": what, "n": int(n), "max_abs_gpu_vs_ref": float(e_gr.max()), "max_abs_gpu_vs_truth": float(e_gt.max()),
-                "max_abs_ref_vs_truth": float(e_rt.max()), "tolerance": "1e-5 nm abs or 1e-4 rel", "checker": kind,
-                "pass": ok}
-    if workload == "allpairs":
-        # two kinds of frames (SURVEY.md section 8(d)): iid (large RMSD, no cancellation) and MD-like (RMSD 0.25 nm on
-        # Rg 1 nm: G_a + G_b - 2 lambda cancels 30x, which is where the tensor core's truncating accumulation would show)
-        F, rows = 4000, 8
-        out = None
-        for name, X in (("iid", O.synth_iid(F, N, seed=14)), ("MD-like", O.synth_md(F, N, seed=14, rg=1.0, sigma=0.1))):
+    out = {}
+    if workload.startswith("allpairs"):
+        # iid (large RMSD, no cancellation), MD-like (RMSD 0.25 nm on Rg 1 nm: G_a + G_b - 2 lambda cancels 30x, where the
+        # tensor core's truncating accumulation would show) and MD-like in three basins 1.4 nm apart (clustering input:
+        # pairs inside a basin far from frame 0 need the multi-reference operands)
+        F, rows_n = 4000, 9
+        sets = (("iid", O.synth_iid(F, N, seed=14)), ("md_like", O.synth_md(F, N, seed=14, rg=1.0, sigma=0.1)),
+                ("md_like_multibasin", O.synth_md_basins(F, N, 3, seed=15, rg=1.0, sigma=0.1, separation=1.4)[0]))
+        for name, X in sets:
             D = mdb.rmsd_matrix(mdb.Trajectory(X.copy()))
+            rows = np.linspace(0, F - 1, rows_n).astype(int)   # three rows in every third of the trajectory
             Xc = X.copy()
             tr = O.center_and_trace(Xc, kind)
-            ref = np.stack([O.one_vs_many_centered(Xc, tr, Xc[i], tr[i], impl=kind) for i in range(rows)])
-            truth = np.stack([O.truth_rmsd_batch(X, X[i]) for i in range(rows)])
-            m = np.ones((rows, F), bool); m[np.arange(rows), np.arange(rows)] = False  # a frame against itself: noise floor
-            v = verdict(D[:rows][m], ref[m], truth[m], f"{rows} rows of the {F}x{F} matrix, {N} atoms, {name} frames", m.sum())
-            if out is None:
-                out = v
-            else:
-                out["md_like"] = v
-                out["pass"] = bool(out["pass"] and v["pass"])
-        return out
-    if workload == "superpose":
+            ref = np.stack([O.one_vs_many_centered(Xc, tr, Xc[i], tr[i], impl=kind) for i in rows])
+            truth = np.stack([O.truth_rmsd_batch(X, X[i]) for i in rows])
+            m = np.ones((rows_n, F), bool); m[np.arange(rows_n), rows] = False  # a frame against itself: noise floor
+            out[name] = _verdict(D[rows][m], ref[m], truth[m], f"{rows_n} rows of the {F}x{F} matrix, {N} atoms, {name} frames", kind)
+    elif workload == "superpose":
         F = 512
         X = O.synth_md(F, N, seed=14)  # MD-like frames: rotations are well conditioned (SURVEY.md section 8(d))
         idx = np.arange(0, N, 5)
@@ -204,78 +220,385 @@ def parity_block(workload, mdb):
         t.superpose(mdb.Trajectory(X.copy()), 0, atom_indices=idx)
         ref = O.superpose(X, X, 0, idx, impl=kind)
         truth = O.truth_superpose(X, X, 0, idx)[0]
-        return verdict(t.xyz, ref, truth, f"superposed coordinates of {F} MD-like frames x {N} atoms, every 5th atom aligned",
-                       F * N * 3)
-    F = int(min(F_full, max(64, min(10_000, 2.4e8 // (N * 12)))))
-    out = None
-    # iid frames (strict parity is meaningful at every N) and MD-like frames (realistic cancellation; the reference
-    # itself drifts from the float64 truth there, SURVEY.md Appendix C, hence the three-way verdict)
-    for name, X in (("iid", O.synth_iid(F, N, seed=14)), ("MD-like", O.synth_md(F, N, seed=14))):
-        got = mdb.rmsd(mdb.Trajectory(X.copy()), mdb.Trajectory(X.copy()), 0)
-        ref = O.rmsd(X, X, 0, impl=kind)
-        truth = O.truth_rmsd_batch(X, X[0])
-        v = verdict(got[1:], ref[1:], truth[1:], f"md.rmsd(t,t,0) on {F} {name} frames x {N} atoms (frame 0 itself left out)",
-                    F - 1)
-        if out is None:
-            out = v
-        else:
-            out["md_like"] = v
-            out["pass"] = bool(out["pass"] and v["pass"])
+        out["md_like"] = _verdict(t.xyz, ref, truth, f"superposed coordinates of {F} MD-like frames x {N} atoms, every 5th atom aligned", kind)
+    else:
+        F = int(min(F_full, max(64, min(10_000, 2.4e8 // (N * 12)))))
+        # iid frames (strict parity is meaningful at every N) and MD-like frames (realistic cancellation; the reference
+        # itself drifts from the float64 truth there, SURVEY.md Appendix C, hence the three-way verdict)
+        for name, X in (("iid", O.synth_iid(F, N, seed=14)), ("md_like", O.synth_md(F, N, seed=14))):
+            got = mdb.rmsd(mdb.Trajectory(X.copy()), mdb.Trajectory(X.copy()), 0)
+            ref = O.rmsd(X, X, 0, impl=kind)
+            truth = O.truth_rmsd_batch(X, X[0])
+            out[name] = _verdict(got[1:], ref[1:], truth[1:], f"md.rmsd(t,t,0) on {F} {name} frames x {N} atoms (frame 0 itself left out)", kind)
+    out["pass"] = bool(all(v["pass"] for v in out.values()))
     return out
 
 
+def reference_arm(args, config):
+    steps = max(1, min(args.steps, 5))
+    info = cpu_reference_run("ovm", steps, 1)
+    line = {"impl": "reference", "metric": METRIC, "value": info["value"], "unit": "rmsd/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": info,
+            "e2e": {"value": info["value"], "unit": "rmsd/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    if not args.no_subs:
+        sub = {}
+        for w in ("superpose", "allpairs_20k", "ovm25k"):
+            try:
+                c = cpu_reference_run(w, 2, 1)
+                sub[w] = {"value": c["value"], "unit": "rmsd/s", "config": {"workload": WORKLOADS[w][2]}, "cpu_baseline": c}
+            except Exception as e:  # noqa: BLE001
+                sub[w] = {"error": repr(e)}
+        sub["allpairs_100k"] = sub.get("allpairs_20k")
+        line["sub"] = sub
+    print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------------
-def ncu_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture."""
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if not os.path.exists(tpath):
-        return None
-    with open(tpath) as fh:
-        return json.load(fh).get(workload)
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def sync_all(c):
+    c.torch.cuda.synchronize(c.dev)
+    if c.world > 1:
+        c.dist.barrier()
+        c.torch.cuda.synchronize(c.dev)
+
+
+def max_over_ranks(c, x):
+    t = c.torch.tensor([x], dtype=c.torch.float64, device=c.dev)
+    if c.world > 1:
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_region(c, step, steps, warmup):
+    """W untimed steps, barrier + synchronize, exactly K steps between two CUDA events on the launching stream,
+    synchronize + barrier, max over ranks.  step(record) may append (start, stop) event pairs around its dominant kernel."""
+    torch = c.torch
+    events = []
+    for _ in range(warmup):
+        step(None)
+    sync_all(c)
+    sampler = ClockSampler(c.local_rank)
+    sampler.start()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step(events)
+    t1.record()
+    sync_all(c)
+    clocks = sampler.result()
+    ms = max_over_ranks(c, t0.elapsed_time(t1)) / steps
+    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in events) if events else None
+    return ms, kern_ms, clocks
+
+
+def bracket(torch, events):
+    """Context manager recording a CUDA-event pair around the dominant kernel of a step."""
+    class _B:
+        def __enter__(self):
+            if events is not None:
+                self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *a):
+            if events is not None:
+                self.e1.record()
+                events.append((self.e0, self.e1))
+    return _B()
+
+
+def host_traj(mdb, arr):
+    t = mdb.Trajectory.__new__(mdb.Trajectory)
+    t.topology, t._xyz, t._rmsd_traces = None, arr, None   # no copy on the way in
+    return t
+
+
+def e2e_measure(c, fn, units, h2d, d2h, api, steps, memory):
+    """fn() = one call of the public API on host buffers, returning a host scalar read from its result."""
+    fn()
+    sync_all(c)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    c.torch.cuda.synchronize(c.dev)
+    ms = max_over_ranks(c, (time.perf_counter() - t0) * 1e3 / steps)
+    return {"value": units * c.world / (ms * 1e-3), "unit": "rmsd/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": ms, "steps": steps, "api": api, "host_memory": memory, "h2d_GBs_per_gpu": h2d / ms / 1e6}
+
+
+def host_copies(c, dev_xyz, N, pinned):
+    """The device-resident synthetic frames as a host (F,N,3) float32 array: pageable numpy or page-locked."""
+    torch = c.torch
+    F = dev_xyz.shape[0]
+    if pinned:
+        host = torch.empty((F, N, 3), dtype=torch.float32, pin_memory=True)
+    else:
+        host = torch.from_numpy(np.empty((F, N, 3), dtype=np.float32))
+    host.copy_(dev_xyz[:, :N, :])
+    torch.cuda.synchronize(c.dev)
+    return host
+
+
+def run_ovm(c, name, steps, warmup, full):
+    """md.rmsd(traj, traj, 0) on a device-resident shard; e2e through mdb.rmsd(host Trajectory)."""
+    torch, mdb, L, capi = c.torch, c.mdb, c.L, c.capi
+    F, N, desc = WORKLOADS[name]
+    dt = mdb.DeviceTrajectory.synthetic_iid(F, N, seed=1000 * 2 + c.rank, device=c.dev)
+    out = torch.empty(F, dtype=torch.float32, device=c.dev)
+    scratch = torch.empty(int(L.b200rmsd_scratch_bytes(F, N)), dtype=torch.uint8, device=c.dev)
+    ref = torch.empty(dt.n_pad * 3, dtype=torch.float32, device=c.dev)
+    stats = torch.empty(capi.REFSTATS_BYTES, dtype=torch.uint8, device=c.dev)
+    n_seg = 1 if N <= 4096 else -(-((N + 3) // 4) // 1024)
+    launches = 2 + (1 if n_seg > 1 else 0)
+
+    def step(events):
+        # md.rmsd(traj, traj, 0): prepare the reference frame, then the streaming kernel
+        capi.check(L.b200rmsd_prepare_reference_dev(dt.xyz_dev.data_ptr(), None, N, 1, 0.0, ref.data_ptr(), stats.data_ptr(),
+                                                    c.stream), "prepare_reference")
+        with bracket(torch, events):
+            capi.check(L.b200rmsd_rmsd_dev(dt.xyz_dev.data_ptr(), F, N, dt.frame_stride, None, N, ref.data_ptr(),
+                                           stats.data_ptr(), None, 0, out.data_ptr(), None, None, None, scratch.data_ptr(),
+                                           scratch.numel(), c.stream), "rmsd_dev")
+    ms, kern_ms, clocks = timed_region(c, step, steps, warmup)
+    algo = 12.0 * N * F
+    peak, peak_src = hbm_peak()
+    rec = {"metric": METRIC, "value": F * c.world / (ms * 1e-3), "unit": "rmsd/s", "n_gpus": c.world, "steps": steps,
+           "warmup": warmup, "ms_per_step": ms, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+           "config": {"workload": desc, "frames_per_gpu": F, "n_atoms": N, "frame": 0,
+                      "l2_policy": "inputs (%.1f GB per GPU) are larger than the 126 MB L2" % (F * N * 12 / 1e9)},
+           "clocks": clocks, "gpu_launches": launches * steps,
+           "roofline": {"bound": "hbm", "kernel": "ovm_tma_kernel" + (" + ovm_finish_kernel" if n_seg > 1 else ""),
+                        "achieved": algo / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": algo / (kern_ms * 1e-3) / 1e9 / peak, "traffic": ncu_fact(name), "peak_source": peak_src,
+                        "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo}}
+    if full:
+        e2e_steps = 3
+        for memory, pinned in (("pageable", False), ("pinned", True)):
+            if pinned and (c.world > 1 or name != "ovm"):
+                continue
+            host = host_copies(c, dt.xyz_dev, N, pinned)
+            ht = host_traj(mdb, host.numpy())
+            ref_host = mdb.Trajectory(host.numpy()[:1].copy())
+            rec["e2e" if not pinned else "e2e_pinned"] = e2e_measure(
+                c, lambda: float(mdb.rmsd(ht, ref_host, 0)[-1]), F, F * N * 12 + N * 12, F * 4,
+                "mdtraj_b200.rmsd(host Trajectory) -> b200rmsd_rmsd_host_multi", e2e_steps, memory)
+            del host, ht
+    del dt, out, scratch
+    torch.cuda.empty_cache()
+    if full and c.rank == 0 and c.world == 1:
+        rec["cpu_baseline"] = _try(lambda: cpu_reference_run(name, 3, 1))
+        rec["parity"] = _try(lambda: parity_block(name, mdb))
+    return rec
+
+
+def run_superpose(c, steps, warmup, full):
+    torch, mdb, L, capi = c.torch, c.mdb, c.L, c.capi
+    F, N, desc = WORKLOADS["superpose"]
+    dt = mdb.DeviceTrajectory.synthetic_iid(F, N, seed=3000 + c.rank, device=c.dev)
+    idx_np = np.arange(0, N, 5, dtype=np.int32)
+    idx = torch.from_numpy(idx_np).to(c.dev)
+    out = torch.empty(F, dtype=torch.float32, device=c.dev)
+    rot = torch.empty((F, 9), dtype=torch.float32, device=c.dev)
+    scratch = torch.empty(int(L.b200rmsd_scratch_bytes(F, N)), dtype=torch.uint8, device=c.dev)
+    ref = torch.empty(((len(idx_np) + 3) // 4 * 4) * 3, dtype=torch.float32, device=c.dev)
+    stats = torch.empty(capi.REFSTATS_BYTES, dtype=torch.uint8, device=c.dev)
+    ref_frame = dt.xyz_dev[0].clone()
+
+    def step(events):
+        capi.check(L.b200rmsd_prepare_reference_dev(ref_frame.data_ptr(), idx.data_ptr(), len(idx_np), 1, 0.0, ref.data_ptr(),
+                                                    stats.data_ptr(), c.stream), "prepare_reference")
+        with bracket(torch, events):
+            capi.check(L.b200rmsd_superpose_dev(dt.xyz_dev.data_ptr(), F, N, dt.frame_stride, idx.data_ptr(), len(idx_np),
+                                                ref.data_ptr(), stats.data_ptr(), out.data_ptr(), rot.data_ptr(), None,
+                                                scratch.data_ptr(), scratch.numel(), c.stream), "superpose_dev")
+    ms, kern_ms, clocks = timed_region(c, step, steps, warmup)
+    algo = 24.0 * N * F
+    peak, peak_src = hbm_peak()
+    rec = {"metric": "frames superposed/sec", "value": F * c.world / (ms * 1e-3), "unit": "frames/s", "n_gpus": c.world,
+           "steps": steps, "warmup": warmup, "ms_per_step": ms, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+           "config": {"workload": desc, "frames_per_gpu": F, "n_atoms": N, "n_aligned": len(idx_np), "frame": 0,
+                      "l2_policy": "inputs (%.1f GB per GPU) are larger than the 126 MB L2" % (F * N * 12 / 1e9)},
+           "clocks": clocks, "gpu_launches": 2 * steps,
+           "roofline": {"bound": "hbm", "kernel": "frame_resident_kernel<OP_SUPERPOSE>", "achieved": algo / (kern_ms * 1e-3) / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": algo / (kern_ms * 1e-3) / 1e9 / peak,
+                        "traffic": ncu_fact("superpose"), "peak_source": peak_src, "kernel_ms": kern_ms,
+                        "algorithmic_bytes_per_launch": algo}}
+    if full:
+        idx_host = np.arange(0, N, 5)
+        for memory, pinned in (("pageable", False), ("pinned", True)):
+            host = host_copies(c, dt.xyz_dev, N, pinned)
+            ht = host_traj(mdb, host.numpy())
+            ref_host = mdb.Trajectory(host.numpy()[:1].copy())
+
+            def call():
+                ht.superpose(ref_host, 0, atom_indices=idx_host)
+                return float(ht.xyz[0, 0, 0])
+            r = e2e_measure(c, call, F, F * N * 12 + N * 12, F * N * 12, "Trajectory.superpose -> b200rmsd_superpose_host_multi",
+                            2, memory)
+            r["unit"] = "frames/s"
+            rec["e2e" if not pinned else "e2e_pinned"] = r
+            del host, ht
+    del dt, out, rot, scratch
+    torch.cuda.empty_cache()
+    if full and c.rank == 0:
+        rec["cpu_baseline"] = _try(lambda: cpu_reference_run("superpose", 2, 1))
+        rec["parity"] = _try(lambda: parity_block("superpose", mdb))
+    return rec
+
+
+def measure_tf32_peak(c):
+    """Dense TF32 GEMM throughput of this GPU, measured the way MEASURED_PEAKS.json measures bf16: torch.matmul 8192^3
+    (cuBLAS, allow_tf32), best of 10 (burst) and back to back for ~1.5 s (sustained).  cuBLAS is the yardstick only."""
+    torch = c.torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn((n, n), device=c.dev); b = torch.randn((n, n), device=c.dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(c.dev)
+        best = 1e9
+        for _ in range(10):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize(c.dev)
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(1500 / best))
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record(); torch.cuda.synchronize(c.dev)
+        sustained = e0.elapsed_time(e1) / reps
+        flop = 2.0 * n ** 3
+        return {"burst_tflops": flop / best / 1e9, "sustained_tflops": flop / sustained / 1e9,
+                "how": "torch.matmul fp32 inputs with allow_tf32 (cuBLAS TF32), 8192^3, best of 10 / back to back %d" % reps}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def allpairs_tiles(c, F):
+    """Tiles (40 x 48 frames) a single-GPU full-matrix launch computes: each unordered pair once (host-side walk)."""
+    import ctypes
+    hook = ctypes.CDLL(c.capi.LIB_PATH).b200rmsd_debug_allpairs_tiles
+    hook.restype = ctypes.c_longlong
+    hook.argtypes = [ctypes.c_longlong] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
+    return int(hook(0, F, 0, F, 0, None, 0, None))
+
+
+def run_allpairs(c, name, steps, warmup, full, tf32):
+    """All-pairs matrix of F frames: one GPU computes it whole (each unordered pair once, mirrored); several GPUs shard
+    row blocks after an NCCL broadcast of the frames and exchange transposed blocks (strong scaling)."""
+    torch, mdb = c.torch, c.mdb
+    from mdtraj_b200 import allpairs as AP
+    from mdtraj_b200 import distributed as DD
+    F, N, desc = WORKLOADS[name]
+    dt = mdb.DeviceTrajectory.synthetic_iid(F, N, seed=2000, device=c.dev)   # the same frames on every rank
+    r0, r1 = DD.shard_bounds(F, c.rank, c.world)
+    out = torch.empty((r1 - r0, F), dtype=torch.float32, device=c.dev) if c.world == 1 else None
+    state = {}
+
+    def step(events):
+        with bracket(torch, events):
+            if c.world == 1:
+                prep = AP.prepare(dt, None)
+                AP.rows(prep, 0, F, out=out)
+            else:  # frames broadcast from rank 0 over NCCL, symmetric block plan, transposed blocks exchanged
+                _, _, blk = DD.rmsd_matrix_sharded(dt, None, broadcast=True, symmetric=True)
+                state["blk"] = blk
+    ms, kern_ms, clocks = timed_region(c, step, steps, warmup)
+    tiles = allpairs_tiles(c, F)
+    kpad = (N + 31) // 32 * 32
+    # per GPU: every unordered pair of row blocks is computed on exactly one rank; iid frames walk no augmentation K blocks
+    issued = tiles / c.world * 128 * 144 * kpad * 2 * 3 / (ms * 1e-3) / 1e12
+    rec = {"metric": METRIC, "value": float(F) * F / (ms * 1e-3), "unit": "rmsd/s", "n_gpus": c.world, "steps": steps,
+           "warmup": warmup, "ms_per_step": ms, "scaling": "strong", "dtype": "tf32x3 products, f32 accumulate, f64 solve",
+           "data": "synthetic",
+           "config": {"workload": desc, "frames_total": F, "n_atoms": N,
+                      "parallelism": "1 GPU" if c.world == 1 else
+                      "frames NCCL-broadcast, %d row blocks, symmetric block plan, transposed blocks sent over NVLink" % c.world,
+                      "l2_policy": "the %.1f GB of matrix written per GPU and step flushes the 126 MB L2 between steps; the "
+                                   "operands (%.2f GB) are meant to stay L2-resident inside a step" % (
+                                       F * F * 4 / 1e9 / c.world, F * kpad * 3 * 4 * 4 / 1e9)},
+           "clocks": clocks, "gpu_launches": 15 * steps if c.world == 1 else None,
+           "roofline": {"bound": "tensor", "kernel": "allpairs_tc144_kernel", "achieved": issued,
+                        "peak": tf32["burst_tflops"], "unit": "TFLOP/s", "frac": issued / tf32["burst_tflops"],
+                        "frac_of_sustained": issued / tf32["sustained_tflops"], "peak_source": "measured in this run: " + tf32["how"],
+                        "tensor_pipe_active_pct_ncu": ncu_fact("allpairs_tensor_pipe_active_pct"),
+                        "traffic": ncu_fact("allpairs"), "step_ms": ms, "useful_tflops": float(F) * F * 18 * N / (ms * 1e-3) / 1e12,
+                        "tiles_per_matrix": tiles, "mma_shape": [128, 144, 8], "per": "GPU",
+                        "note": "achieved = tensor flops issued (3 tf32 MMAs per K-step over the tiles computed, each unordered "
+                                "pair once) / whole step time incl. reference selection, operand preparation and, at N > 1, "
+                                "broadcast + exchange; useful = 18 A flops per reported pair"}}
+    if c.world == 1:
+        info = AP.prepare(dt, None).info()
+        rec["config"]["references_chosen"] = info["n_refs"]
+    if full and c.world == 1:
+        host = host_copies(c, dt.xyz_dev, N, False)
+        ht = host_traj(mdb, host.numpy())
+        host_out = torch.empty((F, F), dtype=torch.float32, pin_memory=True)
+
+        def call():
+            mdb.rmsd_matrix(ht, out=host_out.numpy())  # row blocks, copies overlapped with compute
+            return float(host_out[0, 1])
+        rec["e2e"] = e2e_measure(c, call, float(F) * F, F * N * 12, F * F * 4,
+                                 "mdtraj_b200.rmsd_matrix(host Trajectory, out=page-locked ndarray)", 2, "pageable in, page-locked out")
+        # MD-like frames in three basins: the input clustering sees (references are chosen, augmentation blocks walked)
+        from oracle import oracle as O
+        Xb = O.synth_md_basins(F, N, 3, seed=77, rg=1.0, sigma=0.1, separation=1.4)[0]
+        db = mdb.DeviceTrajectory.from_host(Xb, device=c.dev)
+
+        def step_b(events):
+            prep = AP.prepare(db, None)
+            AP.rows(prep, 0, F, out=out)
+        ms_b, _, _ = timed_region(c, step_b, max(3, steps // 2), 2)
+        rec["md_like_multibasin"] = {"value": float(F) * F / (ms_b * 1e-3), "unit": "rmsd/s", "ms_per_step": ms_b,
+                                     "info": AP.prepare(db, None).info()}
+        del host, ht, host_out, db
+    del dt, out
+    state.clear()
+    torch.cuda.empty_cache()
+    if full and c.rank == 0 and c.world == 1:
+        rec["cpu_baseline"] = _try(lambda: cpu_reference_run(name, 2, 1))
+        rec["parity"] = _try(lambda: parity_block(name, mdb))
+    return rec
+
+
+def _try(fn):
+    try:
+        return fn()
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ovm", choices=sorted(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=None, help="override frames per GPU (development)")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only", default=None, choices=sorted(WORKLOADS), help="development: run one workload as the headline")
+    ap.add_argument("--no-subs", action="store_true", help="headline only")
+    ap.add_argument("--no-e2e", action="store_true", help="development: device-resident numbers only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    F, N, desc = WORKLOADS[args.workload]
-    if args.frames:
-        F = args.frames
-        if args.workload == "allpairs":
-            desc = ("all-pairs RMSD matrix: %dk x %dk frames x %d atoms (BASELINE configs[3]%s)"
-                    % (F // 1000, F // 1000, N, "" if F == 100_000 else " shape, F overridden"))
-    config = {"workload": desc, ("frames_total" if args.workload == "allpairs" else "frames_per_gpu"): F, "n_atoms": N,
-              "frame": 0,
-              "l2_policy": ("the %.1f GB matrix written by every step flushes the 126 MB L2 between steps; the operands "
-                            "(%.2f GB) are meant to stay L2-resident inside a step" % (F * F * 4 / 1e9 / max(world, 1),
-                                                                                       F * N * 12 / 1e9))
-              if args.workload == "allpairs" else
-              "inputs (%.1f GB per GPU) are larger than the 126 MB L2" % (F * N * 12 / 1e9)}
+    F, N, desc = WORKLOADS["ovm"]
+    config = {"workload": desc, "frames_per_gpu": F, "n_atoms": N, "frame": 0,
+              "l2_policy": "inputs (%.1f GB per GPU) are larger than the 126 MB L2" % (F * N * 12 / 1e9)}
 
-    # ---------------- reference arm: CPU only, rank 0 only
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        val, info = cpu_reference_run(args.workload, max(1, min(args.steps, 5)), 1)
-        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rmsd/s", "n_gpus": args.gpus,
-                "steps": max(1, min(args.steps, 5)), "warmup": 1, "ms_per_step": info["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config, "cpu_baseline": info,
-                "e2e": {"value": val, "unit": "rmsd/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
+    if args.impl == "reference":   # CPU only, rank 0 only
+        if rank == 0:
+            reference_arm(args, config)
         return
 
     import torch
@@ -283,240 +606,50 @@ def main():
 
     import mdtraj_b200 as mdb
     from mdtraj_b200 import _capi
-    from mdtraj_b200.device import _Scratch, _stream_ptr
+    from mdtraj_b200.device import _stream_ptr
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; mdtraj_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    c = Ctx()
+    c.torch, c.dist, c.mdb, c.capi, c.L = torch, dist, mdb, _capi, _capi.lib()
+    c.rank, c.world, c.local_rank = rank, world, local_rank
+    c.dev = torch.device("cuda", local_rank)
+    c.stream = _stream_ptr(torch, c.dev)
     mdb.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=c.dev)
+        mdb.set_host_pipeline(copy_threads=max(2, host_threads() // world - 1))   # the ranks share the host's cores
 
-    L = _capi.lib()
-    stream = _stream_ptr(torch, dev)
-    dt = mdb.DeviceTrajectory.synthetic_iid(F, N, seed=1000 * 2 + rank, device=dev)
-    launches_per_step = 0
-    kernel_events = []
-
-    if args.workload in ("ovm", "ovm25k", "ala2"):
-        out = torch.empty(F, dtype=torch.float32, device=dev)
-        scratch = _Scratch.get(torch, dev, L.b200rmsd_scratch_bytes(F, N))
-        ref = torch.empty(dt.n_pad * 3, dtype=torch.float32, device=dev)
-        stats = torch.empty(_capi.REFSTATS_BYTES, dtype=torch.uint8, device=dev)
-        n_seg = 1 if N <= 4096 else -(-((N + 3) // 4) // 1024)
-        launches_per_step = 2 + (1 if n_seg > 1 else 0)
-
-        def step(record=False):
-            # md.rmsd(traj, traj, 0): prepare the reference frame, then the streaming kernel
-            _capi.check(L.b200rmsd_prepare_reference_dev(dt.xyz_dev.data_ptr(), None, N, 1, 0.0, ref.data_ptr(),
-                                                         stats.data_ptr(), stream), "prepare_reference")
-            if record:
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-            _capi.check(L.b200rmsd_rmsd_dev(dt.xyz_dev.data_ptr(), F, N, dt.frame_stride, None, N, ref.data_ptr(),
-                                            stats.data_ptr(), None, 0, out.data_ptr(), None, None, None,
-                                            scratch.data_ptr(), scratch.numel(), stream), "rmsd_dev")
-            if record:
-                e1.record()
-                kernel_events.append((e0, e1))
-        units_per_step = F
-        algo_bytes = 12.0 * N * F
-        dominant = "ovm_tma_kernel"
-    elif args.workload == "superpose":
-        idx_np = np.arange(0, N, 5, dtype=np.int32)
-        idx = torch.from_numpy(idx_np).to(dev)
-        out = torch.empty(F, dtype=torch.float32, device=dev)
-        rot = torch.empty((F, 9), dtype=torch.float32, device=dev)
-        scratch = _Scratch.get(torch, dev, L.b200rmsd_scratch_bytes(F, N))
-        ref = torch.empty(((len(idx_np) + 3) // 4 * 4) * 3, dtype=torch.float32, device=dev)
-        stats = torch.empty(_capi.REFSTATS_BYTES, dtype=torch.uint8, device=dev)
-        ref_frame = dt.xyz_dev[0].clone()
-        launches_per_step = 3
-
-        def step(record=False):
-            _capi.check(L.b200rmsd_prepare_reference_dev(ref_frame.data_ptr(), idx.data_ptr(), len(idx_np), 1, 0.0,
-                                                         ref.data_ptr(), stats.data_ptr(), stream), "prepare_reference")
-            if record:
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-            _capi.check(L.b200rmsd_superpose_dev(dt.xyz_dev.data_ptr(), F, N, dt.frame_stride, idx.data_ptr(),
-                                                 len(idx_np), ref.data_ptr(), stats.data_ptr(), out.data_ptr(),
-                                                 rot.data_ptr(), None, scratch.data_ptr(), scratch.numel(), stream),
-                        "superpose_dev")
-            if record:
-                e1.record()
-                kernel_events.append((e0, e1))
-        units_per_step = F
-        algo_bytes = 24.0 * N * F
-        dominant = "frame_resident_kernel"
-    else:  # allpairs
-        from mdtraj_b200 import allpairs as AP
-        rows_per_rank = F // world
-        r0 = rank * rows_per_rank
-        r1 = F if rank == world - 1 else r0 + rows_per_rank
-        out = torch.empty((r1 - r0, F), dtype=torch.float32, device=dev)
-        launches_per_step = 2
-
-        from mdtraj_b200 import distributed as DD
-
-        def step(record=False):
-            if record:
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-            if world == 1:
-                prep = AP.prepare(dt, None)
-                AP.rows(prep, r0, r1, out=out)
-            else:  # frames broadcast from rank 0 over NCCL, symmetric block plan, transposed blocks exchanged
-                DD.rmsd_matrix_sharded(dt, None, broadcast=True, symmetric=True)
-            if record:
-                e1.record()
-                kernel_events.append((e0, e1))
-        units_per_step = (r1 - r0) * F
-        algo_bytes = None
-        dominant = "allpairs_tc144_kernel"
-
-    def sync_all():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
-
-    for _ in range(args.warmup):
-        step()
-    sync_all()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    t_start = torch.cuda.Event(enable_timing=True); t_stop = torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for _ in range(args.steps):
-        step(record=True)
-    t_stop.record()
-    sync_all()
-    clocks = sampler.result()
-    elapsed_ms = t_start.elapsed_time(t_stop)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
-    total_units = units_per_step * world
-    value = total_units / (ms_per_step * 1e-3)
-    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in kernel_events)
-
-    # ---------------- end-to-end through the public API with pinned host buffers
-    e2e = None
-    if not args.no_e2e:
-        host = torch.empty((F, N, 3), dtype=torch.float32, pin_memory=True)
-        host.copy_(dt.xyz_dev[:, :N, :])
-        torch.cuda.synchronize(dev)
-        ht = mdb.Trajectory.__new__(mdb.Trajectory)
-        ht.topology = None
-        ht._xyz = host.numpy()  # pinned, C-contiguous float32: no copy is made on the way in
-        ht._rmsd_traces = None
-        ref_host = mdb.Trajectory(host.numpy()[:1].copy())
-        e2e_steps = max(2, min(args.steps, 4))
-        if args.workload == "superpose":
-            idx_host = np.arange(0, N, 5)
-
-            def e2e_step():
-                ht.superpose(ref_host, 0, atom_indices=idx_host)
-                return float(ht.xyz[0, 0, 0])
-            h2d = F * N * 12 + N * 12
-            d2h = F * N * 12
-        elif args.workload == "allpairs":
-            # host frames in, this rank's rows of the matrix out to page-locked host memory
-            host_out = torch.empty((r1 - r0, F), dtype=torch.float32, pin_memory=True)
-
-            def e2e_step():
-                if world == 1:
-                    mdb.rmsd_matrix(ht, out=host_out.numpy())  # row blocks, copies overlapped with compute
-                else:
-                    dte = mdb.DeviceTrajectory.from_host(ht.xyz, dev) if rank == 0 else \
-                        mdb.DeviceTrajectory(torch.zeros_like(dt.xyz_dev), N)
-                    _, _, blk = DD.rmsd_matrix_sharded(dte, None, broadcast=True, symmetric=True)
-                    host_out.copy_(blk)
-                return float(host_out[0, 1])
-            h2d = F * N * 12
-            d2h = (r1 - r0) * F * 4
+    full = not args.no_e2e
+    sub_steps = max(3, min(args.steps, 10))
+    if args.only:
+        if args.only.startswith("allpairs"):
+            line = run_allpairs(c, args.only, args.steps, args.warmup, full, measure_tf32_peak(c))
+        elif args.only == "superpose":
+            line = run_superpose(c, args.steps, args.warmup, full)
         else:
-            def e2e_step():
-                return float(mdb.rmsd(ht, ref_host, 0)[-1])
-            h2d = F * N * 12 + N * 12
-            d2h = F * 4
-        e2e_step()
-        sync_all()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize(dev)
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_ms = float(te.item())
-        e2e = {"value": units_per_step * world / (e2e_ms * 1e-3), "unit": "rmsd/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
-               "api": {"superpose": "Trajectory.superpose -> b200rmsd_superpose_host",
-                       "allpairs": "mdtraj_b200.rmsd_matrix(host Trajectory, out=page-locked ndarray)"}.get(
-                           args.workload, "mdtraj_b200.rmsd(host Trajectory) -> b200rmsd_rmsd_host"),
-               "h2d_GBs": h2d / e2e_ms / 1e6}
-        del host
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peak, peak_src = peaks()
-    roofline = None
-    if algo_bytes is not None:
-        achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
-        traffic = ncu_traffic(args.workload)
-        roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes}
-
-    if args.workload == "allpairs":
-        tpeak, tsrc = tf32_peak()
-        kpad = (N + 31) // 32 * 32
-        pairs_per_s = units_per_step / (kern_ms * 1e-3)
-        # flops actually issued: three tf32 MMAs per K-step over the tiles the kernel computes, K padded to 32; a
-        # single-rank full matrix computes each unordered pair once (tiles holding no pair j >= i are skipped)
-        import ctypes
-        from mdtraj_b200 import _capi
-        hook = ctypes.CDLL(_capi.LIB_PATH).b200rmsd_debug_allpairs_tiles   # host-only: walks the kernel's tile order
-        hook.restype = ctypes.c_longlong
-        hook.argtypes = [ctypes.c_longlong] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
-        tiles, mma_n = int(hook(0, F, 0, F, 0, None, 0, None)), 144      # 128x144 tiles = 40x48 frames
-        kpad = (((N + 7) // 8 * 8) + 6 + 31) // 32 * 32                   # atoms + 6 augmentation columns, padded to 32
-        if world > 1:
-            tiles = tiles / world  # symmetric block plan: every unordered pair of row blocks on exactly one rank
-        issued = tiles * 128 * mma_n * kpad * 2 * 3 / (kern_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": dominant, "achieved": issued, "peak": tpeak, "unit": "TFLOP/s",
-                    "frac": issued / tpeak, "traffic": ncu_traffic("allpairs"), "peak_source": tsrc, "kernel_ms": kern_ms,
-                    "useful_tflops": pairs_per_s * 18 * N / 1e12,
-                    "tiles_per_launch": tiles, "mma_shape": [128, mma_n, 8],
-                    "note": "achieved = tensor flops actually issued (3 tf32 MMAs per K-step over the computed "
-                            "tiles; symmetric tiles computed once); useful = 18 * A flops per reported pair"}
-
-    cpu = None
-    parity = None
-    if not args.no_cpu and args.gpus == 1:
-        try:
-            _, cpu = cpu_reference_run(args.workload, 3, 1)
-        except Exception as e:  # noqa: BLE001
-            cpu = {"error": repr(e)}
-        try:
-            parity = parity_block(args.workload, mdb)
-        except Exception as e:  # noqa: BLE001
-            parity = {"error": repr(e)}
-
-    line = {"metric": METRIC, "value": value, "unit": "rmsd/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
-    print(json.dumps(line))
+            line = run_ovm(c, args.only, args.steps, args.warmup, full)
+        line["higher_is_better"] = True
+        line["vs_baseline"] = None
+    else:
+        line = run_ovm(c, "ovm", args.steps, args.warmup, full)
+        line["higher_is_better"] = True
+        line["vs_baseline"] = None
+        if not args.no_subs:
+            tf32 = measure_tf32_peak(c)
+            sub = {}
+            if world == 1:
+                sub["superpose"] = _try(lambda: run_superpose(c, sub_steps, 3, full))
+                sub["allpairs_20k"] = _try(lambda: run_allpairs(c, "allpairs_20k", sub_steps, 3, full, tf32))
+            sub["allpairs_100k"] = _try(lambda: run_allpairs(c, "allpairs_100k", 3, 3, False, tf32))
+            sub["ovm25k"] = _try(lambda: run_ovm(c, "ovm25k", sub_steps, 3, full and world == 1))
+            line["sub"] = sub
+            line["tf32_peak"] = tf32
+            line["gpu_launches"] = int(line["gpu_launches"] + sum((s.get("gpu_launches") or 0) for s in sub.values()
+                                                                  if isinstance(s, dict)))
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -90,7 +90,7 @@ void configure_tma(OvmParams& p)
     p.seg_units = (p.total_units + p.n_seg - 1) / p.n_seg;
     const size_t budget = 232448;  // 227 KB opt-in shared memory per CTA
     const size_t ref_bytes = ((size_t)p.seg_units * 48 + 127) / 128 * 128;
-    const size_t fixed = (size_t)kWarpsPerCta * kBatch * kSumStride * sizeof(float) + 2048;
+    const size_t fixed = (size_t)kWarpsPerCta * kBatch * kSumStride * sizeof(double) + 2048;
     const size_t per_warp = (budget - ref_bytes - fixed) / kWarpsPerCta;
     int chunk = std::min(p.seg_units, env_int("B200RMSD_CHUNK_UNITS", 64));
     int stages = (int)std::min<size_t>(8, per_warp / ((size_t)chunk * 48));
@@ -147,7 +147,7 @@ size_t b200rmsd_scratch_bytes(int64_t n_frames, int n_atoms)
     OvmParams p{};
     p.n_atoms = n_atoms;
     configure_tma(p);
-    size_t partial = p.n_seg > 1 ? (size_t)n_frames * p.n_seg * 16 * sizeof(float) : 0;
+    size_t partial = p.n_seg > 1 ? (size_t)n_frames * p.n_seg * 16 * sizeof(double) : 0;
     size_t rot = (size_t)n_frames * 9 * sizeof(float);
     size_t cen = (size_t)n_frames * 3 * sizeof(double);
     return align256(partial) + align256(rot) + align256(cen) + 256;
@@ -240,10 +240,10 @@ int b200rmsd_rmsd_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t f
         configure_tma(p);
         if (p.stages < 2) return fail(B200RMSD_EINVAL, "rmsd: could not fit a shared-memory ring for n_atoms=%d", n_atoms);
         if (p.n_seg > 1) {
-            const size_t need = (size_t)n_frames * p.n_seg * 16 * sizeof(float);
+            const size_t need = (size_t)n_frames * p.n_seg * 16 * sizeof(double);
             if (!scratch || scratch_bytes < need || !aligned16(scratch))
                 return fail(B200RMSD_EINVAL, "rmsd: n_atoms=%d needs %zu bytes of 16-byte aligned scratch", n_atoms, need);
-            p.partials = (float*)scratch;
+            p.partials = (double*)scratch;
         }
         CU(launch_ovm_tma(p, pre, sm, (cudaStream_t)stream));
     } else {
@@ -279,7 +279,7 @@ int b200rmsd_superpose_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t fr
     cfg.n_atoms = n_atoms;
     configure_tma(cfg);
     char* base = (char*)scratch;
-    const size_t partial = cfg.n_seg > 1 ? align256((size_t)n_frames * cfg.n_seg * 16 * sizeof(float)) : 0;
+    const size_t partial = cfg.n_seg > 1 ? align256((size_t)n_frames * cfg.n_seg * 16 * sizeof(double)) : 0;
     float* rot = out_rot ? out_rot : (float*)(base + partial);
     double* cen = (double*)(base + partial + align256((size_t)n_frames * 9 * sizeof(float)));
     // rmsd output is mandatory for the kernel; park it at the head of the centroid block's tail if not wanted

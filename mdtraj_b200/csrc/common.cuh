@@ -224,6 +224,75 @@ __device__ __forceinline__ int group_reduce_scatter16(float (&v)[16], int lane)
     return base;
 }
 
+// ---- the same reduction with the LAST stages in float64 -------------------------------------------------------------
+// What the float32 butterfly above loses is the rounding of sums whose magnitude is the whole frame's (ulp(1e4) = 1e-3
+// against N msd ~ 30): the first two stages add 2 and 4 lane partials (small, float32 is enough, and they carry 12 of
+// the 16 exchanges), the last stages add the big numbers and run in float64: 20 SHFL + 12 FADD + 4 DADD instead of
+// 16 SHFL + 16 FADD.  The streaming kernels call it once per 1024 atoms (8 units per lane) and add the results in
+// float64, so no float32 number ever holds more than 32 atoms' worth of a sum (numpy emulation of the variants:
+// DESIGN.md section 4 -- all-float64 stages gain nothing more).
+// On return the value of index (lane >> 1), summed over all 32 lanes.
+__device__ __forceinline__ double warp_reduce_scatter16_mixed(float (&v)[16], int lane)
+{
+    const unsigned full = 0xffffffffu;
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float send = up ? v[j] : v[j + 8];
+            const float keep = up ? v[j + 8] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float send = up ? v[j] : v[j + 4];
+            const float keep = up ? v[j + 4] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, 8);
+        }
+    }
+    double d0, d1;
+    {
+        const bool up = lane & 4;
+        const float s0 = up ? v[0] : v[2], k0 = up ? v[2] : v[0];
+        const float s1 = up ? v[1] : v[3], k1 = up ? v[3] : v[1];
+        d0 = (double)k0 + (double)__shfl_xor_sync(full, s0, 4);   // the exchange itself still moves floats
+        d1 = (double)k1 + (double)__shfl_xor_sync(full, s1, 4);
+    }
+    {
+        const bool up = lane & 2;
+        const double send = up ? d0 : d1;
+        const double keep = up ? d1 : d0;
+        d0 = keep + __shfl_xor_sync(full, send, 2);
+    }
+    return d0 + __shfl_xor_sync(full, d0, 1);
+}
+
+// acc_unit with the mean-square shift: every atom's |x - p|^2 enters the running sum minus a constant c (the same for
+// all frames: the reference's mean-square radius), so that the float32 lane partial of sum |x - p|^2 -- all terms
+// positive, by far the largest of the 13 sums -- stays fluctuation-sized instead of growing linearly; the epilogue adds
+// c * n_atoms back in float64.  One FADD per 4 atoms.
+template <bool PRE>
+__device__ __forceinline__ void acc_unit_shift(float (&v)[16], const float4& a0, const float4& a1, const float4& a2,
+                                               const float4& b0, const float4& b1, const float4& b2, float px, float py,
+                                               float pz, int nvalid, float c)
+{
+    acc_unit<PRE>(v, a0, a1, a2, b0, b1, b2, px, py, pz, nvalid);
+    if (!PRE) v[3] = fmaf(-c, nvalid >= 4 ? 4.0f : (float)nvalid, v[3]);
+}
+
+// Mean of one value per lane over the lanes of `mask` (n of them), bit-identical on all of them, in 5 instructions
+// instead of a log2(n)-stage shuffle butterfly: fixed point (2^-7 nm) through the integer REDUX unit.  Only used for the
+// accumulation pivot, which may be ANY finite number near the centroid as long as every lane uses the same one (it is
+// carried along exactly and added back in float64); out-of-range coordinates (> 5e5 nm) merely give a poor pivot.
+__device__ __forceinline__ float lanes_mean_fixed(float x, unsigned mask, float inv_n)
+{
+    const int q = __float2int_rn(x * 128.0f);  // saturating
+    return (float)__reduce_add_sync(mask, q) * (inv_n * 0.0078125f);
+}
+
 __device__ __forceinline__ double warp_sum(double x)
 {
 #pragma unroll

@@ -9,8 +9,9 @@ constexpr int kWarpsPerCta = 16;               // streaming kernels: 512 threads
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 constexpr int kBatch = 16;                     // frames solved together (one lane each) per warp
 constexpr int kSumStride = 17;                 // padded stride of a 16-value sum record in smem
+constexpr int kFlushUnits = 8;                 // 4-atom units a lane accumulates in float32 before the float64 fold
 constexpr int kUnitFloats = 12;                // one "unit" = 4 atoms = 48 bytes = 3 x float4
-constexpr int kMaxSegUnits = 1024;             // reference segment resident in smem: <= 4096 atoms (48 KB)
+constexpr int kMaxSegUnits = 768;              // reference segment resident in smem: <= 3072 atoms (36 KB): >= 3 ring stages
 
 // reference-frame statistics written by prepare_ref_kernel (device memory)
 struct RefStats {
@@ -39,7 +40,7 @@ struct OvmParams {
     int total_units;        // ceil(n_atoms/4)
     int chunk_units;        // units per bulk copy
     int stages;             // ring depth per warp
-    float* partials;        // (F, n_seg, 16) when n_seg > 1
+    double* partials;       // (F, n_seg, 16) float64 when n_seg > 1
 };
 
 struct ApplyParams {

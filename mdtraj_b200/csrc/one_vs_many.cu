@@ -22,13 +22,18 @@
 //   * the centred reference (<= 4096 atoms per segment) is resident in shared memory
 //     for the whole kernel; longer frames are split into atom segments across CTAs
 //     and finished by ovm_finish_kernel;
-//   * single pass: sums are taken about a per-frame pivot (the frame's first atom),
-//     so  G = sum|x-p|^2 - N|mu-p|^2  loses one bit instead of log2(|offset|^2/Rg^2);
-//     since the reference frame is centred, M needs no centring of the target;
-//   * float32 lane partials (<= a few dozen terms each), one 16-value reduce-scatter
-//     per frame (16 shuffles), then everything -- recentring, polynomial, Newton,
-//     the G_a+G_b-2*lambda cancellation, quaternion -- in float64 on one lane per
-//     frame, kBatch frames at a time.
+//   * single pass: sums are taken about a per-frame pivot p close to the centroid (the
+//     mean of 32 atoms spread over what is at hand: the frame's first chunk in shared
+//     memory, the whole frame for short or very long frames), so that x - p is exact in
+//     float32 and  G = sum|x-p|^2 - N|mu-p|^2  loses a fraction of a bit; since the
+//     reference frame is centred, M needs no centring of the target;
+//   * float32 lane partials (<= a few dozen terms each), with |x-p|^2 accumulated minus
+//     the reference's mean-square radius so that this all-positive sum stays
+//     fluctuation-sized; the cross-lane sums of the 16-value reduce-scatter are float64
+//     (24 shuffles per frame); then everything -- recentring, polynomial, Newton, the
+//     G_a+G_b-2*lambda cancellation, quaternion -- in float64 on one lane per frame,
+//     kBatch frames at a time.  Against the float64 truth on MD-like frames this is 5-10x
+//     closer than the reference's float32 SSE accumulation.
 #include <algorithm>
 #include <cstdlib>
 
@@ -36,15 +41,65 @@
 #include "kernels.cuh"
 #include "qcp.cuh"
 
+// Development variants (tools/build_variants.sh compiles them side by side); the defaults are the shipped kernel.
+#ifndef OVM_PIVOT
+#define OVM_PIVOT 2   // 0: the frame's first atom, 2: mean of 8 atoms spread over the frame
+#endif
+#ifndef OVM_REDUCE
+#define OVM_REDUCE 1  // 0: float32 butterfly, 1: last three stages in float64
+#endif
+#ifndef OVM_SHIFT
+#define OVM_SHIFT 1   // mean-square shift of the |x - p|^2 accumulation
+#endif
+#ifndef OVM_FLUSH
+#define OVM_FLUSH 1   // fold the lane partials into float64 every kFlushUnits units per lane
+#endif
+
 namespace b200 {
+
+// Pivot of the float32 accumulation: the mean of 8 atoms spread over the frame.  Lane l holds atom (l & 7) of the eight
+// (lanes 8..31 duplicate them); three butterfly stages leave the bit-identical mean on every lane.  Eight atoms put the
+// pivot within ~0.35 Rg of the centroid, after which the pivot is no longer what limits the accuracy (32 atoms: same
+// error against the float64 truth) -- and 8 sectors per frame cost nothing measurable where 32
+// cost 7-10 % of the HBM rate.
+__device__ __forceinline__ float pivot_mean8(float x)
+{
+#if OVM_PIVOT
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    x += __shfl_xor_sync(0xffffffffu, x, 4);
+    return x * 0.125f;
+#else
+    return x;
+#endif
+}
+__device__ __forceinline__ double reduce16(float (&v)[16], int lane)
+{
+#if OVM_REDUCE == 1
+    return warp_reduce_scatter16_mixed(v, lane);
+#else
+    warp_reduce_scatter16(v, lane);
+    return (double)v[0];
+#endif
+}
 
 // ---------------------------------------------------------------------------
 // per-frame epilogue: 16 float32 sums -> rmsd (+ rotation, centroid)
 //   rec[0..2]  = sum (x - p)          rec[3] = sum |x - p|^2
 //   rec[4..12] = sum (x - p)_i y_j    rec[13..15] = pivot p
 // ---------------------------------------------------------------------------
+// mean-square shift of the |x - p|^2 accumulation (acc_unit_shift): a function of the reference alone
+__device__ __forceinline__ float msq_shift(const OvmParams& p)
+{
+#if OVM_SHIFT
+    return (float)(p.ref_stats->G / (double)p.n_atoms);
+#else
+    return 0.f;
+#endif
+}
+
 template <bool PRE>
-__device__ __forceinline__ void finish_frame(const double rec[16], int64_t f, const OvmParams& p)
+__device__ __forceinline__ void finish_frame(const double rec[16], int64_t f, const OvmParams& p, float cshift)
 {
     const RefStats rs = *p.ref_stats;
     QcpInput q;
@@ -58,7 +113,8 @@ __device__ __forceinline__ void finish_frame(const double rec[16], int64_t f, co
         for (int i = 0; i < 9; ++i) q.M[i] = rec[4 + i];
     } else {
         const double mx = rec[0] * invn, my = rec[1] * invn, mz = rec[2] * invn;  // mean relative to pivot
-        double ga = rec[3] - (rec[0] * mx + rec[1] * my + rec[2] * mz);
+        const double g_raw = rec[3] + (double)cshift * (double)p.n_atoms;  // undo the caller's shift, exactly
+        double ga = g_raw - (rec[0] * mx + rec[1] * my + rec[2] * mz);
         q.Ga = ga > 0.0 ? ga : 0.0;
         // M_c = M' - N mu' (mu_y)^T ; mu_y is the float32 residual of the centred reference
         q.M[0] = rec[4] - mx * rs.sum[0];  q.M[1] = rec[5] - mx * rs.sum[1];  q.M[2] = rec[6] - mx * rs.sum[2];
@@ -95,7 +151,8 @@ __host__ __device__ inline OvmSmemLayout ovm_layout(int seg_units, int chunk_uni
     L.ref_off = 0;
     L.ring_off = align_up((size_t)seg_units * 48, 128);
     L.sums_off = L.ring_off + (size_t)kWarpsPerCta * stages * L.stage_bytes;
-    L.bar_off = align_up(L.sums_off + (size_t)kWarpsPerCta * kBatch * kSumStride * sizeof(float), 8);
+    L.sums_off = align_up(L.sums_off, 8);
+    L.bar_off = align_up(L.sums_off + (size_t)kWarpsPerCta * kBatch * kSumStride * sizeof(double), 8);
     L.total = L.bar_off + ((size_t)kWarpsPerCta * stages + 1) * sizeof(uint64_t);
     return L;
 }
@@ -105,13 +162,14 @@ size_t ovm_tma_smem_bytes(const OvmParams& p) { return ovm_layout(p.seg_units, p
 // the streaming kernel
 // grid = n_seg * ctas_per_seg ; CTA b works on segment (b % n_seg)
 // ---------------------------------------------------------------------------
-template <bool PRE>
+// FLUSH: frames longer than kFlushUnits units per lane (1024 atoms) fold their lane partials into float64 on the way
+template <bool PRE, bool FLUSH>
 __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const OvmSmemLayout L = ovm_layout(p.seg_units, p.chunk_units, p.stages);
     const float4* ref_s = reinterpret_cast<const float4*>(smem + L.ref_off);
-    float* sums_all = reinterpret_cast<float*>(smem + L.sums_off);
+    double* sums_all = reinterpret_cast<double*>(smem + L.sums_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,7 +182,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
     unsigned char* ring = smem + L.ring_off + (size_t)warp * p.stages * L.stage_bytes;
     uint64_t* my_bars = bars + warp * p.stages;
     uint64_t* ref_bar = bars + kWarpsPerCta * p.stages;
-    float* sums = sums_all + warp * kBatch * kSumStride;
+    double* sums = sums_all + warp * kBatch * kSumStride;
 
     if (lane == 0)
         for (int s = 0; s < p.stages; ++s) mbar_init(&my_bars[s], 1);
@@ -167,19 +225,38 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
     uint32_t phase = 0;
     int slot = 0;
     int64_t batch_f0 = f_begin;
-    float npx = 0.f, npy = 0.f, npz = 0.f;
-    if (!PRE && f_begin < f_end) {
-        const float* fp = p.xyz + f_begin * p.frame_stride;
-        npx = __ldg(fp); npy = __ldg(fp + 1); npz = __ldg(fp + 2);
-    }
+    const float cshift = PRE ? 0.f : msq_shift(p);
+    // Pivot = mean of 8 atoms spread over the WHOLE frame (pivot_mean8), read from global memory one frame ahead of the
+    // consumer: one 16-byte load per lane, 8 distinct sectors per frame, the same sectors the bulk copy of that frame
+    // brings through L2.  Every segment's CTA of a long frame computes the bit-identical pivot (the finish kernel adds
+    // their partial sums).  A pivot taken from the frame's first chunk alone is 2-3x worse on chain-like structures.
+#if OVM_PIVOT == 5   // timing experiment: atoms of the chunks the ring already holds of the next frame, loaded late
+    const int piv_span = min(upf, max(1, p.stages - 1) * p.chunk_units);
+    const int piv_unit = seg_unit0 + (int)((((int64_t)(2 * (lane & 7) + 1)) * piv_span) >> 4);
+#else
+    const int piv_unit = OVM_PIVOT ? (int)((((int64_t)(2 * (lane & 7) + 1)) * p.total_units) >> 4) : 0;
+#endif
+    float4 npv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!PRE && f_begin < f_end)
+        npv = __ldg(reinterpret_cast<const float4*>(p.xyz + f_begin * p.frame_stride) + 3 * (size_t)piv_unit);
+    // lane partials are folded into float64 every kFlushUnits units per lane (1024 atoms per warp)
+    const int flush_chunks = max(1, (kFlushUnits * 32) / p.chunk_units);
 
 #pragma unroll 1
     for (int64_t f = f_begin; f < f_end; ++f) {
-        const float px = npx, py = npy, pz = npz;
-        if (!PRE && f + 1 < f_end) {  // prefetch next frame's pivot
-            const float* fp = p.xyz + (f + 1) * p.frame_stride;
-            npx = __ldg(fp); npy = __ldg(fp + 1); npz = __ldg(fp + 2);
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (!PRE) {
+            px = pivot_mean8(npv.x); py = pivot_mean8(npv.y); pz = pivot_mean8(npv.z);
+#if OVM_PIVOT == 3   // timing experiment: the same loads from the CURRENT frame (L2 hits) -- wrong numbers
+            if (f + 1 < f_end)
+                npv = __ldg(reinterpret_cast<const float4*>(p.xyz + f * p.frame_stride) + 3 * (size_t)piv_unit);
+#elif OVM_PIVOT != 5
+            if (f + 1 < f_end)  // prefetch the next frame's pivot atoms
+                npv = __ldg(reinterpret_cast<const float4*>(p.xyz + (f + 1) * p.frame_stride) + 3 * (size_t)piv_unit);
+#endif
         }
+        double tot = 0.0;
+        int until_flush = flush_chunks;
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -188,6 +265,10 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
         for (int c = 0; c < cpf; ++c) {
             const int unit0 = c * p.chunk_units;
             const int units = min(p.chunk_units, upf - unit0);
+#if OVM_PIVOT == 5
+            if (!PRE && c == cpf - 1 && f + 1 < f_end)
+                npv = __ldg(reinterpret_cast<const float4*>(p.xyz + (f + 1) * p.frame_stride) + 3 * (size_t)piv_unit);
+#endif
             mbar_wait(&my_bars[stage], phase);
             const float4* xs = reinterpret_cast<const float4*>(ring + (size_t)stage * L.stage_bytes);
             const float4* ys = ref_s + (size_t)unit0 * 3;
@@ -196,7 +277,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
             for (int u = lane; u < units; u += 32) {
                 const float4 a0 = xs[3 * u], a1 = xs[3 * u + 1], a2 = xs[3 * u + 2];
                 const float4 b0 = ys[3 * u], b1 = ys[3 * u + 1], b2 = ys[3 * u + 2];
-                acc_unit<PRE>(v, a0, a1, a2, b0, b1, b2, px, py, pz, p.n_atoms - (atom0 + 4 * u));
+                acc_unit_shift<PRE>(v, a0, a1, a2, b0, b1, b2, px, py, pz, p.n_atoms - (atom0 + 4 * u), cshift);
             }
             __syncwarp();
             if (lane == 0 && issued < total_chunks) {
@@ -204,23 +285,29 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
                 issue(stage);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            if (FLUSH && OVM_FLUSH && --until_flush == 0 && c + 1 < cpf) {
+                tot += reduce16(v, lane);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                until_flush = flush_chunks;
+            }
         }
 
         if (lane == 0) { v[13] = px; v[14] = py; v[15] = pz; }
-        warp_reduce_scatter16(v, lane);
+        tot += reduce16(v, lane);
 
         if (p.n_seg > 1) {
-            if (!(lane & 1)) p.partials[((size_t)f * p.n_seg + seg) * 16 + (lane >> 1)] = v[0];
+            if (!(lane & 1)) p.partials[((size_t)f * p.n_seg + seg) * 16 + (lane >> 1)] = tot;
         } else {
-            if (!(lane & 1)) sums[slot * kSumStride + (lane >> 1)] = v[0];
+            if (!(lane & 1)) sums[slot * kSumStride + (lane >> 1)] = tot;
             ++slot;
             if (slot == kBatch || f + 1 == f_end) {
                 __syncwarp();
                 if (lane < slot) {
                     double rec[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) rec[i] = (double)sums[lane * kSumStride + i];
-                    finish_frame<PRE>(rec, batch_f0 + lane, p);
+                    for (int i = 0; i < 16; ++i) rec[i] = sums[lane * kSumStride + i];
+                    finish_frame<PRE>(rec, batch_f0 + lane, p, cshift);
                 }
                 __syncwarp();
                 slot = 0;
@@ -276,6 +363,11 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_group_kernel(const OvmP
     uint64_t* ref_bar = bars + n_warps * p.stages;
     float* sums = reinterpret_cast<float*>(smem + G.sums_off) + warp * kGroupBatch * kSumStride;
     const uint32_t frame_bytes = (uint32_t)units * 48u;
+    // pivot (L >= 8, i.e. frames of more than 67 atoms): mean of 8 atoms spread over the frame (the selection), see
+    // pivot_mean8; shorter frames keep their first atom -- their sums are too small for the pivot to matter.  No
+    // mean-square shift here either: sum |x - p|^2 of <= 704 atoms is a few hundred.
+    constexpr bool kMeanPivot = L >= 8 && OVM_PIVOT != 0;
+    const int piv_k = kMeanPivot ? (int)(((int64_t)(2 * (j & 7) + 1) * p.n_atoms) >> 4) : 0;
 
     if (lane == 0)
         for (int s = 0; s < p.stages; ++s) mbar_init(&my_bars[s], 1);
@@ -322,12 +414,18 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_group_kernel(const OvmP
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
         float px = 0.f, py = 0.f, pz = 0.f;
+        if (!PRE) {
+            // every lane of the warp takes part in the shuffles; inactive groups read frame 0 of the stage (harmless)
+            const float* xf = reinterpret_cast<const float*>(active ? xs : reinterpret_cast<const float4*>(
+                                                                              ring + (size_t)stage * G.stage_bytes));
+            const int a0 = sel ? idx_s[piv_k] : piv_k;
+            px = xf[3 * a0]; py = xf[3 * a0 + 1]; pz = xf[3 * a0 + 2];
+            if (kMeanPivot) { px = pivot_mean8(px); py = pivot_mean8(py); pz = pivot_mean8(pz); }
+        }
         if (active && sel) {
-            // the whole frame is in shared memory: gather the selection from there (pivot = first selected atom)
+            // the whole frame is in shared memory: gather the selection from there
             const float* xf = reinterpret_cast<const float*>(xs);
             const float* yf = reinterpret_cast<const float*>(ref_s);
-            const int a0 = idx_s[0];
-            px = xf[3 * a0]; py = xf[3 * a0 + 1]; pz = xf[3 * a0 + 2];
 #pragma unroll 2
             for (int k = j; k < p.n_atoms; k += L) {
                 const int a = idx_s[k];
@@ -335,10 +433,6 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_group_kernel(const OvmP
             }
             if (j == 0) { v[13] = px; v[14] = py; v[15] = pz; }
         } else if (active) {
-            if (!PRE) {
-                const float4 first = xs[0];
-                px = first.x; py = first.y; pz = first.z;
-            }
 #pragma unroll 2
             for (int u = j; u < units; u += L) {
                 const float4 a0 = xs[3 * u], a1 = xs[3 * u + 1], a2 = xs[3 * u + 2];
@@ -354,6 +448,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_group_kernel(const OvmP
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
 
+        // frames of <= 704 atoms: <= 44 atoms per lane and sums of a few hundred -- float32 throughout is already in the
+        // 1e-6 nm class here; the float64 stages of the long-frame kernels would cost 5-15 % of HBM rate
         const int base = group_reduce_scatter16<L>(v, lane);
 #pragma unroll
         for (int k = 0; k < 16 / L; ++k) sums[(slot + g) * kSumStride + base + k] = v[k];
@@ -365,7 +461,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_group_kernel(const OvmP
                 double rec[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) rec[i] = (double)sums[lane * kSumStride + i];
-                finish_frame<PRE>(rec, f, p);
+                finish_frame<PRE>(rec, f, p, 0.f);
             }
             __syncwarp();
             slot = 0;
@@ -384,17 +480,17 @@ __global__ void ovm_finish_kernel(const OvmParams p)
 #pragma unroll
     for (int i = 0; i < 16; ++i) rec[i] = 0.0;
     for (int s = 0; s < p.n_seg; ++s) {
-        const float4* src = reinterpret_cast<const float4*>(p.partials + ((size_t)f * p.n_seg + s) * 16);
+        const double2* src = reinterpret_cast<const double2*>(p.partials + ((size_t)f * p.n_seg + s) * 16);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 t = src[i];
-            rec[4 * i] += t.x; rec[4 * i + 1] += t.y; rec[4 * i + 2] += t.z; rec[4 * i + 3] += t.w;
+        for (int i = 0; i < 8; ++i) {
+            const double2 t = src[i];
+            rec[2 * i] += t.x; rec[2 * i + 1] += t.y;
         }
     }
     // every segment carried the same pivot in slots 13..15
     const double inv = 1.0 / p.n_seg;
     rec[13] *= inv; rec[14] *= inv; rec[15] *= inv;
-    finish_frame<PRE>(rec, f, p);
+    finish_frame<PRE>(rec, f, p, PRE ? 0.f : msq_shift(p));
 }
 
 // ---------------------------------------------------------------------------
@@ -404,14 +500,17 @@ __global__ void ovm_finish_kernel(const OvmParams p)
 template <bool PRE>
 __global__ void __launch_bounds__(256) ovm_gather_kernel(const OvmParams p)
 {
-    __shared__ float sums_all[8 * kBatch * kSumStride];
+    __shared__ double sums_all[8 * kBatch * kSumStride];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sums = sums_all + warp * kBatch * kSumStride;
+    double* sums = sums_all + warp * kBatch * kSumStride;
     const int64_t W = (int64_t)gridDim.x * 8;
     const int64_t gw = (int64_t)blockIdx.x * 8 + warp;
     const int64_t f_begin = p.n_frames * gw / W, f_end = p.n_frames * (gw + 1) / W;
     const int n = p.n_atoms;
-    const int piv = p.idx ? __ldg(p.idx) : 0;
+    // pivot: mean of 32 selected atoms spread over the selection, one per lane (their sectors are read again below)
+    const int piv_k = (int)(((int64_t)lane * n) >> 5);
+    const int piv = p.idx ? __ldg(p.idx + piv_k) : piv_k;
+    const float cshift = PRE ? 0.f : msq_shift(p);
     int slot = 0;
     int64_t batch_f0 = f_begin;
 
@@ -419,28 +518,43 @@ __global__ void __launch_bounds__(256) ovm_gather_kernel(const OvmParams p)
     for (int64_t f = f_begin; f < f_end; ++f) {
         const float* fr = p.xyz + f * p.frame_stride;
         float px = 0.f, py = 0.f, pz = 0.f;
-        if (!PRE) { px = __ldg(fr + 3 * piv); py = __ldg(fr + 3 * piv + 1); pz = __ldg(fr + 3 * piv + 2); }
+        if (!PRE) {
+            px = warp_sum(__ldg(fr + 3 * piv)) * 0.03125f;
+            py = warp_sum(__ldg(fr + 3 * piv + 1)) * 0.03125f;
+            pz = warp_sum(__ldg(fr + 3 * piv + 2)) * 0.03125f;
+        }
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        double tot = 0.0;
+#pragma unroll 1
+        for (int k0 = 0; k0 < n; k0 += kFlushUnits * 64) {  // float32 lane partials over 512 atoms, then float64
+            const int k1 = min(n, k0 + kFlushUnits * 64);
 #pragma unroll 4
-        for (int k = lane; k < n; k += 32) {
-            const int a = p.idx ? __ldg(p.idx + k) : k;
-            const float ax = __ldg(fr + 3 * a), ay = __ldg(fr + 3 * a + 1), az = __ldg(fr + 3 * a + 2);
-            const float bx = __ldg(p.ref + 3 * k), by = __ldg(p.ref + 3 * k + 1), bz = __ldg(p.ref + 3 * k + 2);
-            acc_atom<PRE>(v, ax, ay, az, bx, by, bz, px, py, pz);
+            for (int k = k0 + lane; k < k1; k += 32) {
+                const int a = p.idx ? __ldg(p.idx + k) : k;
+                const float ax = __ldg(fr + 3 * a), ay = __ldg(fr + 3 * a + 1), az = __ldg(fr + 3 * a + 2);
+                const float bx = __ldg(p.ref + 3 * k), by = __ldg(p.ref + 3 * k + 1), bz = __ldg(p.ref + 3 * k + 2);
+                acc_atom<PRE>(v, ax, ay, az, bx, by, bz, px, py, pz);
+                if (!PRE) v[3] -= cshift;
+            }
+            if (k1 < n) {
+                tot += warp_reduce_scatter16_mixed(v, lane);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
         }
         if (lane == 0) { v[13] = px; v[14] = py; v[15] = pz; }
-        warp_reduce_scatter16(v, lane);
-        if (!(lane & 1)) sums[slot * kSumStride + (lane >> 1)] = v[0];
+        tot += warp_reduce_scatter16_mixed(v, lane);
+        if (!(lane & 1)) sums[slot * kSumStride + (lane >> 1)] = tot;
         ++slot;
         if (slot == kBatch || f + 1 == f_end) {
             __syncwarp();
             if (lane < slot) {
                 double rec[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) rec[i] = (double)sums[lane * kSumStride + i];
-                finish_frame<PRE>(rec, batch_f0 + lane, p);
+                for (int i = 0; i < 16; ++i) rec[i] = sums[lane * kSumStride + i];
+                finish_frame<PRE>(rec, batch_f0 + lane, p, cshift);
             }
             __syncwarp();
             slot = 0;
@@ -456,7 +570,9 @@ cudaError_t launch_ovm_tma(const OvmParams& p, bool precentered, int sm_count, c
 {
     if (p.n_frames <= 0) return cudaSuccess;
     const size_t smem = ovm_tma_smem_bytes(p);
-    auto kern = precentered ? ovm_tma_kernel<true> : ovm_tma_kernel<false>;
+    const bool flush = p.seg_units > kFlushUnits * 32;
+    auto kern = precentered ? (flush ? ovm_tma_kernel<true, true> : ovm_tma_kernel<true, false>)
+                            : (flush ? ovm_tma_kernel<false, true> : ovm_tma_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int ctas_per_seg = sm_count / p.n_seg;

@@ -347,6 +347,21 @@ def synth_md(n_frames, n_atoms, seed=0, rg=1.5, sigma=0.1, box=5.0):
     return X.astype(np.float32)
 
 
+def synth_md_chain(n_frames, n_atoms, seed=0, bond=0.15, sigma=0.1, box=5.0):
+    """D-chain: a random-walk polymer (bond nm per step, Rg ~ bond*sqrt(N/6)) -- consecutive atoms are spatially correlated
+    as in a real protein, so a pivot or centroid estimated from the first atoms of a frame is a poor one.  Per-frame noise,
+    random rigid motion, +-box nm offset."""
+    rng = np.random.default_rng(seed)
+    steps = rng.standard_normal((n_atoms, 3))
+    steps /= np.linalg.norm(steps, axis=1, keepdims=True)
+    base = np.cumsum(bond * steps, 0)
+    base -= base.mean(0)
+    X = base[None] + rng.standard_normal((n_frames, n_atoms, 3)) * sigma
+    R = random_rotations(n_frames, rng)
+    X = np.einsum("fni,fij->fnj", X, R) + rng.uniform(-box, box, size=(n_frames, 1, 3))
+    return X.astype(np.float32)
+
+
 def synth_md_basins(n_frames, n_atoms, n_basins=3, seed=0, rg=1.0, sigma=0.1, separation=1.4, interleave=False, box=5.0):
     """Multi-basin MD-like frames: `n_basins` base structures `separation` nm of RMSD apart from the first one (and
     ~separation*sqrt(2) from each other), per-frame noise sigma, random rigid motion.  Frames of a basin are contiguous

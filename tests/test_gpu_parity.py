@@ -445,7 +445,7 @@ def test_allpairs_multi_basin(mdb, oracle_mod, n_basins, interleave):
     e_gpu, e_ref, e_gr = _sampled_rows_vs_truth(O, X, Ds, rows[:3], atom_indices=idx)
     assert e_gpu < 1e-5 and e_gr < 1e-5, (e_gpu, e_ref, e_gr)
     blk = AP.rows(prep, 1000, 1100).cpu().numpy()
-    assert np.abs(blk - D[1000:1100]).max() < 2e-6
+    assert np.abs(blk - D[1000:1100]).max() < 5e-6  # mirrored vs computed orientation: two results of the 1e-6 class
 
 
 def test_allpairs_single_reference_would_fail_multi_basin(mdb, oracle_mod):
@@ -814,7 +814,7 @@ def test_host_pipeline_pageable_pinned_and_chunking_agree(mdb, oracle_mod, small
     import torch
     O = oracle_mod
     F = 9000 if N > 30 else 40000
-    X = O.synth_md(F, N, seed=70 + N)
+    X = O.synth_md(F, N, seed=70 + N, rg=0.4 if N < 30 else 1.5)   # a 22-atom molecule is 0.3-0.4 nm across, not 1.5
     ref = mdb.Trajectory(X[:3].copy())
     idx = np.arange(0, N, 3)
     pinned = torch.empty((F, N, 3), dtype=torch.float32).pin_memory()

@@ -9,7 +9,11 @@ from mdtraj_b200.device import _Scratch, _stream_ptr, prepare_reference
 
 def main():
     geom = "--geom" in sys.argv
-    Ns = [int(a) for a in sys.argv[1:] if a != "--geom"] or [22, 50, 100, 200, 300, 500, 1000]
+    tma = "--tma" in sys.argv   # ring geometry of the chunked kernel (dev build): chunk units x stages
+    libs = [a[6:] for a in sys.argv[1:] if a.startswith("--lib=")]   # variants/*.so built by tools/build_variants.sh
+    if libs:
+        _capi.LIB_PATH = os.path.abspath(libs[0])
+    Ns = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [22, 50, 100, 200, 300, 500, 1000]
     dev = torch.device("cuda", 0)
     L = _capi.lib()
     for N in Ns:
@@ -29,18 +33,22 @@ def main():
             envs.append({"B200RMSD_NO_GROUP": "1"})
             envs += [{"B200RMSD_GROUP_LANES": str(l)} for l in (2, 4, 8, 16)] if n_pad * 12 <= 3072 else \
                     [{"B200RMSD_GROUP_WARPS": str(w), "B200RMSD_GROUP_MAX_BYTES": "14000"} for w in (4, 5, 6, 8, 10, 12)]
+        if tma:
+            envs += [{"B200RMSD_NO_GROUP": "1", "B200RMSD_CHUNK_UNITS": str(c), "B200RMSD_STAGES": str(st)}
+                     for c in (32, 48, 64, 96) for st in (2, 3, 4, 6, 8)]
         for env in envs:
-            for k in ("B200RMSD_NO_GROUP", "B200RMSD_GROUP_LANES", "B200RMSD_GROUP_WARPS", "B200RMSD_GROUP_MAX_BYTES"):
+            for k in ("B200RMSD_NO_GROUP", "B200RMSD_GROUP_LANES", "B200RMSD_GROUP_WARPS", "B200RMSD_GROUP_MAX_BYTES",
+                      "B200RMSD_CHUNK_UNITS", "B200RMSD_STAGES"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             for _ in range(3): run()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(10): run()
+            for _ in range(20): run()
             e1.record(); torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 10
-            print(json.dumps({"N": N, "F": F, "env": env, "ms": round(ms, 4), "frames_per_s": F / ms * 1e3,
+            ms = e0.elapsed_time(e1) / 20
+            print(json.dumps({"N": N, "F": F, "env": env, **({"lib": os.path.basename(libs[0])} if libs else {}), "ms": round(ms, 4), "frames_per_s": F / ms * 1e3,
                               "GBs_algorithmic": F * N * 12 / ms / 1e6, "GBs_padded": F * n_pad * 12 / ms / 1e6,
                               "frac": round(F * n_pad * 12 / ms / 1e6 / 6540.8, 3)}), flush=True)
         del dt, out
