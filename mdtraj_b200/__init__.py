@@ -41,19 +41,23 @@ def __getattr__(name):
 def patch_mdtraj():
     """Swap this implementation into an importable ``mdtraj``.
 
-    Replaces ``mdtraj.rmsd``, ``mdtraj._rmsd``-level functions and the two ``Trajectory`` methods that
-    call them, leaving everything else of mdtraj untouched.
+    Replaces the Cython module ``mdtraj._rmsd`` (``mdtraj/rmsd/_rmsd.pyx``), the two names ``mdtraj/__init__.py:118``
+    re-exports from it (``mdtraj.rmsd``, ``mdtraj.rmsf``) and ``Trajectory.superpose`` (trajectory.py:1083-1173, fused into
+    one call here).  ``Trajectory.center_coordinates`` is left alone: upstream's unweighted branch (trajectory.py:2130-2135)
+    looks ``mdtraj._rmsd._center_inplace_atom_major`` up at call time and so lands in the CUDA library, and its
+    mass-weighted branch keeps working.  Everything else of mdtraj is untouched.  tests/test_reference_integration.py runs
+    the reference's own tests against the result.
     """
     import sys
 
     import mdtraj  # noqa: F401  (raises ImportError if the reference is not installed)
 
     from . import _rmsd as ours
-    from .trajectory import center_coordinates_host, superpose_host
+    from .trajectory import superpose_host
 
     sys.modules["mdtraj._rmsd"] = ours
     mdtraj._rmsd = ours
     mdtraj.rmsd = ours.rmsd
+    mdtraj.rmsf = ours.rmsf
     mdtraj.Trajectory.superpose = superpose_host
-    mdtraj.Trajectory.center_coordinates = center_coordinates_host
     return mdtraj

@@ -11,7 +11,7 @@ constexpr int kBatch = 16;                     // frames solved together (one la
 constexpr int kSumStride = 17;                 // padded stride of a 16-value sum record in smem
 constexpr int kFlushUnits = 8;                 // 4-atom units a lane accumulates in float32 before the float64 fold
 constexpr int kUnitFloats = 12;                // one "unit" = 4 atoms = 48 bytes = 3 x float4
-constexpr int kMaxSegUnits = 768;              // reference segment resident in smem: <= 3072 atoms (36 KB): >= 3 ring stages
+constexpr int kMaxSegUnits = 896;              // reference segment resident in smem: <= 3584 atoms (42 KB), leaves a 3-stage ring
 
 // reference-frame statistics written by prepare_ref_kernel (device memory)
 struct RefStats {

@@ -196,21 +196,23 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
         bulk_g2s(smem + L.ref_off, p.ref + (size_t)seg_unit0 * kUnitFloats, bytes, ref_bar);
     }
 
-    // static contiguous frame range of this warp
+    // static contiguous frame range of this warp; everything below counts frames and chunks relative to it in 32 bits
+    // (a warp's share of even 10^11 frames fits), which keeps the kernel under the 128-register ceiling of 512 threads
     const int64_t W = (int64_t)ctas_per_seg * kWarpsPerCta;
     const int64_t gw = (int64_t)cta_in_seg * kWarpsPerCta + warp;
-    const int64_t f_begin = p.n_frames * gw / W, f_end = p.n_frames * (gw + 1) / W;
+    const int64_t f_begin = p.n_frames * gw / W;
+    const int n_my = (int)(p.n_frames * (gw + 1) / W - f_begin);
+    const float* my_xyz = p.xyz + f_begin * p.frame_stride + (size_t)seg_unit0 * kUnitFloats;  // this warp's first frame, this segment
     const int cpf = (upf + p.chunk_units - 1) / p.chunk_units;  // bulk copies per frame
-    const int64_t total_chunks = (f_end - f_begin) * cpf;
+    const int total_chunks = n_my * cpf;
 
     // producer cursor (meaningful on lane 0 only)
-    int64_t pf = f_begin, issued = 0;
-    int pc = 0;
+    int pf = 0, pc = 0, issued = 0;
     const uint64_t pol = l2_policy_evict_first();
     auto issue = [&](int stage) {
         const int units = min(p.chunk_units, upf - pc * p.chunk_units);
         const uint32_t bytes = (uint32_t)units * 48u;
-        const float* src = p.xyz + pf * p.frame_stride + (size_t)(seg_unit0 + pc * p.chunk_units) * kUnitFloats;
+        const float* src = my_xyz + (int64_t)pf * p.frame_stride + (size_t)(pc * p.chunk_units) * kUnitFloats;
         mbar_arrive_expect_tx(&my_bars[stage], bytes);
         bulk_g2s_hint(ring + (size_t)stage * L.stage_bytes, src, bytes, &my_bars[stage], pol);
         if (++pc == cpf) { pc = 0; ++pf; }
@@ -224,36 +226,36 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
     int stage = 0;
     uint32_t phase = 0;
     int slot = 0;
-    int64_t batch_f0 = f_begin;
+    int batch_i0 = 0;
     const float cshift = PRE ? 0.f : msq_shift(p);
     // Pivot = mean of 8 atoms spread over the WHOLE frame (pivot_mean8), read from global memory one frame ahead of the
     // consumer: one 16-byte load per lane, 8 distinct sectors per frame, the same sectors the bulk copy of that frame
     // brings through L2.  Every segment's CTA of a long frame computes the bit-identical pivot (the finish kernel adds
     // their partial sums).  A pivot taken from the frame's first chunk alone is 2-3x worse on chain-like structures.
-#if OVM_PIVOT == 5   // timing experiment: atoms of the chunks the ring already holds of the next frame, loaded late
-    const int piv_span = min(upf, max(1, p.stages - 1) * p.chunk_units);
-    const int piv_unit = seg_unit0 + (int)((((int64_t)(2 * (lane & 7) + 1)) * piv_span) >> 4);
-#else
-    const int piv_unit = OVM_PIVOT ? (int)((((int64_t)(2 * (lane & 7) + 1)) * p.total_units) >> 4) : 0;
-#endif
-    float4 npv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!PRE && f_begin < f_end)
-        npv = __ldg(reinterpret_cast<const float4*>(p.xyz + f_begin * p.frame_stride) + 3 * (size_t)piv_unit);
+    const float4* piv_ptr = reinterpret_cast<const float4*>(p.xyz + f_begin * p.frame_stride) +
+                            3 * (OVM_PIVOT ? (int)((((int64_t)(2 * (lane & 7) + 1)) * p.total_units) >> 4) : 0);
+    // (an 8-byte and a 4-byte load, not one of 16: the unused fourth register of a 16-byte destination gets reused by the
+    // compiler for the chunk counter, whose first write then waits a whole load latency on it, every frame -- ncu source
+    // page of round 2, 12-17 % of all stall samples on that one MOV)
+    float npx = 0.f, npy = 0.f, npz = 0.f;
+    auto load_pivot = [&]() {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(piv_ptr));
+        npx = t.x; npy = t.y;
+        npz = __ldg(reinterpret_cast<const float*>(piv_ptr) + 2);
+    };
+    if (!PRE && n_my > 0) load_pivot();
     // lane partials are folded into float64 every kFlushUnits units per lane (1024 atoms per warp)
     const int flush_chunks = max(1, (kFlushUnits * 32) / p.chunk_units);
 
 #pragma unroll 1
-    for (int64_t f = f_begin; f < f_end; ++f) {
+    for (int fi = 0; fi < n_my; ++fi) {
         float px = 0.f, py = 0.f, pz = 0.f;
         if (!PRE) {
-            px = pivot_mean8(npv.x); py = pivot_mean8(npv.y); pz = pivot_mean8(npv.z);
-#if OVM_PIVOT == 3   // timing experiment: the same loads from the CURRENT frame (L2 hits) -- wrong numbers
-            if (f + 1 < f_end)
-                npv = __ldg(reinterpret_cast<const float4*>(p.xyz + f * p.frame_stride) + 3 * (size_t)piv_unit);
-#elif OVM_PIVOT != 5
-            if (f + 1 < f_end)  // prefetch the next frame's pivot atoms
-                npv = __ldg(reinterpret_cast<const float4*>(p.xyz + (f + 1) * p.frame_stride) + 3 * (size_t)piv_unit);
-#endif
+            px = pivot_mean8(npx); py = pivot_mean8(npy); pz = pivot_mean8(npz);
+            if (fi + 1 < n_my) {  // prefetch the next frame's pivot atoms
+                piv_ptr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(piv_ptr) + p.frame_stride);
+                load_pivot();
+            }
         }
         double tot = 0.0;
         int until_flush = flush_chunks;
@@ -265,10 +267,6 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
         for (int c = 0; c < cpf; ++c) {
             const int unit0 = c * p.chunk_units;
             const int units = min(p.chunk_units, upf - unit0);
-#if OVM_PIVOT == 5
-            if (!PRE && c == cpf - 1 && f + 1 < f_end)
-                npv = __ldg(reinterpret_cast<const float4*>(p.xyz + (f + 1) * p.frame_stride) + 3 * (size_t)piv_unit);
-#endif
             mbar_wait(&my_bars[stage], phase);
             const float4* xs = reinterpret_cast<const float4*>(ring + (size_t)stage * L.stage_bytes);
             const float4* ys = ref_s + (size_t)unit0 * 3;
@@ -294,24 +292,25 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1) ovm_tma_kernel(const OvmPar
         }
 
         if (lane == 0) { v[13] = px; v[14] = py; v[15] = pz; }
-        tot += reduce16(v, lane);
+        if (FLUSH) tot += reduce16(v, lane);
+        else tot = reduce16(v, lane);
 
         if (p.n_seg > 1) {
-            if (!(lane & 1)) p.partials[((size_t)f * p.n_seg + seg) * 16 + (lane >> 1)] = tot;
+            if (!(lane & 1)) p.partials[((size_t)(f_begin + fi) * p.n_seg + seg) * 16 + (lane >> 1)] = tot;
         } else {
             if (!(lane & 1)) sums[slot * kSumStride + (lane >> 1)] = tot;
             ++slot;
-            if (slot == kBatch || f + 1 == f_end) {
+            if (slot == kBatch || fi + 1 == n_my) {
                 __syncwarp();
                 if (lane < slot) {
                     double rec[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) rec[i] = sums[lane * kSumStride + i];
-                    finish_frame<PRE>(rec, batch_f0 + lane, p, cshift);
+                    finish_frame<PRE>(rec, f_begin + batch_i0 + lane, p, cshift);
                 }
                 __syncwarp();
                 slot = 0;
-                batch_f0 = f + 1;
+                batch_i0 = fi + 1;
             }
         }
     }

@@ -881,3 +881,115 @@ def test_host_pipeline_error_paths(mdb):
                                         out.ctypes.data, d.ctypes.data if len(devs) else None, len(devs))
         assert rc == _capi.EINVAL or rc == _capi.ENODEVICE, (devs, rc)
         assert L.b200rmsd_last_error()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# legacy raw-array entry points of mdtraj._rmsd (/root/reference/mdtraj/rmsd/_rmsd.pyx:502-674) against the compiled
+# reference loops; the only callers of b200rmsd_rotate_dev
+# ---------------------------------------------------------------------------------------------------------------------
+def _ref_superpose_atom_major(O, align_target_frame, g_target, align_mobile, g_mobile, displace):
+    """The reference's superpose_atom_major loop (oracle/ref_loops.cpp, or the C port), in place on `displace`."""
+    F, n_align, n_disp = align_mobile.shape[0], align_mobile.shape[1], displace.shape[1]
+    rot = np.zeros((F, 9), dtype=np.float32)
+    tgt = np.ascontiguousarray(align_target_frame, dtype=np.float32)
+    if O.ref_available():
+        O.ref_lib().refloops_superpose_atom_major(O._ptr(tgt), float(g_target), O._ptr(align_mobile), O._ptr(g_mobile), F,
+                                                  n_align, O._ptr(displace), n_disp, 1, O._ptr(rot))
+    else:
+        O.port_lib().oracle_superpose_atom_major(O._ptr(tgt), float(g_target), O._ptr(align_mobile), O._ptr(g_mobile), F,
+                                                 n_align, O._ptr(displace), n_disp, O._ptr(rot))
+    return rot.reshape(F, 3, 3)
+
+
+@pytest.mark.parametrize("F,N,Nd", [(300, 57, 57), (120, 1000, 1203), (40, 4100, 300)])
+def test_legacy_raw_array_entry_points(mdb, oracle_mod, F, N, Nd):
+    O = oracle_mod
+    kind = "reference" if O.ref_available() else "port"
+    X = O.synth_md(F, N, seed=900 + N)
+    Y = O.synth_md(7, N, seed=901 + N)
+    Xc, Yc = X.copy(), Y.copy()
+    g, gy = O.center_and_trace(Xc, kind), O.center_and_trace(Yc, kind)
+    m = np.arange(F) != 3
+
+    # getMultipleRMSDs_atom_major: same array twice (frame against itself is exactly 0), and two different arrays
+    got = mdb.getMultipleRMSDs_atom_major(Xc, Xc, g, g, 3)
+    want = O.one_vs_many_centered(Xc, g, Xc[3], g[3], impl=kind)
+    assert got.dtype == np.float32 and got.shape == (F,) and got[3] == 0.0
+    assert_three_way(got[m], want[m], O.truth_rmsd_batch(X, X[3])[m], "getMultipleRMSDs_atom_major (same array)")
+    got2 = mdb.getMultipleRMSDs_atom_major(Yc, Xc, gy, g, 5)
+    want2 = O.one_vs_many_centered(Xc, g, Yc[5], gy[5], impl=kind)
+    assert_three_way(got2, want2, O.truth_rmsd_batch(X, Y[5]), "getMultipleRMSDs_atom_major (two arrays)")
+    with pytest.raises(ValueError):
+        mdb.getMultipleRMSDs_atom_major(Yc, Xc, gy, g, 7)           # frame out of range, _rmsd.pyx:586-588
+    with pytest.raises(ValueError):
+        mdb.getMultipleRMSDs_atom_major(Yc[:, :-1].copy(), Xc, gy, g, 0)  # atom counts differ, :583-585
+
+    # getMultipleRMSDs_axis_major: (F, 3, N) layout, the same numbers
+    Xa, Ya = np.ascontiguousarray(Xc.transpose(0, 2, 1)), np.ascontiguousarray(Yc.transpose(0, 2, 1))
+    got_a = mdb.getMultipleRMSDs_axis_major(Xa, Xa, g, g, 3)
+    assert got_a[3] == 0.0 and np.abs(got_a - got).max() <= 1e-6
+    got_a2 = mdb.getMultipleRMSDs_axis_major(Ya, Xa, gy, g, 5)
+    assert np.abs(got_a2 - got2).max() <= 1e-6
+
+    # superpose_atom_major: rotation from the centred align arrays, applied in place to a displace array of another
+    # atom count (align != displace, trajectory.py:1152-1160)
+    rng = np.random.default_rng(5 + N)
+    D = (rng.standard_normal((F, Nd, 3)) * 2.0).astype(np.float32)
+    D_gpu, D_ref = D.copy(), D.copy()
+    assert mdb.superpose_atom_major(Xc, Xc, g, g, D_gpu, 3) is None
+    R_ref = _ref_superpose_atom_major(O, Xc[3], g[3], Xc, g, D_ref)
+    D_truth = np.empty_like(D, dtype=np.float64)
+    for i in range(F):
+        R, _ = O.truth_kabsch(X[i], X[3])
+        D_truth[i] = D[i].astype(np.float64) @ R
+    assert_three_way(D_gpu[m], D_ref[m], D_truth[m], "superpose_atom_major displaced coordinates", atol=2e-5)
+    assert np.abs(D_gpu[m] - D_truth[m]).max() < 2e-5
+    assert np.abs(R_ref[m] - np.stack([O.truth_kabsch(X[i], X[3])[0] for i in range(F)])[m]).max() < 1e-3  # oracle sanity
+    with pytest.raises(ValueError):
+        mdb.superpose_atom_major(Xc, Xc[:-1], g, g[:-1], D_gpu, 0)   # frame counts differ, :650-651
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json shapes against the oracle inside pytest (sizes the CPU side finishes in seconds)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F,N,step,gen", [(10000, 1000, 1, "md"), (2000, 5000, 5, "md"), (800, 25000, 1, "md"),
+                                          (800, 25000, 1, "chain"), (3000, 1000, 1, "chain")])
+def test_baseline_shapes_vs_oracle_three_way(mdb, oracle_mod, F, N, step, gen):
+    """C2 (N = 1000), C3's selection (every 5th of 5000 atoms) and C5 (N = 25000: atom segments + ovm_finish_kernel)
+    against the compiled reference and the float64 truth; and the accuracy class this round's accumulation buys:
+    at least 3x closer to the truth than the reference's float32 accumulation wherever that is measurable."""
+    O = oracle_mod
+    kind = "reference" if O.ref_available() else "port"
+    X = O.synth_md(F, N, seed=40 + N // 1000) if gen == "md" else O.synth_md_chain(F, N, seed=41 + N // 1000)
+    idx = None if step == 1 else np.arange(0, N, step)
+    got = mdb.rmsd(mdb.Trajectory(X.copy()), mdb.Trajectory(X.copy()), 0, atom_indices=idx)
+    want = O.rmsd(X, X, 0, atom_indices=idx, impl=kind)
+    truth = O.truth_rmsd_batch(X if idx is None else X[:, idx], X[0] if idx is None else X[0, idx])
+    assert_three_way(got[1:], want[1:], truth[1:], f"N={N} step={step} {gen}")
+    e_gpu, e_ref = np.abs(got[1:] - truth[1:]).max(), np.abs(want[1:] - truth[1:]).max()
+    assert e_gpu < 1e-5, (e_gpu, e_ref)
+    if e_ref > 6e-6:
+        assert e_gpu < e_ref / 3, (e_gpu, e_ref)
+    if idx is None:  # superposed coordinates of the same shape
+        a = mdb.Trajectory(X[:200].copy()); a.superpose(mdb.Trajectory(X[:1].copy()), 0)
+        sup_truth, _ = O.truth_superpose(X[:200], X[:1], 0)
+        assert np.abs(a.xyz - sup_truth).max() < 1e-5
+
+
+def test_nccl_two_ranks_match_single_gpu():
+    """The NCCL paths (mdtraj_b200.distributed: frame-sharded md.rmsd / superpose with all_gather, all-pairs with the
+    broadcast + symmetric block exchange) against the single-GPU results, two ranks under torchrun
+    (tools/multi_gpu_check.py holds the assertions).  Skipped on a one-GPU box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=900,
+                         cwd=root)
+    assert res.returncode == 0, (res.stdout[-1500:], res.stderr[-3000:])
+    assert "multi-GPU check ok" in res.stdout

@@ -13,6 +13,8 @@ def main():
     libs = [a[6:] for a in sys.argv[1:] if a.startswith("--lib=")]   # variants/*.so built by tools/build_variants.sh
     if libs:
         _capi.LIB_PATH = os.path.abspath(libs[0])
+    extra_env = dict(a[6:].split("=", 1) for a in sys.argv[1:] if a.startswith("--env="))   # dev-build switches
+    os.environ.update(extra_env)
     Ns = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [22, 50, 100, 200, 300, 500, 1000]
     dev = torch.device("cuda", 0)
     L = _capi.lib()
@@ -48,7 +50,7 @@ def main():
             for _ in range(20): run()
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 20
-            print(json.dumps({"N": N, "F": F, "env": env, **({"lib": os.path.basename(libs[0])} if libs else {}), "ms": round(ms, 4), "frames_per_s": F / ms * 1e3,
+            print(json.dumps({"N": N, "F": F, "env": {**extra_env, **env}, **({"lib": os.path.basename(libs[0])} if libs else {}), "ms": round(ms, 4), "frames_per_s": F / ms * 1e3,
                               "GBs_algorithmic": F * N * 12 / ms / 1e6, "GBs_padded": F * n_pad * 12 / ms / 1e6,
                               "frac": round(F * n_pad * 12 / ms / 1e6 / 6540.8, 3)}), flush=True)
         del dt, out
