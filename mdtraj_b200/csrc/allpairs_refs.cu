@@ -89,6 +89,42 @@ ap_select_update_kernel(int r, int64_t n_frames, int n_sel, const float* __restr
     }
 }
 
+// Reference r >= 1 is turned into the orientation of the reference it is nearest to (the rotation its frame got in the
+// passes so far), so that all references -- and with them all frames, which are rotated onto their owners -- share one
+// orientation up to second-order terms.  The all-pairs epilogue solves for lambda - tr M (qcp_msd_shift), which is only
+// small, and only then cheap to get to float32 accuracy, when the two frames of a pair are not rotated against each
+// other.  One block; the float32 residual sum of the centred reference is recomputed for the rotated coordinates.
+__global__ void __launch_bounds__(256)
+ap_rotate_ref_kernel(float* __restrict__ ref, int n_sel, const float* __restrict__ rot9, RefStats* __restrict__ stats)
+{
+    __shared__ double s_sum[8][3];
+    float R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = rot9[i];
+    double sx = 0, sy = 0, sz = 0;
+    for (int k = threadIdx.x; k < n_sel; k += 256) {
+        const float x = ref[3 * k], y = ref[3 * k + 1], z = ref[3 * k + 2];
+        const float nx = fmaf(x, R[0], fmaf(y, R[3], z * R[6]));
+        const float ny = fmaf(x, R[1], fmaf(y, R[4], z * R[7]));
+        const float nz = fmaf(x, R[2], fmaf(y, R[5], z * R[8]));
+        ref[3 * k] = nx; ref[3 * k + 1] = ny; ref[3 * k + 2] = nz;
+        sx += nx; sy += ny; sz += nz;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_sum[warp][0] = sx; s_sum[warp][1] = sy; s_sum[warp][2] = sz; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { sx += s_sum[w][0]; sy += s_sum[w][1]; sz += s_sum[w][2]; }
+        stats->sum[0] = sx; stats->sum[1] = sy; stats->sum[2] = sz;
+    }
+}
+
 // owner >= 0: stored as a difference from reference `owner`; the blocks of four references a j-tile (48 frames) needs
 __global__ void __launch_bounds__(64)
 ap_tile_aug_kernel(const int* __restrict__ owner, int64_t n_frames, int2* __restrict__ tile_aug)
@@ -134,6 +170,10 @@ int ap_select_references(const float* xyz, int64_t n_frames, int n_atoms, int64_
         float* ref = (float*)(base + g.ref_off + (size_t)R * g.ref_stride);
         if (int rc = b200rmsd_prepare_reference_dev(xyz + ref_frame * frame_stride, idx, n_sel, 1, 0.f, ref, stats + R, st))
             return rc;
+        if (R > 0) {  // into the orientation of its nearest reference so far (rot[] still holds the passes before this one)
+            ap_rotate_ref_kernel<<<1, 256, 0, st>>>(ref, n_sel, rot + ref_frame * 9, stats + R);
+            if (cudaGetLastError() != cudaSuccess) return set_error(B200RMSD_ECUDA, "allpairs_prepare: reference rotation launch failed");
+        }
         if (int rc = b200rmsd_rmsd_dev(xyz, n_frames, n_atoms, frame_stride, idx, n_sel, ref, stats + R, nullptr, 0,
                                        tmp_rmsd, tmp_rot, cen, nullptr, base + g.scratch_off, g.scratch_bytes, st))
             return rc;

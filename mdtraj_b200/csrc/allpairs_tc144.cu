@@ -385,10 +385,22 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                             m[6 + q] = __shfl_sync(0xffffffffu, send2, src2);
                         }
                     };
+                    // the same block with its rows in the order x, y, z: the shifted solver (qcp_msd_shift) relies on
+                    // frame i and frame j sharing an orientation, which the cyclic permutation above would undo
+                    auto gather_xyz = [&](int jg, float (&m)[9]) {
+                        float t[9];
+                        gather(jg, t);
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            m[q] = sel3(c, t[q], t[6 + q], t[3 + q]);
+                            m[3 + q] = sel3(c, t[3 + q], t[q], t[6 + q]);
+                            m[6 + q] = sel3(c, t[6 + q], t[3 + q], t[q]);
+                        }
+                    };
 #pragma unroll
                     for (int u = 0; u < NP; ++u) {
                         const int jg = NP * jp + u;
-                        gather(jg, M[u]);
+                        gather_xyz(jg, M[u]);
                         fj[u] = (int64_t)tj * kJFrames + seg * 12 + 3 * jg + c;
                         ok[u] = i_ok && fj[u] >= p.col0 && fj[u] < p.col1;
                         Ga[u] = ok[u] ? __ldg(p.traces + fj[u]) : 1.0f;
@@ -401,22 +413,27 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                         for (int u = 0; u < NP; ++u) res[u] = M[u][0];
                     } else
 #endif
-                    if (p.flags & B200RMSD_FAST_SOLVE) {  // all-float32 solve (reference-class precision)
+                    if (p.flags & B200RMSD_FAST_SOLVE) {  // all-float32 solve on lambda (reference-class precision)
                         qcp_msd_f32<NP>(M, Ga, Gb, ok, inv_n, res, trusted);
-                    } else {
-                        qcp_msd_fast<NP>(M, Ga, Gb, ok, inv_n, res, trusted);
+                    } else {                              // float32 solve on lambda - tr M: 1e-7 nm class on aligned pairs
+                        qcp_msd_shift<NP>(M, Ga, Gb, ok, (float)p.n_sel, res, trusted);
                     }
                     bool all_trusted = true;
 #pragma unroll
                     for (int u = 0; u < NP; ++u) all_trusted = all_trusted && trusted[u];
                     if (!__all_sync(0xffffffffu, all_trusted)) {
-                        // rare (collinear atoms, two-atom selections: a double largest root): fetch the blocks again --
-                        // M is dead by now, which keeps it out of the solver's register budget -- and take the closed form
+                        // Uncommon.  (1) similar frames that do not share an orientation: the float64-polished solve on
+                        // lambda; (2) collinear atoms, two-atom selections (a double largest root): the closed form.
+                        // The blocks are fetched again -- M is dead by now, which keeps it out of the fast solver's
+                        // register budget (unrolled: the accumulator registers must stay statically indexed).
+                        float M2[NP][9], res2[NP];
+                        bool trusted2[NP];
 #pragma unroll
-                        for (int u = 0; u < NP; ++u) {  // unrolled: the accumulator registers must stay statically indexed
-                            float m[9];
-                            gather(NP * jp + u, m);
-                            if (!trusted[u]) res[u] = qcp_rmsd_closed(m, Ga[u], Gb[u], inv_n);
+                        for (int u = 0; u < NP; ++u) gather(NP * jp + u, M2[u]);
+                        qcp_msd_fast<NP>(M2, Ga, Gb, ok, inv_n, res2, trusted2);
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) {
+                            if (!trusted[u]) res[u] = trusted2[u] ? res2[u] : qcp_rmsd_closed(M2[u], Ga[u], Gb[u], inv_n);
                         }
                     }
 #pragma unroll

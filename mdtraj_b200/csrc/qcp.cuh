@@ -339,6 +339,139 @@ __device__ __forceinline__ void qcp_msd_fast(const float (&M)[NP][9], const floa
     }
 }
 
+// error-free transformation a + b = s + e (Knuth), 6 float32 operations, no ordering of |a|, |b| needed
+__device__ __forceinline__ void two_sum(float a, float b, float& s, float& e)
+{
+    s = __fadd_rn(a, b);
+    const float bb = __fadd_rn(s, -a);
+    e = __fadd_rn(__fadd_rn(a, -__fadd_rn(s, -bb)), __fadd_rn(b, -bb));
+}
+
+// ---------------------------------------------------------------------------------------------
+// All-pairs epilogue solver, round 2: float32 throughout, and MORE accurate than the float64 polish above on the
+// inputs the all-pairs operands produce -- because it never forms the cancelling quantity.
+//
+// RMSD^2 = 2 (S - lambda)/N with S = (G_a + G_b)/2 and lambda the largest eigenvalue of the 4x4 key matrix K(M).
+// Frames reach the epilogue pre-aligned (every frame is rotated onto its nearest reference structure, the references
+// onto each other: allpairs_refs.cu), so for the pairs whose RMSD is small against their size -- the ones where
+// S - lambda cancels -- the residual rotation is small and lambda = T + delta with T = tr M and delta second order in
+// it.  With K' = K - T I = [[0, a^T], [a, B]]  (a = the antisymmetric part of M, B = -2 (T I - sym M) restricted
+// suitably: B11 = -2 (Syy + Szz), B12 = Sxy + Syx, ...) the characteristic polynomial in delta is
+//
+//     delta^4 + 4T delta^3 + (c(B) - |a|^2) delta^2 - (det B + a^T B a + 4T |a|^2) delta - a^T adj(B) a,
+//
+// whose coefficients are sums of products WITHOUT the catastrophic cancellation of P(lambda) near lambda ~ S, and
+//
+//     S - lambda = (S - T) - delta:   S - T is evaluated exactly (error-free float32 sums), delta is small and its
+//                                     float32 relative error is harmless.
+//
+// Numpy emulation of exactly this arithmetic: pre-aligned MD-like pairs 3e-8 nm from the
+// float64 eigenvalue (the float64-polished route: 1e-6 class, float32 route of the reference: 1e-5), iid pairs 2.5e-7.
+// Newton from the upper bound of delta (monotone, as for lambda); 3-4 steps on pre-aligned pairs.
+//
+// trusted[] = false where float32 is not enough: pairs that are similar but NOT in a common orientation (delta large
+// against S - lambda: the estimated root error 4e-7 * sum|terms| / P'(delta) exceeds the tolerance), and (nearly) double
+// largest roots.  The caller redoes those through qcp_msd_fast / the closed form.
+// ---------------------------------------------------------------------------------------------
+template <int NP>
+__device__ __forceinline__ void qcp_msd_shift(const float (&M)[NP][9], const float (&Ga)[NP], const float (&Gb)[NP],
+                                              const bool (&active)[NP], float n_atoms, float (&rmsd)[NP],
+                                              bool (&trusted)[NP])
+{
+    float p3[NP], p2[NP], p1[NP], p0[NP], d[NP], e0[NP], s1v[NP], cn0[NP], cn1[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ss = fmaf(M[p][i], M[p][i], ss);
+        float ub = fminf(sqrt_approx(3.0f * ss) * 1.000001f, 0.5f * (Ga[p] + Gb[p]) * 1.000001f);
+        ub = fmaxf(ub, 1e-30f);
+        const int e = ((__float_as_int(ub) >> 23) & 0xff) - 127;
+        const float s1 = __int_as_float((127 - e) << 23);  // exact power of two: ub * s1 in [1, 2)
+        s1v[p] = s1;
+        const float m0 = M[p][0] * s1, m1 = M[p][1] * s1, m2 = M[p][2] * s1, m3 = M[p][3] * s1, m4 = M[p][4] * s1,
+                    m5 = M[p][5] * s1, m6 = M[p][6] * s1, m7 = M[p][7] * s1, m8 = M[p][8] * s1;
+        const float T = (m0 + m4) + m8;
+        const float a1 = m7 - m5, a2 = m2 - m6, a3 = m3 - m1;
+        const float B11 = -2.0f * (m4 + m8), B22 = -2.0f * (m0 + m8), B33 = -2.0f * (m0 + m4);
+        const float B12 = m1 + m3, B13 = m2 + m6, B23 = m5 + m7;
+        const float A11 = B22 * B33 - B23 * B23, A22 = B11 * B33 - B13 * B13, A33 = B11 * B22 - B12 * B12;
+        const float A12 = B13 * B23 - B12 * B33, A13 = B12 * B23 - B13 * B22, A23 = B12 * B13 - B11 * B23;
+        const float cB = A11 + A22 + A33;
+        const float detB = B11 * A11 + B12 * A12 + B13 * A13;
+        const float aa = a1 * a1 + a2 * a2 + a3 * a3;
+        const float aBa = a1 * (B11 * a1 + B12 * a2 + B13 * a3) + a2 * (B12 * a1 + B22 * a2 + B23 * a3) +
+                          a3 * (B13 * a1 + B23 * a2 + B33 * a3);
+        const float aAa = a1 * (A11 * a1 + A12 * a2 + A13 * a3) + a2 * (A12 * a1 + A22 * a2 + A23 * a3) +
+                          a3 * (A13 * a1 + A23 * a2 + A33 * a3);
+        // rounding noise of the coefficients themselves, which cancel internally for near-singular B (two-atom and
+        // collinear selections): |d p0| <~ eps |B|^2 |a|^2, |d p1| <~ eps |B|^3
+        const float bb = B11 * B11 + B22 * B22 + B33 * B33 + 2.0f * (B12 * B12 + B13 * B13 + B23 * B23);
+        cn0[p] = bb * aa;
+        cn1[p] = bb * sqrt_approx(bb);
+        p3[p] = 4.0f * T;
+        p2[p] = cB - aa;
+        p1[p] = -(detB + aBa + p3[p] * aa);
+        p0[p] = -aAa;
+        // S - T without rounding: (G_a/2 + G_b/2) - ((m0 + m4) + m8), every partial sum carried as (high, low)
+        float h1, l1, h2, l2, h3, l3, h4, l4;
+        two_sum(0.5f * Ga[p] * s1, 0.5f * Gb[p] * s1, h1, l1);
+        two_sum(m0, m4, h2, l2);
+        two_sum(h2, m8, h3, l3);
+        two_sum(h1, -h3, h4, l4);
+        e0[p] = h4 + (((l1 - l2) - l3) + l4);
+        d[p] = fmaxf(ub * s1 - T, 0.0f) + 4e-6f;  // upper bound of delta
+    }
+#pragma unroll 1
+    for (int it = 0; it < 10; ++it) {  // two steps per trip: half the votes and branches on the dependency chain
+        bool conv = true;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float x = d[p];
+                const float b3 = x + p3[p];
+                const float b2 = fmaf(b3, x, p2[p]);
+                const float b1 = fmaf(b2, x, p1[p]);
+                const float val = fmaf(b1, x, p0[p]);
+                const float c2 = fmaf(b3 + x, x, b2);
+                const float den = fmaf(c2, x, b1);
+                const float step = (fabsf(den) > 1e-30f) ? val * rcp_approx(den) : 0.0f;
+                d[p] = x - step;
+                if (half == 1) conv = conv && (!active[p] || fabsf(step) <= fmaf(2e-7f, fabsf(d[p]), 1e-9f));
+            }
+        }
+        if (__all_sync(0xffffffffu, conv)) break;  // warp-uniform exit: no divergence inside the loop
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const float x = d[p], ax = fabsf(x);
+        const float es = fmaxf(e0[p] - x, 0.0f);                     // (S - lambda), scaled
+        const float msd = 2.0f * es / (s1v[p] * n_atoms);
+        rmsd[p] = sqrt_approx(msd);
+        // one more evaluation at the final iterate: convergence, P' > 0, P'' > 0 and the float32 root-error estimate
+        const float b3 = x + p3[p];
+        const float b2 = fmaf(b3, x, p2[p]);
+        const float b1 = fmaf(b2, x, p1[p]);
+        const float val = fmaf(b1, x, p0[p]);
+        const float den = fmaf(fmaf(b3 + x, x, b2), x, b1);
+        const float mag = fmaf(fmaf(fmaf(ax + fabsf(p3[p]), ax, fabsf(p2[p])), ax, fabsf(p1[p])), ax, fabsf(p0[p]));
+        // float32 noise of P at the iterate: evaluation (4e-7 * sum |terms|) plus the coefficients' own rounding
+        const float noise = fmaf(4e-7f, mag, 2e-7f * fmaf(cn1[p], ax, cn0[p]));
+        // acceptable error of the RMSD: 4e-6 nm + 5e-5 relative on the ESTIMATE (the estimate is ~4x conservative; the
+        // parity tolerance is 1e-5 nm or 1e-4 relative); d(rmsd) = d(delta) / (N s1 rmsd); plus the 3e-7 noise floor of M
+        const float tol = fmaf(n_atoms * s1v[p] * rmsd[p], fmaf(5e-5f, rmsd[p], 4e-6f), 3e-7f);
+        const float half_curv = fmaf(6.0f * x, x + 0.5f * p3[p], p2[p]);   // P''(x) / 2
+        // converged: the next Newton step would be negligible, or P is at its noise floor; P' > 0 and P'' > 0: right of
+        // every other root; the root-error estimate noise / P' within tolerance; and the root simple at float32
+        // resolution -- next to a (nearly) double root the error is sqrt(2 noise / P'') instead, and the linear estimate
+        // only holds while P'^2 >> noise * P''
+        const bool ok = den > 0.0f && fabsf(val) <= fmaxf(den * fmaf(1e-6f, ax, 4e-9f), 2.0f * noise) && half_curv > 0.0f &&
+                        noise <= den * tol && den * den >= 64.0f * noise * half_curv;
+        trusted[p] = ok || !active[p];
+    }
+}
+
 // All-float32 variant (development / comparison): coefficients, Newton and the final cancellation in float32,
 // i.e. the precision class of the reference's own msdFromMandG (theobald_rmsd.cpp:217-277).  ok[] as in qcp_msd_fast.
 template <int NP>

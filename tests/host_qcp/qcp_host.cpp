@@ -33,4 +33,24 @@ void host_qcp_msd_fast(const float* M, const float* Ga, const float* Gb, int n_a
         rmsd[i] = ok[0] ? r[0] : qcp_rmsd_closed(m[0], ga[0], gb[0], inv_n);  // what the epilogue does
     }
 }
+// round 2's epilogue solver: qcp_msd_shift first; where it does not trust itself, qcp_msd_fast, then the closed form --
+// the same cascade as allpairs_tc144.cu.  M must be in the natural row order (x, y, z).  stage[i]: 0 shift, 1 fast, 2 closed.
+void host_qcp_msd_shift(const float* M, const float* Ga, const float* Gb, int n_atoms, long n, float* rmsd,
+                        unsigned char* stage)
+{
+    const float inv_n = 1.0f / (float)n_atoms;
+    for (long i = 0; i < n; ++i) {
+        float m[1][9], ga[1] = {Ga[i]}, gb[1] = {Gb[i]}, r[1];
+        bool act[1] = {true}, ok[1];
+        for (int k = 0; k < 9; ++k) m[0][k] = M[9 * i + k];
+        qcp_msd_shift<1>(m, ga, gb, act, (float)n_atoms, r, ok);
+        stage[i] = 0;
+        if (!ok[0]) {
+            qcp_msd_fast<1>(m, ga, gb, act, inv_n, r, ok);
+            stage[i] = 1;
+            if (!ok[0]) { r[0] = qcp_rmsd_closed(m[0], ga[0], gb[0], inv_n); stage[i] = 2; }
+        }
+        rmsd[i] = r[0];
+    }
+}
 }

@@ -11,6 +11,7 @@
 #define __noinline__ __attribute__((noinline))
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline float __fadd_rn(float a, float b) { volatile float s = a + b; return s; }  // volatile: no reassociation, no excess precision
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
