@@ -176,6 +176,14 @@ int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atom
  *   max_refs:      upper bound on the reference structures prepare may choose (default and maximum 32). */
 int b200rmsd_allpairs_configure(int min_tc_frames, int max_refs);
 
+/* Tensor-core kernel geometry: cta_pair != 0 runs the GEMM on 2-CTA clusters -- the two SMs of a TPC share one
+ * M = 256 tcgen05.mma (cta_group::2), each loading its own rows of A and half of the rows of B, which cuts the
+ * L2 -> shared-memory operand traffic by a quarter (74.7 -> 54.9 GB per 20k x 20k matrix); 0 (the default) selects the
+ * single-CTA kernel (M = 128).  Both produce bit-identical matrices.  The kernel is bound by its epilogue and the
+ * tensor pipe, not by operand delivery, so the pair geometry measures 0-7 % SLOWER on one B200
+ * and is kept as an option.  Process-wide; returns the previous setting. */
+int b200rmsd_allpairs_set_cta_pair(int cta_pair);
+
 /* What prepare found (synchronises `stream`): number of reference structures, number of frames stored as they are
  * because no reference is near them, covering radius (largest RMSD of a frame to its nearest reference, nm) and the
  * frame indices of the references (up to ref_frames_cap).  Any pointer may be NULL. */

@@ -25,6 +25,7 @@ namespace b200 {
 
 int g_ap_min_tc_frames = 512;
 int g_ap_max_refs = kApMaxRefs;
+int g_ap_cta_pair = 0;
 
 // one warp per frame
 __global__ void __launch_bounds__(256) allpairs_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames,
@@ -175,6 +176,13 @@ int b200rmsd_allpairs_configure(int min_tc_frames, int max_refs)
     if (min_tc_frames > 0) g_ap_min_tc_frames = min_tc_frames;
     if (max_refs > 0) g_ap_max_refs = max_refs < kApMaxRefs ? max_refs : kApMaxRefs;
     return 0;
+}
+
+int b200rmsd_allpairs_set_cta_pair(int cta_pair)
+{
+    const int was = g_ap_cta_pair;
+    g_ap_cta_pair = cta_pair != 0;
+    return was;
 }
 
 int b200rmsd_allpairs_info_dev(const void* workspace, size_t workspace_bytes, int* n_refs, int* n_far, float* cover_radius,

@@ -52,9 +52,18 @@ constexpr int kQuarterBytes = 32 * kK * 4;      // 4 KB: one 32-row A box
 constexpr int kABytes = kM * kK * 4;            // 16 KB
 constexpr int kBBytes = kN * kK * 4;            // 18 KB
 constexpr int kStage = 2 * kABytes + 2 * kBBytes;  // A_hi, A_lo, B_hi, B_lo = 68 KB (a multiple of 1024)
-constexpr uint32_t kAccStride = 256;            // TMEM columns between the two accumulator stages
+constexpr int kAccStages = 3;                   // accumulator stages in TMEM: the epilogue warps of a tile finish at different
+                                                // times (Newton trip counts, the rare fall-back pass); with two stages the
+                                                // fastest warp could run at most one tile ahead of the slowest
+constexpr uint32_t kAccStride = 160;            // TMEM columns between accumulator stages (144 used; 3 x 160 <= 512)
 constexpr uint32_t kTmem = 512;                 // allocation (power of two >= 256 + 144)
 constexpr int kSegCols = 36;                    // columns per epilogue segment = 12 j-frames
+// CTA-pair mode (cta_group::2): each CTA of a 2-CTA cluster holds its own 128 rows of A and HALF of the B box (72 rows);
+// one M = 256 MMA issued by the leader feeds both accumulators.  A stage shrinks to 50 KB, the ring grows to 4 stages,
+// and the L2 -> SM traffic per tile falls from 272 to 200 operand rows.
+constexpr int kRingPair = 4;
+constexpr int kBHalfBytes = (kN / 2) * kK * 4;  // 9 KB
+constexpr int kStagePair = 2 * kABytes + 2 * kBHalfBytes;  // 50 KB (a multiple of 1024)
 // Tile rasterisation: super-blocks of 24 x 20 tiles = 960 x 960 frames, row-major inside a block and across blocks, so
 // that the ~150 CTAs in flight share a working set of 2 x 960 frames (15 MB of operands at K = 320) that stays
 // L2-resident instead of sweeping the whole operand once per tile row.
@@ -75,6 +84,7 @@ struct Tc144Params {
     int n_sel;
     int nk;                  // K blocks of 32 (atoms)
     const int2* tile_aug;    // per absolute j-tile: first and last augmentation K block (first > last: none)
+    int pair;                // CTA-pair mode: a slot is TWO i-tiles (ti, ti + 1) x one j-tile, one per CTA of the cluster
     int symmetric;           // square block on the diagonal: tiles that hold no pair j >= i are skipped, values mirrored
     unsigned flags;
 };
@@ -83,16 +93,51 @@ struct Tc144Params {
 // Evaluated identically by the three warp roles.
 __host__ __device__ __forceinline__ bool tile_of_slot(int64_t t, const Tc144Params& p, int& ti, int& tj)
 {
-    const int64_t blk = t / (kSupI * kSupJ);
-    const int in = (int)(t - blk * (kSupI * kSupJ));
+    const int sup_i = p.pair ? kSupI / 2 : kSupI;  // rows of slots per super-block (a pair slot is two tiles high)
+    const int64_t blk = t / (sup_i * kSupJ);
+    const int in = (int)(t - blk * (sup_i * kSupJ));
     const int bi = (int)(blk / p.n_bj), bj = (int)(blk - (int64_t)bi * p.n_bj);
-    const int li = bi * kSupI + in / kSupJ, lj = bj * kSupJ + in % kSupJ;
-    ti = p.tiles_i0 + li;
+    const int li = (bi * sup_i + in / kSupJ) * (p.pair ? 2 : 1), lj = bj * kSupJ + in % kSupJ;
+    ti = p.tiles_i0 + li;  // pair mode: the leader's tile; the peer takes ti + 1
     tj = p.tiles_j0 + lj;
     if (li >= p.tiles_i || lj >= p.tiles_j) return false;
     // symmetric: the tile is needed iff its last j-frame is not before its first i-frame
     return !p.symmetric || (int64_t)tj * kJFrames + (kJFrames - 1) >= (int64_t)ti * kIFrames;
 }
+
+// The same walk without the 64-bit divisions: every thread of the three warp roles visits every slot (skipped ones
+// included, about half of them in symmetric mode), and t / (sup_i * kSupJ), blk / n_bj were 6 % of the kernel's stall
+// samples.  The step between a CTA's slots is smaller than a super-block, so the position advances by carries.
+struct SlotWalk {
+    int64_t t;
+    int in, bi, bj, per_block, step;
+    __device__ __forceinline__ SlotWalk(int64_t t0, int step_, const Tc144Params& p) : t(t0), step(step_)
+    {
+        per_block = (p.pair ? kSupI / 2 : kSupI) * kSupJ;
+        const int64_t blk = t0 / per_block;
+        in = (int)(t0 - blk * per_block);
+        bi = (int)(blk / p.n_bj);
+        bj = (int)(blk - (int64_t)bi * p.n_bj);
+    }
+    __device__ __forceinline__ void next(const Tc144Params& p)
+    {
+        t += step;
+        in += step;
+        while (in >= per_block) {
+            in -= per_block;
+            if (++bj == p.n_bj) { bj = 0; ++bi; }
+        }
+    }
+    __device__ __forceinline__ bool tile(const Tc144Params& p, int& ti, int& tj) const
+    {
+        const int row = in / kSupJ, col = in - row * kSupJ;
+        const int li = (bi * (p.pair ? kSupI / 2 : kSupI) + row) * (p.pair ? 2 : 1), lj = bj * kSupJ + col;
+        ti = p.tiles_i0 + li;
+        tj = p.tiles_j0 + lj;
+        if (li >= p.tiles_i || lj >= p.tiles_j) return false;
+        return !p.symmetric || (int64_t)tj * kJFrames + (kJFrames - 1) >= (int64_t)ti * kIFrames;
+    }
+};
 
 __device__ __forceinline__ float sel3(int c, float a0, float a1, float a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
 
@@ -206,7 +251,7 @@ allpairs_tc144_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames, i
 
 // EPI_WARPS in {8, 16}: epilogue warps (each TMEM lane quarter is served by EPI_WARPS/4 warps that split the four
 // 36-column segments of the accumulator); NP in {1, 2}: independent solves interleaved per lane.
-template <int EPI_WARPS, int NP>
+template <int EPI_WARPS, int NP, bool PAIR>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -216,22 +261,33 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is not guaranteed to have it
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRing * kStage);
-    uint64_t* empty = full + kRing;
-    uint64_t* tfull = empty + kRing;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    constexpr int kRingN = PAIR ? kRingPair : kRing;
+    constexpr int kStageN = PAIR ? kStagePair : kStage;
+    constexpr int kBBytesN = PAIR ? kBHalfBytes : kBBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRingN * kStageN);
+    uint64_t* empty = full + kRingN;
+    uint64_t* tfull = empty + kRingN;
+    uint64_t* tempty = tfull + kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // PAIR: rank of this CTA in its 2-CTA cluster (0 = leader: issues the MMAs, owns the full[] and tempty[] barriers
+    // both CTAs signal); slots are walked per cluster
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const int64_t slot0 = PAIR ? blockIdx.x >> 1 : blockIdx.x, slot_step = PAIR ? gridDim.x >> 1 : gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kRing; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
+        for (int s = 0; s < kRingN; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
         fence_mbar_init();
     }
-    if (warp == EPI_WARPS) tmem_alloc(tmem_slot, kTmem);
+    if (warp == EPI_WARPS) {
+        if (PAIR) tmem_alloc_pair(tmem_slot, kTmem);
+        else tmem_alloc(tmem_slot, kTmem);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -243,50 +299,68 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t t = blockIdx.x; t < p.n_slots; t += gridDim.x) {
+            // PAIR: both CTAs load (their A rows, their half of the B rows); every load's bytes are counted on the
+            // LEADER's full[stage], which the leader arms with the bytes of both CTAs.  A peer load may land before the
+            // leader has armed the phase: the transaction count just goes negative for a moment (the phase cannot
+            // complete before the leader's own arrival), and never earlier than that, because the peer only refills a
+            // stage after the commit of the MMAs that read it, i.e. after the leader's previous phase completed.
+            auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+                if (PAIR) tma_load_2d_pair(dst, map, bar, c0, c1);
+                else tma_load_2d(dst, map, bar, c0, c1);
+            };
+            for (SlotWalk w(slot0, (int)slot_step, p); w.t < p.n_slots; w.next(p)) {
                 int ti, tj;
-                if (!tile_of_slot(t, p, ti, tj)) continue;
-                const int a_row = ti * (3 * kIFrames), b_row = tj * kN;
+                if (!w.tile(p, ti, tj)) continue;
+                ti += rank;
+                const int a_row = ti * (3 * kIFrames), b_row = tj * kN + rank * (kN / 2);
                 for (int kb = 0; kb < p.nk; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    unsigned char* st = smem + stage * kStage;
-                    mbar_arrive_expect_tx(&full[stage], kStage);
+                    unsigned char* st = smem + stage * kStageN;
+                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], PAIR ? 2 * kStageN : kStageN);
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {  // lane quarter w <- rows of frames 10w .. 10w+9 (+2 ignored rows)
-                        tma_load_2d(st + w * kQuarterBytes, &map_a_hi, &full[stage], kb * kK, a_row + 30 * w);
-                        tma_load_2d(st + kABytes + w * kQuarterBytes, &map_a_lo, &full[stage], kb * kK, a_row + 30 * w);
+                        load(st + w * kQuarterBytes, &map_a_hi, &full[stage], kb * kK, a_row + 30 * w);
+                        load(st + kABytes + w * kQuarterBytes, &map_a_lo, &full[stage], kb * kK, a_row + 30 * w);
                     }
-                    tma_load_2d(st + 2 * kABytes, &map_b_hi, &full[stage], kb * kK, b_row);
-                    tma_load_2d(st + 2 * kABytes + kBBytes, &map_b_lo, &full[stage], kb * kK, b_row);
-                    if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                    load(st + 2 * kABytes, &map_b_hi, &full[stage], kb * kK, b_row);
+                    load(st + 2 * kABytes + kBBytesN, &map_b_lo, &full[stage], kb * kK, b_row);
+                    if (++stage == kRingN) { stage = 0; phase ^= 1u; }
                 }
                 // augmentation K blocks of the references this tile's column frames are stored against (no B_lo part)
                 const int2 aug = __ldg(p.tile_aug + tj);
                 for (int g = aug.x; g <= aug.y; ++g) {
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    unsigned char* st = smem + stage * kStage;
-                    mbar_arrive_expect_tx(&full[stage], kStage - kBBytes);
+                    unsigned char* st = smem + stage * kStageN;
+                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], (PAIR ? 2 : 1) * (kStageN - kBBytesN));
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
-                        tma_load_2d(st + w * kQuarterBytes, &map_g_a_hi, &full[stage], g * kK, a_row + 30 * w);
-                        tma_load_2d(st + kABytes + w * kQuarterBytes, &map_g_a_lo, &full[stage], g * kK, a_row + 30 * w);
+                        load(st + w * kQuarterBytes, &map_g_a_hi, &full[stage], g * kK, a_row + 30 * w);
+                        load(st + kABytes + w * kQuarterBytes, &map_g_a_lo, &full[stage], g * kK, a_row + 30 * w);
                     }
-                    tma_load_2d(st + 2 * kABytes, &map_g_b, &full[stage], g * kK, b_row);
-                    if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                    load(st + 2 * kABytes, &map_g_b, &full[stage], g * kK, b_row);
+                    if (++stage == kRingN) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == EPI_WARPS + 1) {
         // ===================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_tf32_idesc(kM, kN);
+        if (lane == 0 && rank == 0) {  // PAIR: the leader issues the M = 256 MMAs for both CTAs
+            constexpr uint32_t idesc = make_tf32_idesc(PAIR ? 2 * kM : kM, kN);
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc_flag) {
+                if (PAIR) umma_tf32_pair(d, a, b, idesc, acc_flag);
+                else umma_tf32(d, a, b, idesc, acc_flag);
+            };
+            auto commit = [&](uint64_t* bar) {  // PAIR: arrives on the barrier at this offset in BOTH CTAs
+                if (PAIR) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int64_t t = blockIdx.x; t < p.n_slots; t += gridDim.x) {
+            for (SlotWalk w(slot0, (int)slot_step, p); w.t < p.n_slots; w.next(p)) {
                 int ti_unused, tj;
-                if (!tile_of_slot(t, p, ti_unused, tj)) continue;
+                if (!w.tile(p, ti_unused, tj)) continue;
                 mbar_wait(&tempty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
@@ -294,41 +368,41 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     bool continue_mma = true;
-                    unsigned char* st = smem + stage * kStage;
+                    unsigned char* st = smem + stage * kStageN;
                     const uint64_t a_hi = make_sw128_kmajor_desc(st), a_lo = make_sw128_kmajor_desc(st + kABytes);
                     const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * kABytes),
-                                   b_lo = make_sw128_kmajor_desc(st + 2 * kABytes + kBBytes);
+                                   b_lo = make_sw128_kmajor_desc(st + 2 * kABytes + kBBytesN);
 #pragma unroll
 #ifdef B200RMSD_DEV_SWITCHES
                     if (p.flags & 0x200u) continue_mma = false;  // development: skip the MMAs (operand delivery alone)
 #endif
                     for (int ks = 0; ks < (continue_mma ? kK / 8 : 0); ++ks) {
                         const uint64_t off = (uint64_t)(ks * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
-                        umma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, (kb | ks) != 0 ? 1u : 0u);
-                        umma_tf32(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
-                        umma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
+                        mma(d_tmem, a_lo + off, b_hi + off, (kb | ks) != 0 ? 1u : 0u);
+                        mma(d_tmem, a_hi + off, b_lo + off, 1u);
+                        mma(d_tmem, a_hi + off, b_hi + off, 1u);
                     }
-                    umma_commit(&empty[stage]);  // frees this smem stage when the MMAs above have read it
-                    if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                    commit(&empty[stage]);  // frees this smem stage when the MMAs above have read it
+                    if (++stage == kRingN) { stage = 0; phase ^= 1u; }
                 }
                 const int2 aug = __ldg(p.tile_aug + tj);
                 for (int g = aug.x; g <= aug.y; ++g) {  // + X'_i c_r^T for the four references of block g: (g1 + g2 + g3) . e
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    unsigned char* st = smem + stage * kStage;
+                    unsigned char* st = smem + stage * kStageN;
                     const uint64_t a_hi = make_sw128_kmajor_desc(st), a_lo = make_sw128_kmajor_desc(st + kABytes);
                     const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * kABytes);
 #pragma unroll
                     for (int ks = 0; ks < kK / 8; ++ks) {
                         const uint64_t off = (uint64_t)(ks * 2);
-                        umma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, 1u);
-                        umma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
+                        mma(d_tmem, a_lo + off, b_hi + off, 1u);
+                        mma(d_tmem, a_hi + off, b_hi + off, 1u);
                     }
-                    umma_commit(&empty[stage]);
-                    if (++stage == kRing) { stage = 0; phase ^= 1u; }
+                    commit(&empty[stage]);
+                    if (++stage == kRingN) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tfull[acc]);        // accumulator complete
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                commit(&tfull[acc]);             // accumulator complete (both CTAs' epilogues)
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else {
@@ -342,9 +416,10 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         const float inv_n = 1.0f / (float)p.n_sel;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int64_t t = blockIdx.x; t < p.n_slots; t += gridDim.x) {
+        for (SlotWalk w(slot0, (int)slot_step, p); w.t < p.n_slots; w.next(p)) {
             int ti, tj;
-            if (!tile_of_slot(t, p, ti, tj)) continue;
+            if (!w.tile(p, ti, tj)) continue;
+            ti += rank;
             const int64_t fi = (int64_t)ti * kIFrames + ew * 10 + tq;  // row frame of this lane
             const bool i_ok = row_valid && fi >= p.row0 && fi < p.row1;
             const float Gi = i_ok ? __ldg(p.traces + fi) : 1.0f;
@@ -436,6 +511,14 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                             if (!trusted[u]) res[u] = trusted2[u] ? res2[u] : qcp_rmsd_closed(M2[u], Ga[u], Gb[u], inv_n);
                         }
                     }
+#ifdef B200RMSD_DEV_SWITCHES
+                    if (p.flags & 0x400u) {  // development: no global stores (one per warp so the work is not dead code)
+                        float acc_v = 0.f;
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) acc_v += res[u];
+                        if (acc_v == 123.456f) p.out[0] = acc_v;
+                    } else
+#endif
 #pragma unroll
                     for (int u = 0; u < NP; ++u)
                         if (ok[u]) {
@@ -452,16 +535,21 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_leader(&tempty[acc]);  // the leader's MMA thread waits for both CTAs' epilogues
+                else mbar_arrive(&tempty[acc]);
+            }
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();  // neither CTA may exit (or free its TMEM) while the other can still reach into it
+    else __syncthreads();
     if (warp == EPI_WARPS) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmem);
+        if (PAIR) tmem_dealloc_pair(tmem_base, kTmem);
+        else tmem_dealloc(tmem_base, kTmem);
     }
 }
 
@@ -469,9 +557,10 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
 // host side
 // ---------------------------------------------------------------------------------------------
 // tile grid and super-block walk of the block [row0,row1) x [col0,col1)
-static Tc144Params tc144_tiling(int64_t row0, int64_t row1, int64_t col0, int64_t col1, bool has_out_t)
+static Tc144Params tc144_tiling(int64_t row0, int64_t row1, int64_t col0, int64_t col1, bool has_out_t, bool pair = false)
 {
     Tc144Params p{};
+    p.pair = pair ? 1 : 0;
     p.row0 = row0;
     p.row1 = row1;
     p.col0 = col0;
@@ -486,7 +575,8 @@ static Tc144Params tc144_tiling(int64_t row0, int64_t row1, int64_t col0, int64_
     if (getenv("B200RMSD_NO_SYMMETRIC")) p.symmetric = 0;
 #endif
     p.n_bj = (p.tiles_j + kSupJ - 1) / kSupJ;
-    p.n_slots = (int64_t)((p.tiles_i + kSupI - 1) / kSupI) * p.n_bj * (kSupI * kSupJ);
+    // a super-block is kSupI i-tiles high either way: kSupI slots, or kSupI / 2 pair slots
+    p.n_slots = (int64_t)((p.tiles_i + kSupI - 1) / kSupI) * p.n_bj * ((pair ? kSupI / 2 : kSupI) * kSupJ);
     return p;
 }
 
@@ -535,17 +625,22 @@ int launch_allpairs_tc144_block(const ApGeometry& g, const char* base, int n_sel
                                 int64_t ld_t, unsigned flags, int sm_count, cudaStream_t st)
 {
     (void)n_frames;
+    bool pair = g_ap_cta_pair != 0 && sm_count >= 2;
+#ifdef B200RMSD_DEV_SWITCHES
+    if (const char* v = getenv("B200RMSD_TC_PAIR")) pair = atoi(v) != 0 && sm_count >= 2;
+#endif
+    const int b_box = pair ? kN / 2 : kN;  // CTA-pair mode: each CTA loads half of the B rows of a j-tile
     CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo, map_g_a_hi, map_g_a_lo, map_g_b;
     auto op = [&](size_t off) { return (const float*)(base + off); };
     if (!make_operand_map(&map_a_hi, op(g.a_hi_off), g.rows_pad, g.k_pad, 32) ||
         !make_operand_map(&map_a_lo, op(g.a_lo_off), g.rows_pad, g.k_pad, 32) ||
-        !make_operand_map(&map_b_hi, op(g.b_hi_off), g.rows_pad, g.k_pad, kN) ||
-        !make_operand_map(&map_b_lo, op(g.b_lo_off), g.rows_pad, g.k_pad, kN) ||
+        !make_operand_map(&map_b_hi, op(g.b_hi_off), g.rows_pad, g.k_pad, b_box) ||
+        !make_operand_map(&map_b_lo, op(g.b_lo_off), g.rows_pad, g.k_pad, b_box) ||
         !make_operand_map(&map_g_a_hi, op(g.aug_a_hi_off), g.rows_pad, kApAugCols, 32) ||
         !make_operand_map(&map_g_a_lo, op(g.aug_a_lo_off), g.rows_pad, kApAugCols, 32) ||
-        !make_operand_map(&map_g_b, op(g.aug_b_off), g.rows_pad, kApAugCols, kN))
+        !make_operand_map(&map_g_b, op(g.aug_b_off), g.rows_pad, kApAugCols, b_box))
         return set_error(B200RMSD_ECUDA, "allpairs: cuTensorMapEncodeTiled failed");
-    Tc144Params p = tc144_tiling(row0, row1, col0, col1, out_t != nullptr);
+    Tc144Params p = tc144_tiling(row0, row1, col0, col1, out_t != nullptr, pair);
     p.traces = op(g.traces_off);
     p.out = out;
     p.ld = ld;
@@ -560,25 +655,40 @@ int launch_allpairs_tc144_block(const ApGeometry& g, const char* base, int n_sel
     if (const char* dbg = getenv("B200RMSD_TC_DEBUG")) p.flags |= (unsigned)strtoul(dbg, nullptr, 0) & 0xff00u;
     if (const char* cfg = getenv("B200RMSD_TC_EPILOGUE")) sscanf(cfg, "%dx%d", &ew, &np);  // "<warps>x<np>", e.g. 16x1
 #endif
-    const size_t smem = (size_t)kRing * kStage + 1024 + 256;
+    const size_t smem = (size_t)(pair ? kRingPair * kStagePair : kRing * kStage) + 1024 + 256;
     int64_t ctas = sm_count;
     const int64_t n_tiles = (int64_t)p.tiles_i * p.tiles_j;
     if (ctas > n_tiles) ctas = n_tiles;
     if (ctas < 1) ctas = 1;
+    if (pair) ctas = std::max<int64_t>(2, ctas & ~(int64_t)1);  // whole clusters
     cudaError_t e = cudaSuccess;
-#define B200_LAUNCH_TC144(EW, NP)                                                                                          \
+    // one launch path for both modes: a 2-CTA cluster (the two SMs of a TPC) in pair mode
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define B200_LAUNCH_TC144(EW, NP, PAIR)                                                                                    \
     do {                                                                                                                   \
-        e = cudaFuncSetAttribute(allpairs_tc144_kernel<EW, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        auto kern = allpairs_tc144_kernel<EW, NP, PAIR>;                                                                   \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                            \
+        cfg.blockDim = dim3(64 + 32 * EW);                                                                                 \
         if (e == cudaSuccess)                                                                                              \
-            allpairs_tc144_kernel<EW, NP><<<(unsigned)ctas, 64 + 32 * EW, smem, st>>>(                                    \
-                map_a_hi, map_a_lo, map_b_hi, map_b_lo, map_g_a_hi, map_g_a_lo, map_g_b, p);                              \
+            e = cudaLaunchKernelEx(&cfg, kern, map_a_hi, map_a_lo, map_b_hi, map_b_lo, map_g_a_hi, map_g_a_lo, map_g_b, p); \
     } while (0)
 #ifdef B200RMSD_DEV_SWITCHES
-    if (ew == 8 && np == 2) B200_LAUNCH_TC144(8, 2);
-    else if (ew == 16 && np == 1) B200_LAUNCH_TC144(16, 1);
+    if (ew == 8 && np == 2) B200_LAUNCH_TC144(8, 2, false);
+    else if (ew == 16 && np == 1) B200_LAUNCH_TC144(16, 1, false);
     else
 #endif
-        B200_LAUNCH_TC144(16, 2);
+    if (pair) B200_LAUNCH_TC144(16, 2, true);
+    else B200_LAUNCH_TC144(16, 2, false);
 #undef B200_LAUNCH_TC144
     if (e != cudaSuccess) return set_error(B200RMSD_ECUDA, "allpairs: %s", cudaGetErrorString(e));
     e = cudaGetLastError();

@@ -993,3 +993,27 @@ def test_nccl_two_ranks_match_single_gpu():
                          cwd=root)
     assert res.returncode == 0, (res.stdout[-1500:], res.stderr[-3000:])
     assert "multi-GPU check ok" in res.stdout
+
+
+def test_allpairs_cta_pair_geometry_is_bit_identical(mdb, oracle_mod):
+    """The cta_group::2 geometry of the tcgen05 kernel (2-CTA clusters, one M = 256 MMA per pair of tiles, each CTA loading
+    half of the B rows) against the single-CTA kernel: the same matrix bit for bit -- full symmetric matrix, an
+    unsymmetric row block at an odd tile offset, and a block with a transposed copy (odd and even tile counts)."""
+    import torch
+    from mdtraj_b200 import allpairs as AP
+    O = oracle_mod
+    for F in (2090, 1640):
+        X, _ = O.synth_md_basins(F, 150, 2, seed=3 + F, rg=1.0, sigma=0.1, separation=1.2)
+        dt = mdb.DeviceTrajectory.from_host(X)
+        prep = AP.prepare(dt)
+        got = {}
+        try:
+            for pair in (False, True):
+                AP.configure(cta_pair=pair)
+                full = AP.rows(prep, 0, F).clone()
+                blk = AP.rows(prep, 41, 41 + 333).clone()
+                got[pair] = (full, blk)
+        finally:
+            AP.configure(cta_pair=False)
+        assert torch.equal(got[False][0], got[True][0]) and torch.equal(got[False][1], got[True][1])
+        assert torch.isfinite(got[True][0]).all()
