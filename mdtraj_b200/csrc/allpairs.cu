@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restr
         __syncthreads();
     }
 
+    const double inv_n = 1.0 / (double)n_sel;
 #pragma unroll
     for (int si = 0; si < 2; ++si)
 #pragma unroll
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restr
                 r = 0.f;  // a frame against itself in the same memory: theobald_rmsd_sse.h:256-262
             } else {
                 QcpInput q;
-                q.n_atoms = n_sel;
+                q.inv_n = inv_n;
                 q.Ga = (double)traces[j];
                 q.Gb = (double)traces[i];
 #pragma unroll

@@ -208,6 +208,7 @@ int b200rmsd_rmsd_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t f
     p.n_frames = n_frames;
     p.frame_stride = frame_stride;
     p.n_atoms = idx ? n_sel : n_atoms;
+    p.inv_n = 1.0 / (double)p.n_atoms;
     p.idx = idx;
     p.ref = ref;
     p.ref_stats = (const RefStats*)ref_stats;

@@ -147,6 +147,14 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
     // warp 16 lane 0: loader.  warp 17 lane 0: storer.  Two threads so that waiting for a store to drain
     // (cp.async.bulk.wait_group.read is the only completion mechanism of shared->global bulk copies) never delays
     // the issue of a load into another buffer: the storer publishes drained[buf], the loader refills it at once.
+    // Superpose with one buffer per group on 8 or more groups (frames up to ~25 KB): the group's own first
+    // thread stores its slot, waits for the store to have read the buffer and loads the group's next slot into it.  The
+    // group can do nothing else in between anyway, and the two DMA threads' queues drop out of the cycle: with eight
+    // groups handing over at random times a slot waited 2400 cycles for the storer thread, which blocks ~1100 cycles
+    // per store in cp.async.bulk.wait_group.read (12 % of the 20 000-cycle cycle of a group, tools/fused_trace.py).
+    // Measured (gpurun r02_fused_sweep vs r02_fused_sweep2): +0.01-0.025 of HBM peak there; centring and the 3-5 group
+    // geometries of larger frames lose up to 0.15 without the DMA threads, so they keep them.
+    const bool self_dma = OP == OP_SUPERPOSE && p.nbuf == G && G >= 8;
     if (warp == kFrWarps) {
         if (lane == 0) {
             if (OP == OP_SUPERPOSE) {
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
                 mbar_arrive_expect_tx(ref_bar, bytes);
                 bulk_g2s(smem + L.ref_off, p.ref, bytes, ref_bar);
             }
-            for (int64_t s = 0; s < n_slots; ++s) {
+            for (int64_t s = 0; s < (self_dma ? (n_slots < G ? n_slots : G) : n_slots); ++s) {  // self_dma: first round only
                 const int buf = (int)(s % p.nbuf);
                 const int64_t left = n - s * fpb;
                 const uint32_t bytes = (uint32_t)(left < fpb ? left : fpb) * frame_bytes;
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
         return;
     }
     if (warp == kFrWarps + 1) {
-        if (lane == 0) {
+        if (lane == 0 && !self_dma) {
             // Up to K stores in flight: store s is issued, then the storer waits only until store s-K has drained and
             // publishes that buffer.  K = 0 when every buffer is busy computing or loading (nbuf == G); small slots
             // need K > 0 or the drain latency of each 4-12 KB store would serialise the whole pipeline.
@@ -310,10 +318,10 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
 #pragma unroll
                     for (int q = 0; q < 16; ++q) rec[q] = (double)rec_all[((size_t)g * fpb + j) * kRecStride + q];
                 }
-                const double invn = 1.0 / (double)p.n_sel;
+                const double invn = p.inv_n_sel;
                 const double mx = rec[0] * invn, my = rec[1] * invn, mz = rec[2] * invn;
                 QcpInput q;
-                q.n_atoms = p.n_sel;
+                q.inv_n = invn;
                 q.Gb = rs.G;
                 const double ga = rec[3] - (rec[0] * mx + rec[1] * my + rec[2] * mz);
                 q.Ga = ga > 0.0 ? ga : 0.0;
@@ -430,8 +438,31 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
         if (gtid == 0) FR_STAMP(s, 3);
         fence_proxy_async_smem();
         group_sync(g, wpf);
-        if (gtid == 0) { mbar_arrive(&done[buf]); FR_STAMP(s, 4); }
+        if (gtid == 0) {
+            if (!self_dma) {
+                mbar_arrive(&done[buf]);
+                FR_STAMP(s, 4);
+            } else {
+                FR_STAMP(s, 4);
+                const uint32_t bytes = (uint32_t)cnt * frame_bytes;
+                bulk_s2g(p.xyz + fbase * p.frame_stride, slot_s, bytes);
+                bulk_commit();
+                FR_STAMP(s, 5);
+                bulk_wait_read<0>();  // the buffer has been read: it may be refilled
+                FR_STAMP(s, 6);
+                const int64_t s2 = s + G;
+                if (s2 < n_slots) {
+                    const int64_t left2 = n - s2 * fpb;
+                    const uint32_t bytes2 = (uint32_t)(left2 < fpb ? left2 : fpb) * frame_bytes;
+                    mbar_arrive_expect_tx(&full[buf], bytes2);
+                    bulk_g2s(slot_s, p.xyz + (f0 + s2 * fpb) * p.frame_stride, bytes2, &full[buf]);
+                    FR_STAMP(s2, 7);
+                }
+            }
+        }
     }
+    // self_dma: the stores of this thread must have completed (not just been read) before the CTA's memory goes away
+    if (self_dma && gtid == 0) bulk_wait<0>();
 }
 
 static int fr_team_warps(int G, int fpb)
@@ -657,7 +688,9 @@ cudaError_t launch_frame_resident(const FusedParams& p, int op, int sm_count, cu
     const int64_t per_round = (int64_t)p.batch * p.fpb;
     const int64_t need = (p.n_frames + per_round - 1) / per_round;
     if (ctas > need) ctas = need;
-    kern<<<(unsigned)ctas, kFrThreads, L.total, st>>>(p);
+    FusedParams q = p;
+    q.inv_n_sel = 1.0 / (double)(p.n_sel > 0 ? p.n_sel : 1);
+    kern<<<(unsigned)ctas, kFrThreads, L.total, st>>>(q);
     return cudaGetLastError();
 }
 

@@ -41,6 +41,7 @@ struct OvmParams {
     int chunk_units;        // units per bulk copy
     int stages;             // ring depth per warp
     double* partials;       // (F, n_seg, 16) float64 when n_seg > 1
+    double inv_n;           // 1 / n_atoms (set by the launchers)
 };
 
 struct ApplyParams {
@@ -74,6 +75,7 @@ struct FusedParams {
     int fpb;                // frames per slot (> 1 only when frame_stride == 3*n_pad)
     int team_warps;         // warps sharing one frame inside a group: 16/G or 1
     int lanes;              // team_warps == 1: lanes sharing one frame inside a warp (2, 4, 8, 16, 32)
+    double inv_n_sel;       // 1 / n_sel (set by launch_frame_resident)
 };
 bool fused_config(FusedParams& p, int op);
 bool fused_override(FusedParams& p, int op, int G, int nbuf, int fpb, int lanes);

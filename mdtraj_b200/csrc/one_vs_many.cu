@@ -103,9 +103,9 @@ __device__ __forceinline__ void finish_frame(const double rec[16], int64_t f, co
 {
     const RefStats rs = *p.ref_stats;
     QcpInput q;
-    q.n_atoms = p.n_atoms;
+    const double invn = p.inv_n;
+    q.inv_n = invn;
     q.Gb = rs.G;
-    const double invn = 1.0 / (double)p.n_atoms;
     double cx = 0, cy = 0, cz = 0;
     if (PRE) {
         q.Ga = (double)p.traces[f];

@@ -18,7 +18,7 @@ namespace b200 {
 struct QcpInput {
     double M[9];  // M[3*i+j] = sum_k a_k[i] * b_k[j], both frames centred
     double Ga, Gb;
-    int n_atoms;
+    double inv_n;  // 1 / number of atoms, computed once by the caller (a float64 division is ~30 dependent instructions)
 };
 
 // Closed form of the largest root, for the inputs Newton cannot be trusted on.
@@ -178,7 +178,7 @@ __device__ __forceinline__ double qcp_solve(const QcpInput& in, float* rot, bool
         double m[9] = {Sxx, Sxy, Sxz, Syx, Syy, Syz, Szx, Szy, Szz};
         lam = qcp_lambda_closed(m);
     }
-    double msd = (in.Ga + in.Gb - 2.0 * lam) / in.n_atoms;
+    double msd = (in.Ga + in.Gb - 2.0 * lam) * in.inv_n;
     if (!(msd > 0.0)) msd = 0.0;
 
     if (rot != nullptr) {

@@ -14,7 +14,7 @@ void host_qcp_solve(const double* M, const double* Ga, const double* Gb, int n_a
     for (long i = 0; i < n; ++i) {
         QcpInput q;
         for (int k = 0; k < 9; ++k) q.M[k] = M[9 * i + k];
-        q.Ga = Ga[i]; q.Gb = Gb[i]; q.n_atoms = n_atoms;
+        q.Ga = Ga[i]; q.Gb = Gb[i]; q.inv_n = 1.0 / (double)n_atoms;
         bool d = false;
         msd[i] = qcp_solve(q, rot ? rot + 9 * i : nullptr, &d);
         degen[i] = d;

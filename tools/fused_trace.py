@@ -22,8 +22,11 @@ def run():
                 scratch.numel(), _stream_ptr(torch, dev)), "superpose")
 for _ in range(3): run()
 torch.cuda.synchronize()
-n = F // 148
+geo = (ctypes.c_int * 6)()
+ctypes.CDLL(_capi.LIB_PATH).b200rmsd_debug_fused_geometry(0, N, int(idx.numel()), 1, 1, geo)
+print("geometry: G=%d nbuf=%d fpb=%d team_warps=%d lanes=%d smem=%d" % tuple(geo))
 per = (F // 148 + 2) * 8
+n = F // 148 // max(1, geo[2]) - 1   # slots per CTA
 buf = (ctypes.c_longlong * (per + 148 * 2))()
 fn = ctypes.CDLL(_capi.LIB_PATH).b200rmsd_debug_fused_trace
 fn.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
@@ -34,9 +37,9 @@ t0 = t[t > 0].min()
 t = (t - t0).astype(np.float64)
 names = ["arrived", "reduced", "solved", "xformed", "handed", "st_issue", "st_drain", "ld_issue"]
 print("frame  " + "  ".join(f"{x:>9s}" for x in names) + "   (cycles since first stamp)")
-for i in list(range(0, 12)) + list(range(100, 112)):
+for i in list(range(0, 12)) + list(range(min(100, n - 14), min(112, n - 2))):
     print(f"{i:5d}  " + "  ".join(f"{v:9.0f}" for v in t[i]))
-d = t[20:n-5]
+d = t[min(20, n // 3):n-3]
 print("mean per-frame period (cycles):", (d[-1, 4] - d[0, 4]) / (len(d) - 1))
 print("mean arrived->reduced %.0f  reduced->solved %.0f  solved->xformed %.0f  xformed->handed %.0f  handed->st_issue %.0f  st_issue->drain %.0f" % tuple(
     np.mean(d[:, b] - d[:, a]) for a, b in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6))))
