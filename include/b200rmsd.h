@@ -178,10 +178,10 @@ int b200rmsd_allpairs_configure(int min_tc_frames, int max_refs);
 
 /* Tensor-core kernel geometry: cta_pair != 0 runs the GEMM on 2-CTA clusters -- the two SMs of a TPC share one
  * M = 256 tcgen05.mma (cta_group::2), each loading its own rows of A and half of the rows of B, which cuts the
- * L2 -> shared-memory operand traffic by a quarter (74.7 -> 54.9 GB per 20k x 20k matrix); 0 (the default) selects the
- * single-CTA kernel (M = 128).  Both produce bit-identical matrices.  The kernel is bound by its epilogue and the
- * tensor pipe, not by operand delivery, so the pair geometry measures 0-7 % SLOWER on one B200
- * and is kept as an option.  Process-wide; returns the previous setting. */
+ * L2 -> shared-memory operand traffic by a quarter (74.7 -> 54.9 GB per 20k x 20k matrix) and is the default; 0
+ * selects the single-CTA kernel (M = 128).  Both produce bit-identical matrices.  Measured on one B200, 20k x 20k x 300
+ * atoms: 5.63 vs 5.72 ms on iid frames, 5.31 vs 6.27 ms on MD-like frames (profiles/r02_ap_isolate_uni.jsonl; DESIGN.md
+ * section 8.4).  Process-wide; returns the previous setting. */
 int b200rmsd_allpairs_set_cta_pair(int cta_pair);
 
 /* What prepare found (synchronises `stream`): number of reference structures, number of frames stored as they are

@@ -25,7 +25,7 @@ namespace b200 {
 
 int g_ap_min_tc_frames = 512;
 int g_ap_max_refs = kApMaxRefs;
-int g_ap_cta_pair = 0;
+int g_ap_cta_pair = 1;
 
 // one warp per frame
 __global__ void __launch_bounds__(256) allpairs_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames,

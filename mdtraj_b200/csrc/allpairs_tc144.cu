@@ -11,16 +11,17 @@
 //              matrices of their own, add X'_i c_r^T to the blocks whose column frame refers to c_r, so that the
 //              accumulator holds X'_i D_j^T (fluctuation-sized) until the last K-steps -- the tensor core's fp32
 //              accumulation truncates, and the bias is proportional to the running sum (allpairs_tc144_prepare_kernel);
-//   tile       40 i-frames x 48 j-frames.  The A operand (M = 128 TMEM lanes) is brought by FOUR 32-row TMA boxes
-//              starting at rows 120*ti + 30*w, so that each epilogue warp's lane quarter holds 10 whole frames (lanes 30
-//              and 31 of a quarter carry the first rows of the next frame and are ignored); the B operand (N = 144
+//   tile       40 i-frames x 48 j-frames.  The A operand (M = 128 TMEM lanes) is four 32-row quarters starting at rows
+//              120*ti + 30*w, so that each epilogue warp's lane quarter holds 10 whole frames (lanes 30 and 31 of a
+//              quarter are zero-filled and ignored); the B operand (N = 144
 //              accumulator columns) is one 144-row box = 48 whole frames.  Columns are registers of the reading
 //              thread, so frames may sit at any column: each of the 16 epilogue warps takes 36 columns = 12 j-frames
 //              = 4 passes of 3 frames per lane triplet, every pass full (the 128-column layout of allpairs_tc.cu
 //              padded every 32 columns to 10 frames and left the fourth pass two-thirds empty: 1600 pairs per tile
 //              for the same epilogue passes that now deliver 1920);
-//   loads      cp.async.bulk.tensor.2d, SWIZZLE_128B, 3-stage shared-memory ring (68 KB per stage), mbarrier
-//              full/empty pipeline;
+//   loads      two cp.async.bulk.tensor copies per K block, SWIZZLE_128B: the A box (4-d: 32 floats x 32 rows x 4 quarters
+//              x {hi, lo}, see make_a_operand_map) and the B box (3-d: 32 floats x 144 rows x {hi, lo}); 3-stage
+//              shared-memory ring (68 KB per stage), mbarrier full/empty pipeline;
 //   MMA        one elected thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128 N=144 K=8, three per K-step
 //              (lo.hi, hi.lo, hi.hi: "3xTF32", the dropped lo.lo term is ~2^-22 relative) accumulating fp32 in TMEM;
 //              tcgen05.commit releases smem stages and publishes finished accumulators;
@@ -139,6 +140,16 @@ struct SlotWalk {
     }
 };
 
+// every wait of this kernel is long by design (a role whose next tile or stage is not ready): parked, not polled
+__device__ __forceinline__ void ap_wait(uint64_t* bar, uint32_t parity)
+{
+#ifdef B200RMSD_AP_WAIT_SPIN  // development: the polling wait, for A/B timings
+    mbar_wait(bar, parity);
+#else
+    mbar_wait_parked(bar, parity);
+#endif
+}
+
 __device__ __forceinline__ float sel3(int c, float a0, float a1, float a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
 
 }  // namespace
@@ -253,10 +264,9 @@ allpairs_tc144_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames, i
 // 36-column segments of the accumulator); NP in {1, 2}: independent solves interleaved per lane.
 template <int EPI_WARPS, int NP, bool PAIR>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
-allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                      const __grid_constant__ CUtensorMap map_g_a_hi, const __grid_constant__ CUtensorMap map_g_a_lo,
-                      const __grid_constant__ CUtensorMap map_g_b, const Tc144Params p)
+allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_g_a, const __grid_constant__ CUtensorMap map_g_b,
+                      const Tc144Params p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is not guaranteed to have it
@@ -270,7 +280,9 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     uint64_t* tempty = tfull + kAccStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: provably warp-uniform for the compiler, so that everything the two DMA/MMA
+    // roles derive from it lives in uniform registers (see the note at the MMA issuer)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // PAIR: rank of this CTA in its 2-CTA cluster (0 = leader: issues the MMAs, owns the full[] and tempty[] barriers
     // both CTAs signal); slots are walked per cluster
     const int rank = PAIR ? (int)cluster_ctarank() : 0;
@@ -289,14 +301,19 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
     else __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     // Warp roles: warps [0, EPI_WARPS) epilogue, warp EPI_WARPS = TMA producer, warp EPI_WARPS+1 = MMA issuer.
     // The two single-thread roles get the highest warp ids: the SMSP arbiter favours higher warp ids, and a late
     // TMA or MMA issue stalls the whole pipeline while a late epilogue instruction does not.
+    // Both roles run their loops with the WHOLE warp (uniform control flow, uniform values) and elect one lane only around
+    // the instructions that must be issued once.  Inside `if (lane == 0)` the compiler cannot keep descriptors and
+    // addresses in uniform registers, and wrapped every tcgen05.mma in a loop of ELECT + five R2UR.BROADCAST + votes:
+    // ~110 cycles of dependent scalar code per 72-cycle MMA -- the issuing thread, not the tensor pipe or the operand
+    // delivery, set the pace (ncu source page, round 2: 74 % of that warp's samples inside its own issue code).
     if (warp == EPI_WARPS) {
         // ===================================================== TMA producer
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0;
             // PAIR: both CTAs load (their A rows, their half of the B rows); every load's bytes are counted on the
@@ -304,47 +321,51 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             // leader has armed the phase: the transaction count just goes negative for a moment (the phase cannot
             // complete before the leader's own arrival), and never earlier than that, because the peer only refills a
             // stage after the commit of the MMAs that read it, i.e. after the leader's previous phase completed.
-            auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-                if (PAIR) tma_load_2d_pair(dst, map, bar, c0, c1);
-                else tma_load_2d(dst, map, bar, c0, c1);
+            // Two copies per stage: the A box (hi and lo planes, four 30-row quarters each) and the B box (hi and lo planes)
+            auto load_a = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int k0, int quarter) {
+                if (PAIR) tma_load_4d_pair(dst, map, bar, k0, 0, quarter, 0);
+                else tma_load_4d(dst, map, bar, k0, 0, quarter, 0);
+            };
+            auto load_b = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int k0, int row) {
+                if (PAIR) tma_load_3d_pair(dst, map, bar, k0, row, 0);
+                else tma_load_3d(dst, map, bar, k0, row, 0);
+            };
+            auto load_b1 = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int k0, int row) {  // single plane
+                if (PAIR) tma_load_2d_pair(dst, map, bar, k0, row);
+                else tma_load_2d(dst, map, bar, k0, row);
             };
             for (SlotWalk w(slot0, (int)slot_step, p); w.t < p.n_slots; w.next(p)) {
                 int ti, tj;
                 if (!w.tile(p, ti, tj)) continue;
                 ti += rank;
-                const int a_row = ti * (3 * kIFrames), b_row = tj * kN + rank * (kN / 2);
+                const int a_quarter = ti * 4, b_row = tj * kN + rank * (kN / 2);  // quarter q = rows 30q .. 30q+29
                 for (int kb = 0; kb < p.nk; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1u);
+                    ap_wait(&empty[stage], phase ^ 1u);
                     unsigned char* st = smem + stage * kStageN;
-                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], PAIR ? 2 * kStageN : kStageN);
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {  // lane quarter w <- rows of frames 10w .. 10w+9 (+2 ignored rows)
-                        load(st + w * kQuarterBytes, &map_a_hi, &full[stage], kb * kK, a_row + 30 * w);
-                        load(st + kABytes + w * kQuarterBytes, &map_a_lo, &full[stage], kb * kK, a_row + 30 * w);
+                    if (elect_one_sync()) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], PAIR ? 2 * kStageN : kStageN);
+                        load_a(st, &map_a, &full[stage], kb * kK, a_quarter);
+                        load_b(st + 2 * kABytes, &map_b, &full[stage], kb * kK, b_row);
                     }
-                    load(st + 2 * kABytes, &map_b_hi, &full[stage], kb * kK, b_row);
-                    load(st + 2 * kABytes + kBBytesN, &map_b_lo, &full[stage], kb * kK, b_row);
                     if (++stage == kRingN) { stage = 0; phase ^= 1u; }
                 }
                 // augmentation K blocks of the references this tile's column frames are stored against (no B_lo part)
                 const int2 aug = __ldg(p.tile_aug + tj);
                 for (int g = aug.x; g <= aug.y; ++g) {
-                    mbar_wait(&empty[stage], phase ^ 1u);
+                    ap_wait(&empty[stage], phase ^ 1u);
                     unsigned char* st = smem + stage * kStageN;
-                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], (PAIR ? 2 : 1) * (kStageN - kBBytesN));
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        load(st + w * kQuarterBytes, &map_g_a_hi, &full[stage], g * kK, a_row + 30 * w);
-                        load(st + kABytes + w * kQuarterBytes, &map_g_a_lo, &full[stage], g * kK, a_row + 30 * w);
+                    if (elect_one_sync()) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], (PAIR ? 2 : 1) * (kStageN - kBBytesN));
+                        load_a(st, &map_g_a, &full[stage], g * kK, a_quarter);
+                        load_b1(st + 2 * kABytes, &map_g_b, &full[stage], g * kK, b_row);
                     }
-                    load(st + 2 * kABytes, &map_g_b, &full[stage], g * kK, b_row);
                     if (++stage == kRingN) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == EPI_WARPS + 1) {
         // ===================================================== MMA issuer
-        if (lane == 0 && rank == 0) {  // PAIR: the leader issues the M = 256 MMAs for both CTAs
+        if (rank == 0) {  // PAIR: the leader issues the M = 256 MMAs for both CTAs
             constexpr uint32_t idesc = make_tf32_idesc(PAIR ? 2 * kM : kM, kN);
             auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc_flag) {
                 if (PAIR) umma_tf32_pair(d, a, b, idesc, acc_flag);
@@ -361,47 +382,52 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             for (SlotWalk w(slot0, (int)slot_step, p); w.t < p.n_slots; w.next(p)) {
                 int ti_unused, tj;
                 if (!w.tile(p, ti_unused, tj)) continue;
-                mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                ap_wait(&tempty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
                 for (int kb = 0; kb < p.nk; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    ap_wait(&full[stage], phase);
                     tc_fence_after();
                     bool continue_mma = true;
                     unsigned char* st = smem + stage * kStageN;
                     const uint64_t a_hi = make_sw128_kmajor_desc(st), a_lo = make_sw128_kmajor_desc(st + kABytes);
                     const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * kABytes),
                                    b_lo = make_sw128_kmajor_desc(st + 2 * kABytes + kBBytesN);
-#pragma unroll
 #ifdef B200RMSD_DEV_SWITCHES
                     if (p.flags & 0x200u) continue_mma = false;  // development: skip the MMAs (operand delivery alone)
 #endif
-                    for (int ks = 0; ks < (continue_mma ? kK / 8 : 0); ++ks) {
-                        const uint64_t off = (uint64_t)(ks * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
-                        mma(d_tmem, a_lo + off, b_hi + off, (kb | ks) != 0 ? 1u : 0u);
-                        mma(d_tmem, a_hi + off, b_lo + off, 1u);
-                        mma(d_tmem, a_hi + off, b_hi + off, 1u);
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int ks = 0; ks < kK / 8; ++ks) {
+                            if (!continue_mma) break;
+                            const uint64_t off = (uint64_t)(ks * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
+                            mma(d_tmem, a_lo + off, b_hi + off, (kb | ks) != 0 ? 1u : 0u);
+                            mma(d_tmem, a_hi + off, b_lo + off, 1u);
+                            mma(d_tmem, a_hi + off, b_hi + off, 1u);
+                        }
+                        commit(&empty[stage]);  // frees this smem stage when the MMAs above have read it
                     }
-                    commit(&empty[stage]);  // frees this smem stage when the MMAs above have read it
                     if (++stage == kRingN) { stage = 0; phase ^= 1u; }
                 }
                 const int2 aug = __ldg(p.tile_aug + tj);
                 for (int g = aug.x; g <= aug.y; ++g) {  // + X'_i c_r^T for the four references of block g: (g1 + g2 + g3) . e
-                    mbar_wait(&full[stage], phase);
+                    ap_wait(&full[stage], phase);
                     tc_fence_after();
                     unsigned char* st = smem + stage * kStageN;
                     const uint64_t a_hi = make_sw128_kmajor_desc(st), a_lo = make_sw128_kmajor_desc(st + kABytes);
                     const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * kABytes);
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int ks = 0; ks < kK / 8; ++ks) {
-                        const uint64_t off = (uint64_t)(ks * 2);
-                        mma(d_tmem, a_lo + off, b_hi + off, 1u);
-                        mma(d_tmem, a_hi + off, b_hi + off, 1u);
+                        for (int ks = 0; ks < kK / 8; ++ks) {
+                            const uint64_t off = (uint64_t)(ks * 2);
+                            mma(d_tmem, a_lo + off, b_hi + off, 1u);
+                            mma(d_tmem, a_hi + off, b_hi + off, 1u);
+                        }
+                        commit(&empty[stage]);
                     }
-                    commit(&empty[stage]);
                     if (++stage == kRingN) { stage = 0; phase ^= 1u; }
                 }
-                commit(&tfull[acc]);             // accumulator complete (both CTAs' epilogues)
+                if (elect_one_sync()) commit(&tfull[acc]);  // accumulator complete (both CTAs' epilogues)
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -423,7 +449,7 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             const int64_t fi = (int64_t)ti * kIFrames + ew * 10 + tq;  // row frame of this lane
             const bool i_ok = row_valid && fi >= p.row0 && fi < p.row1;
             const float Gi = i_ok ? __ldg(p.traces + fi) : 1.0f;
-            mbar_wait(&tfull[acc], acc_phase);
+            ap_wait(&tfull[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < kSegsPerWarp; ++cc) {
@@ -444,38 +470,30 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                     int64_t fj[NP];
                     bool ok[NP], trusted[NP];
                     // column 9*jg + 3*m + q of the segment = (this lane's row) . (component q of j-frame 3*jg + m).
-                    // Lane (tq, c) ends up with rows (c, c+1, c+2) mod 3 of the block of pair (i_tq, j-frame 3*jg + c):
-                    // a cyclic permutation of x,y,z = a proper rotation of frame i, which leaves the RMSD unchanged.
+                    // Lane (tq, c) ends up with the block of pair (i_tq, j-frame 3*jg + c) as m[3r + q] =
+                    // M[(c+r)%3][(c+q)%3]: rows AND columns in the cyclic order starting at the lane's own component.
+                    // That relabels the axes of both frames the same way (x,y,z -> y,z,x is a proper rotation applied to
+                    // both), so the key matrix keeps its eigenvalues, tr M and the common orientation the shifted solver
+                    // relies on -- and every entry costs ONE lane-dependent select: in round r the lane that holds row
+                    // (c+r)%3 publishes the entry of the j-frame its reader works on, already at its permuted column.
                     // Warp-collective (shuffles).
                     auto gather = [&](int jg, float (&m)[9]) {
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
-                            const float m0 = __uint_as_float(r[9 * jg + q]);
-                            const float m1 = __uint_as_float(r[9 * jg + 3 + q]);
-                            const float m2 = __uint_as_float(r[9 * jg + 6 + q]);
-                            m[q] = sel3(c, m0, m1, m2);
-                            const float send1 = sel3(c, m2, m0, m1);  // for the reader whose component is (c+2)%3
-                            const float send2 = sel3(c, m1, m2, m0);  // for the reader whose component is (c+1)%3
+                            const float e0 = __uint_as_float(r[9 * jg + q]);                    // j-frame 0, column q
+                            const float e1 = __uint_as_float(r[9 * jg + 3 + (q + 1) % 3]);      // j-frame 1, column q+1
+                            const float e2 = __uint_as_float(r[9 * jg + 6 + (q + 2) % 3]);      // j-frame 2, column q+2
+                            m[q] = sel3(c, e0, e1, e2);
+                            const float send1 = sel3(c, e2, e0, e1);  // for the reader whose component is (c+2)%3
+                            const float send2 = sel3(c, e1, e2, e0);  // for the reader whose component is (c+1)%3
                             m[3 + q] = __shfl_sync(0xffffffffu, send1, src1);
                             m[6 + q] = __shfl_sync(0xffffffffu, send2, src2);
-                        }
-                    };
-                    // the same block with its rows in the order x, y, z: the shifted solver (qcp_msd_shift) relies on
-                    // frame i and frame j sharing an orientation, which the cyclic permutation above would undo
-                    auto gather_xyz = [&](int jg, float (&m)[9]) {
-                        float t[9];
-                        gather(jg, t);
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            m[q] = sel3(c, t[q], t[6 + q], t[3 + q]);
-                            m[3 + q] = sel3(c, t[3 + q], t[q], t[6 + q]);
-                            m[6 + q] = sel3(c, t[6 + q], t[3 + q], t[q]);
                         }
                     };
 #pragma unroll
                     for (int u = 0; u < NP; ++u) {
                         const int jg = NP * jp + u;
-                        gather_xyz(jg, M[u]);
+                        gather(jg, M[u]);
                         fj[u] = (int64_t)tj * kJFrames + seg * 12 + 3 * jg + c;
                         ok[u] = i_ok && fj[u] >= p.col0 && fj[u] < p.col1;
                         Ga[u] = ok[u] ? __ldg(p.traces + fj[u]) : 1.0f;
@@ -630,14 +648,11 @@ int launch_allpairs_tc144_block(const ApGeometry& g, const char* base, int n_sel
     if (const char* v = getenv("B200RMSD_TC_PAIR")) pair = atoi(v) != 0 && sm_count >= 2;
 #endif
     const int b_box = pair ? kN / 2 : kN;  // CTA-pair mode: each CTA loads half of the B rows of a j-tile
-    CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo, map_g_a_hi, map_g_a_lo, map_g_b;
+    CUtensorMap map_a, map_b, map_g_a, map_g_b;
     auto op = [&](size_t off) { return (const float*)(base + off); };
-    if (!make_operand_map(&map_a_hi, op(g.a_hi_off), g.rows_pad, g.k_pad, 32) ||
-        !make_operand_map(&map_a_lo, op(g.a_lo_off), g.rows_pad, g.k_pad, 32) ||
-        !make_operand_map(&map_b_hi, op(g.b_hi_off), g.rows_pad, g.k_pad, b_box) ||
-        !make_operand_map(&map_b_lo, op(g.b_lo_off), g.rows_pad, g.k_pad, b_box) ||
-        !make_operand_map(&map_g_a_hi, op(g.aug_a_hi_off), g.rows_pad, kApAugCols, 32) ||
-        !make_operand_map(&map_g_a_lo, op(g.aug_a_lo_off), g.rows_pad, kApAugCols, 32) ||
+    if (!make_a_operand_map(&map_a, op(g.a_hi_off), g.rows_pad, g.k_pad, g.a_lo_off - g.a_hi_off) ||
+        !make_b_operand_map(&map_b, op(g.b_hi_off), g.rows_pad, g.k_pad, b_box, g.b_lo_off - g.b_hi_off) ||
+        !make_a_operand_map(&map_g_a, op(g.aug_a_hi_off), g.rows_pad, kApAugCols, g.aug_a_lo_off - g.aug_a_hi_off) ||
         !make_operand_map(&map_g_b, op(g.aug_b_off), g.rows_pad, kApAugCols, b_box))
         return set_error(B200RMSD_ECUDA, "allpairs: cuTensorMapEncodeTiled failed");
     Tc144Params p = tc144_tiling(row0, row1, col0, col1, out_t != nullptr, pair);
@@ -680,7 +695,7 @@ int launch_allpairs_tc144_block(const ApGeometry& g, const char* base, int n_sel
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                            \
         cfg.blockDim = dim3(64 + 32 * EW);                                                                                 \
         if (e == cudaSuccess)                                                                                              \
-            e = cudaLaunchKernelEx(&cfg, kern, map_a_hi, map_a_lo, map_b_hi, map_b_lo, map_g_a_hi, map_g_a_lo, map_g_b, p); \
+            e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_g_a, map_g_b, p);                                        \
     } while (0)
 #ifdef B200RMSD_DEV_SWITCHES
     if (ew == 8 && np == 2) B200_LAUNCH_TC144(8, 2, false);

@@ -50,6 +50,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// The same wait with a suspend-time hint: the thread is parked until the phase completes (or the hint, in nanoseconds,
+// runs out) instead of coming back every ~100 cycles.  For waits that are long by design -- a warp whose next tile is not
+// ready: in the all-pairs kernel the polling loops were 16 % of all issued instructions, on the schedulers the
+// epilogue warps need.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+    } while (!ok);
+}
 
 // generic-proxy accesses before this point are ordered before later async-proxy
 // (bulk copy) accesses to the same shared memory

@@ -367,7 +367,7 @@ __device__ __forceinline__ void two_sum(float a, float b, float& s, float& e)
 //
 // Numpy emulation of exactly this arithmetic: pre-aligned MD-like pairs 3e-8 nm from the
 // float64 eigenvalue (the float64-polished route: 1e-6 class, float32 route of the reference: 1e-5), iid pairs 2.5e-7.
-// Newton from the upper bound of delta (monotone, as for lambda); 3-4 steps on pre-aligned pairs.
+// Laguerre's iteration from the upper bound of delta (monotone, as Newton's is for lambda); 2-3 steps on pre-aligned pairs.
 //
 // trusted[] = false where float32 is not enough: pairs that are similar but NOT in a common orientation (delta large
 // against S - lambda: the estimated root error 4e-7 * sum|terms| / P'(delta) exceeds the tolerance), and (nearly) double
@@ -422,25 +422,37 @@ __device__ __forceinline__ void qcp_msd_shift(const float (&M)[NP][9], const flo
         e0[p] = h4 + (((l1 - l2) - l3) + l4);
         d[p] = fmaxf(ub * s1 - T, 0.0f) + 4e-6f;  // upper bound of delta
     }
+    // Laguerre's iteration (degree 4) from the upper bound: for a polynomial whose roots are all real -- the key matrix
+    // is symmetric -- the iterates fall monotonically onto the largest root like Newton's, but the first step from far
+    // away already lands next to it and convergence is cubic:
+    //     x <- x - 4 P / (P' + sqrt(9 P'^2 - 24 P P''/2 ... )) = x - 4 P / (P' + 3 sqrt(P'^2 - (8/3) P (P''/2))).
+    // float32 emulation on 20 000 pairs (300 atoms): iid frames 2.7 steps on average, 4.1 for the slowest of the 64 pairs
+    // a warp carries (Newton: 6.4, and 12 for the slowest: every lane waits for it); pre-aligned MD-like pairs 2.
+    // A step of <= 1e-3 relative leaves an error of ~1e-9; a step <= 0 means P <= 0 at the iterate: rounding noise,
+    // nothing left to gain (the certificate below evaluates the polynomial once more at the final iterate either way).
+    auto laguerre = [&](int p) -> bool {
+        const float x = d[p];
+        const float b3 = x + p3[p];
+        const float b2 = fmaf(b3, x, p2[p]);
+        const float b1 = fmaf(b2, x, p1[p]);
+        const float val = fmaf(b1, x, p0[p]);
+        const float c3 = b3 + x;
+        const float c2 = fmaf(c3, x, b2);
+        const float den = fmaf(c2, x, b1);           // P'
+        const float hc = fmaf(c3 + x, x, c2);        // P'' / 2
+        const float disc = fmaxf(fmaf(-2.6666667f * val, hc, den * den), 0.0f);
+        const float dd = fmaf(3.0f, sqrt_approx(disc), den);
+        const float step = (fabsf(dd) > 1e-30f) ? 4.0f * val * rcp_approx(dd) : 0.0f;
+        d[p] = x - step;
+        return step <= fmaf(1e-3f, fabsf(d[p]), 1e-9f);
+    };
+#pragma unroll
+    for (int p = 0; p < NP; ++p) laguerre(p);
 #pragma unroll 1
-    for (int it = 0; it < 10; ++it) {  // two steps per trip: half the votes and branches on the dependency chain
+    for (int it = 0; it < 12; ++it) {
         bool conv = true;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                const float x = d[p];
-                const float b3 = x + p3[p];
-                const float b2 = fmaf(b3, x, p2[p]);
-                const float b1 = fmaf(b2, x, p1[p]);
-                const float val = fmaf(b1, x, p0[p]);
-                const float c2 = fmaf(b3 + x, x, b2);
-                const float den = fmaf(c2, x, b1);
-                const float step = (fabsf(den) > 1e-30f) ? val * rcp_approx(den) : 0.0f;
-                d[p] = x - step;
-                if (half == 1) conv = conv && (!active[p] || fabsf(step) <= fmaf(2e-7f, fabsf(d[p]), 1e-9f));
-            }
-        }
+        for (int p = 0; p < NP; ++p) conv = (laguerre(p) || !active[p]) && conv;  // idle lanes must not hold the warp back
         if (__all_sync(0xffffffffu, conv)) break;  // warp-uniform exit: no divergence inside the loop
     }
 #pragma unroll

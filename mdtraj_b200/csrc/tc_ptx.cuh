@@ -9,12 +9,36 @@
 namespace b200 {
 
 // ---- tcgen05 / TMA PTX wrappers -------------------------------------------------------------
+// one lane of the (converged) warp: the idiom that lets a warp-uniform loop issue single-thread instructions
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
 {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols)
@@ -65,6 +89,23 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                 int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols)
@@ -177,6 +218,37 @@ inline bool make_operand_map(CUtensorMap* map, const float* base, int64_t rows, 
     const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// The A operand of a 40-frame i-tile in ONE copy: the hi and lo matrices (two allocations `plane_bytes` apart) seen as
+// a 4-d tensor (k, row within a 30-row quarter, quarter, plane).  A box of 32 x 32 x 4 x 2 lands as
+// [plane][quarter][32 rows][128 bytes]: quarter w of plane h at h * 16 KB + w * 4 KB, rows 30 and 31 of every quarter
+// zero-filled (they are past the end of the 30-row dimension) -- the layout the four 32-row boxes per plane produced,
+// for one TMA instruction instead of eight.
+inline bool make_a_operand_map(CUtensorMap* map, const float* base_hi, int64_t rows, int k_pad, size_t plane_bytes)
+{
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)k_pad, 30u, (cuuint64_t)(rows / 30), 2u};
+    const cuuint64_t strides[3] = {(cuuint64_t)k_pad * 4, (cuuint64_t)k_pad * 4 * 30, (cuuint64_t)plane_bytes};
+    const cuuint32_t box[4] = {32u, 32u, 4u, 2u};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base_hi), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// The B operand of a j-tile in one copy: (k, row, plane), box 32 x box_rows x 2 -> [plane][box_rows][128 bytes]
+inline bool make_b_operand_map(CUtensorMap* map, const float* base_hi, int64_t rows, int k_pad, int box_rows, size_t plane_bytes)
+{
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)k_pad, (cuuint64_t)rows, 2u};
+    const cuuint64_t strides[2] = {(cuuint64_t)k_pad * 4, (cuuint64_t)plane_bytes};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 2u};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base_hi), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

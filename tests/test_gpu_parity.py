@@ -1014,6 +1014,6 @@ def test_allpairs_cta_pair_geometry_is_bit_identical(mdb, oracle_mod):
                 blk = AP.rows(prep, 41, 41 + 333).clone()
                 got[pair] = (full, blk)
         finally:
-            AP.configure(cta_pair=False)
+            AP.configure(cta_pair=True)
         assert torch.equal(got[False][0], got[True][0]) and torch.equal(got[False][1], got[True][1])
         assert torch.isfinite(got[True][0]).all()
