@@ -37,12 +37,13 @@ namespace b200 {
 __device__ long long* g_fr_trace = nullptr;
 #define FR_STAMP(i, k) do { if (g_fr_trace && blockIdx.x == 0) g_fr_trace[(i) * 8 + (k)] = clock64(); } while (0)
 
+extern int g_fr_pipe_min_bytes;
 constexpr int kFrWarps = 16;                      // compute warps
 constexpr int kFrThreads = kFrWarps * 32 + 64;    // + loader warp + storer warp
 constexpr int kRecStride = 25;  // floats per frame record (odd: the solver lanes read one record each, conflict-free)
 
 struct FrLayout {
-    size_t buf_off, ref_off, idx_off, rec_off, dsum_off, cpart_off, bar_off, total;
+    size_t buf_off, ref_off, idx_off, rec_off, dsum_off, cpart_off, bar_off, rs_off, total;
     size_t buf_bytes;
 };
 __host__ __device__ inline size_t fr_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -62,7 +63,8 @@ __host__ __device__ inline FrLayout fr_layout(int n_pad, int nbuf, int n_sel_pad
     L.dsum_off = fr_align(L.rec_off + (records ? (size_t)G * fpb * team_warps * kRecStride * sizeof(float) : 0), 8);
     L.cpart_off = L.dsum_off + (records && team_warps > 1 ? (size_t)G * fpb * 16 * sizeof(double) : 0);
     L.bar_off = L.cpart_off + (size_t)kFrWarps * 4 * sizeof(double);
-    L.total = L.bar_off + (size_t)(3 * nbuf + 1) * sizeof(uint64_t);
+    L.rs_off = L.bar_off + (size_t)(3 * nbuf + 1) * sizeof(uint64_t);  // RefStats copy (OP_SUPERPOSE)
+    L.total = L.rs_off + 64;
     return L;
 }
 
@@ -103,6 +105,58 @@ __device__ __forceinline__ double lanes_sum(double x, int L)  // all-reduce over
     return x;
 }
 
+
+// One frame of a slot: sums record -> RMSD, rotation and the transform record of xf_atom, by one lane.
+// rec_f: the frame's float32 record (sums 0..12, pivot 13..15) or nullptr when rec_d holds the float64 sums of several
+// warps; t: where the 15 floats of the transform go -- the frame's own (first) record, so everything needed from the
+// sums is read before the first write.  The centroid and the pivot are read a second time after the solve instead of
+// being carried across it, and the reference's statistics stay in shared memory: the QCP solve needs ~90 registers of
+// float64 on its own, and what it pushed to local memory was re-read at L2 latency in the middle of a 6700-cycle chain
+// (tools/fused_trace.py; ncu: local loads with a 48 % L1 hit rate).
+__device__ __forceinline__ void fr_solve_frame(const float* rec_f, const double* rec_d, float* t, const RefStats* rs_s,
+                                               double invn, int64_t f, const FusedParams& p)
+{
+    auto sum = [&](int q) -> double { return rec_f ? (double)rec_f[q] : rec_d[q]; };
+    float R[9];
+    {
+        const double s0 = sum(0), s1 = sum(1), s2 = sum(2);
+        const double mx = s0 * invn, my = s1 * invn, mz = s2 * invn;
+        const double r0 = rs_s->sum[0], r1 = rs_s->sum[1], r2 = rs_s->sum[2];
+        QcpInput q;
+        q.inv_n = invn;
+        q.Gb = rs_s->G;
+        const double ga = sum(3) - (s0 * mx + s1 * my + s2 * mz);
+        q.Ga = ga > 0.0 ? ga : 0.0;
+        q.M[0] = sum(4) - mx * r0;  q.M[1] = sum(5) - mx * r1;  q.M[2] = sum(6) - mx * r2;
+        q.M[3] = sum(7) - my * r0;  q.M[4] = sum(8) - my * r1;  q.M[5] = sum(9) - my * r2;
+        q.M[6] = sum(10) - mz * r0; q.M[7] = sum(11) - mz * r1; q.M[8] = sum(12) - mz * r2;
+        bool degen = false;
+        const double msd = qcp_solve(q, R, &degen);
+        if (p.out_rmsd) p.out_rmsd[f] = sqrtf((float)msd);
+        if (degen && p.degenerate) atomicAdd(p.degenerate, 1u);
+    }
+    if (p.out_rot) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) p.out_rot[f * 9 + c] = R[c];
+    }
+    // centroid = pivot + mean shift, split into a float32 part (subtracted per atom) and a float64 remainder
+    double clo[3];
+    float chi[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double cen = sum(13 + c) + sum(c) * invn;
+        chi[c] = (float)cen;
+        clo[c] = cen - (double)chi[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) t[c] = R[c];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        t[9 + c] = chi[c];
+        t[12 + c] = (float)(rs_s->mean[c] - (clo[0] * (double)R[c] + clo[1] * (double)R[3 + c] + clo[2] * (double)R[6 + c]));
+    }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const FusedParams p)
 {
@@ -136,9 +190,11 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
 
     unsigned long long t_start_ns = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
+    RefStats* rs_s = reinterpret_cast<RefStats*>(smem + L.rs_off);
     if (tid == 0) {
         for (int i = 0; i < p.nbuf; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], 1); mbar_init(&drained[i], 1); }
         mbar_init(ref_bar, 1);
+        if (OP == OP_SUPERPOSE) *rs_s = *p.ref_stats;
     }
     fence_mbar_init();
     __syncthreads();
@@ -226,11 +282,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
     const int ttid = tw > 1 ? ts * 32 + lane : lane - sj * Lt, tthreads = tw > 1 ? tw * 32 : Lt;
     if (OP == OP_SUPERPOSE && p.idx)
         for (int k = tid; k < p.n_sel; k += n_cw * 32) idx_s[k] = __ldg(p.idx + k);
-    RefStats rs{};
-    if (OP == OP_SUPERPOSE) {
-        rs = *p.ref_stats;
-        mbar_wait(ref_bar, 0);
-    }
+    if (OP == OP_SUPERPOSE) mbar_wait(ref_bar, 0);
     asm volatile("bar.sync 0, %0;" ::"r"(n_cw * 32) : "memory");  // idx_s visible to all compute warps
 
 #pragma unroll 1
@@ -309,48 +361,9 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
             if (gtid < cnt) {
                 if (gtid == 0) FR_STAMP(s, 1);
                 const int j = gtid;
-                const int64_t f = fbase + j;
-                double rec[16];
-                if (tw > 1) {
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) rec[q] = dsum_s[((size_t)g * fpb + j) * 16 + q];
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) rec[q] = (double)rec_all[((size_t)g * fpb + j) * kRecStride + q];
-                }
-                const double invn = p.inv_n_sel;
-                const double mx = rec[0] * invn, my = rec[1] * invn, mz = rec[2] * invn;
-                QcpInput q;
-                q.inv_n = invn;
-                q.Gb = rs.G;
-                const double ga = rec[3] - (rec[0] * mx + rec[1] * my + rec[2] * mz);
-                q.Ga = ga > 0.0 ? ga : 0.0;
-                q.M[0] = rec[4] - mx * rs.sum[0];  q.M[1] = rec[5] - mx * rs.sum[1];  q.M[2] = rec[6] - mx * rs.sum[2];
-                q.M[3] = rec[7] - my * rs.sum[0];  q.M[4] = rec[8] - my * rs.sum[1];  q.M[5] = rec[9] - my * rs.sum[2];
-                q.M[6] = rec[10] - mz * rs.sum[0]; q.M[7] = rec[11] - mz * rs.sum[1]; q.M[8] = rec[12] - mz * rs.sum[2];
-                float R[9];
-                bool degen = false;
-                const double msd = qcp_solve(q, R, &degen);
-                if (p.out_rmsd) p.out_rmsd[f] = sqrtf((float)msd);
-                if (p.out_rot) {
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) p.out_rot[f * 9 + c] = R[c];
-                }
-                if (degen && p.degenerate) atomicAdd(p.degenerate, 1u);
-                float* t = rec_all + ((size_t)g * fpb + j) * tw * kRecStride;  // every partial of this frame has been read
-#pragma unroll
-                for (int c = 0; c < 9; ++c) t[c] = R[c];
-                const double cen[3] = {rec[13] + mx, rec[14] + my, rec[15] + mz};
-                double clo[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float h = (float)cen[c];
-                    t[9 + c] = h;
-                    clo[c] = cen[c] - (double)h;
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    t[12 + c] = (float)(rs.mean[c] - (clo[0] * (double)R[c] + clo[1] * (double)R[3 + c] + clo[2] * (double)R[6 + c]));
+                float* rec0 = rec_all + ((size_t)g * fpb + j) * tw * kRecStride;   // the frame's first record
+                fr_solve_frame(tw > 1 ? nullptr : rec0, dsum_s + ((size_t)g * fpb + j) * 16, rec0, rs_s, p.inv_n_sel,
+                               fbase + j, p);
                 if (gtid == 0) FR_STAMP(s, 2);
             }
             group_sync(g, wpf);
@@ -465,6 +478,322 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_resident_kernel(const Fus
     if (self_dma && gtid == 0) bulk_wait<0>();
 }
 
+
+// =====================================================================================================================
+// Stage-pipelined superpose.  The ring kernel above gives every slot to ONE group of 1-2 warps from arrival to hand-over:
+// a 25 KB slot then sits in shared memory for ~19 500 cycles (tools/fused_trace.py, N = 300: load 3800, sums 2800, the
+// float64 solve 6700 with the group's other warp idle at its barrier, transform 4400, store 1300) while the HBM rate
+// only allows 8 x 2200, and everything but N = 500 / 1000 / 3000 stayed at 0.78 of peak.  Here the stages of a slot are
+// taken by different warps, so that the streaming stages cost a slot ~1/8 of that time and nobody waits for a solve:
+//
+//   loader (warp 16)        bulk load slot s into buffer s % nbuf as soon as it is drained               -> full[b]
+//   streaming warps 0..T-1  ALL of them on one slot at a time: sums of slot i (one lane group or W warps per frame)
+//                           -> reduced[b]; then the transform of slot i - depth, whose solve has finished meanwhile
+//                           (waits on solved[b])                                                         -> done[b]
+//   solver warps T..15      warp v takes slots v, v + S, ...: one lane per frame, float64 QCP solve + transform record
+//                           (waits on reduced[b])                                                        -> solved[b]
+//   storer (warp 17)        bulk store, then drained[b] once the copy has read the buffer
+//
+// A buffer is in flight to or from HBM, in one of the two short streaming stages, or waiting for its solve; `depth`
+// slots are between the sums and the transform, S solver warps work on different slots at once (S ~ solve latency /
+// slot period + 1: 8 for 22-atom frames where the solves dominate, 3 for 2000 atoms).
+// mbarrier parity: the streaming warps, the loader and the storer see every phase of every barrier they wait on, in
+// order.  A solver warp only waits on the slots it owns; the phase before one of those was completed by the streaming
+// warps before they completed the solver's previous slot (slots are reduced in order and nbuf >= S), and the phase after
+// it cannot start before the solver has finished (the buffer is not reloaded until its slot is stored).
+// =====================================================================================================================
+constexpr int kPipeMaxFrames = 32;  // frames per slot: one solver lane each
+
+struct PipeLayout {
+    size_t buf_off, ref_off, idx_off, rec_off, dsum_off, bar_off, rs_off, total;
+    size_t buf_bytes;
+};
+// rec: per buffer and frame, W records of kRecStride floats (partial sums per streaming warp of the frame; the first
+// one is overwritten with the frame's transform by its solver lane); dsum: W > 1 only, the partials added in float64
+__host__ __device__ inline PipeLayout pipe_layout(int n_pad, int nbuf, int n_sel_pad, int n_idx, int fpb, int W)
+{
+    PipeLayout L;
+    L.buf_bytes = (size_t)n_pad * 12 * fpb;
+    L.buf_off = 0;
+    L.ref_off = fr_align((size_t)nbuf * L.buf_bytes, 128);
+    L.idx_off = L.ref_off + fr_align((size_t)n_sel_pad * 12, 16);
+    L.rec_off = fr_align(L.idx_off + (size_t)n_idx * 4, 16);
+    L.dsum_off = fr_align(L.rec_off + (size_t)nbuf * fpb * W * kRecStride * sizeof(float), 8);
+    L.bar_off = L.dsum_off + (W > 1 ? (size_t)nbuf * fpb * 16 * sizeof(double) : 0);
+    L.rs_off = L.bar_off + (size_t)(5 * nbuf + 1) * sizeof(uint64_t);  // RefStats copy
+    L.total = L.rs_off + 64;
+    return L;
+}
+
+__global__ void __launch_bounds__(kFrThreads, 1) superpose_pipe_kernel(const FusedParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int n_sel_pad = (p.n_sel + 3) & ~3;
+    const int S = p.batch, T = kFrWarps - S, D = p.depth, W = p.team_warps, fpb = p.fpb, nbuf = p.nbuf;
+    const PipeLayout L = pipe_layout(p.n_pad, nbuf, n_sel_pad, p.idx ? p.n_sel : 0, fpb, W);
+    const float* ref_s = reinterpret_cast<const float*>(smem + L.ref_off);
+    int* idx_s = reinterpret_cast<int*>(smem + L.idx_off);
+    float* rec_all = reinterpret_cast<float*>(smem + L.rec_off);
+    double* dsum_s = reinterpret_cast<double*>(smem + L.dsum_off);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint64_t* reduced = full + nbuf;
+    uint64_t* solved = reduced + nbuf;
+    uint64_t* done = solved + nbuf;
+    uint64_t* drained = done + nbuf;
+    uint64_t* ref_bar = drained + nbuf;
+
+    // warp-uniform by construction (a shuffle), so that the DMA warps' loops stay on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int units = p.n_pad >> 2;
+    const uint32_t frame_bytes = (uint32_t)p.n_pad * 12u;
+    const int frame_floats = p.n_pad * 3;
+    const int64_t f0 = p.n_frames * blockIdx.x / gridDim.x, f1 = p.n_frames * (blockIdx.x + 1) / gridDim.x;
+    const int64_t n = f1 - f0;
+    const int n_slots = (int)((n + fpb - 1) / fpb);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nbuf; ++i) {
+            mbar_init(&full[i], 1); mbar_init(&reduced[i], T); mbar_init(&solved[i], 1); mbar_init(&done[i], T);
+            mbar_init(&drained[i], 1);
+        }
+        mbar_init(ref_bar, 1);
+        *reinterpret_cast<RefStats*>(smem + L.rs_off) = *p.ref_stats;
+    }
+    fence_mbar_init();
+    __syncthreads();
+
+    // ================================================================== loader
+    if (warp == kFrWarps) {
+        if (elect_one_sync()) {
+            const uint32_t bytes = (uint32_t)n_sel_pad * 12u;
+            mbar_arrive_expect_tx(ref_bar, bytes);
+            bulk_g2s(smem + L.ref_off, p.ref, bytes, ref_bar);
+        }
+        for (int s = 0; s < n_slots; ++s) {
+            const int buf = s % nbuf;
+            if (s >= nbuf) mbar_wait(&drained[buf], (uint32_t)(((s / nbuf) - 1) & 1));
+            if (elect_one_sync()) {
+                const int64_t left = n - (int64_t)s * fpb;
+                const uint32_t bytes = (uint32_t)(left < fpb ? left : fpb) * frame_bytes;
+                mbar_arrive_expect_tx(&full[buf], bytes);
+                bulk_g2s(smem + L.buf_off + (size_t)buf * L.buf_bytes, p.xyz + (f0 + (int64_t)s * fpb) * p.frame_stride, bytes,
+                         &full[buf]);
+            }
+        }
+        return;
+    }
+    // ================================================================== storer
+    if (warp == kFrWarps + 1) {
+        // up to K stores in flight: store s is issued, then the storer waits until store s-K has been read out of its
+        // buffer and publishes that buffer (see the ring kernel above)
+        int K = nbuf - D - 3;
+        K = K < 0 ? 0 : (K > 3 ? 3 : K);
+        for (int s = 0; s < n_slots; ++s) {
+            const int buf = s % nbuf;
+            mbar_wait(&done[buf], (uint32_t)((s / nbuf) & 1));
+            if (elect_one_sync()) {
+                const int64_t left = n - (int64_t)s * fpb;
+                const uint32_t bytes = (uint32_t)(left < fpb ? left : fpb) * frame_bytes;
+                bulk_s2g(p.xyz + (f0 + (int64_t)s * fpb) * p.frame_stride, smem + L.buf_off + (size_t)buf * L.buf_bytes, bytes);
+                bulk_commit();
+                switch (K) {
+                    case 0: bulk_wait_read<0>(); break;
+                    case 1: bulk_wait_read<1>(); break;
+                    case 2: bulk_wait_read<2>(); break;
+                    default: bulk_wait_read<3>(); break;
+                }
+                if (s >= K) mbar_arrive(&drained[(s - K) % nbuf]);  // that buffer may be refilled
+            }
+        }
+        if (elect_one_sync()) {
+            bulk_wait_read<0>();
+            for (int s = n_slots - K < 0 ? 0 : n_slots - K; s < n_slots; ++s) mbar_arrive(&drained[s % nbuf]);
+            bulk_wait<0>();  // the stores must have completed before the CTA's shared memory goes away
+        }
+        return;
+    }
+    // ================================================================== solver warps
+    if (warp >= T) {
+        const RefStats* rs_s = reinterpret_cast<const RefStats*>(smem + L.rs_off);
+#pragma unroll 1
+        for (int s = warp - T; s < n_slots; s += S) {
+            const int buf = s % nbuf;
+            const int64_t left = n - (int64_t)s * fpb;
+            const int cnt = (int)(left < fpb ? left : fpb);
+            const int64_t fbase = f0 + (int64_t)s * fpb;
+            float* rec_b = rec_all + (size_t)buf * fpb * W * kRecStride;
+            mbar_wait(&reduced[buf], (uint32_t)((s / nbuf) & 1));
+            if (W > 1) {
+                // several warps per frame: 16 lanes add up the partials in float64, one value each
+                if (lane < 16) {
+                    for (int j = 0; j < cnt; ++j) {
+                        double d = 0.0;
+                        for (int w = 0; w < W; ++w) d += (double)rec_b[((size_t)j * W + w) * kRecStride + lane];
+                        dsum_s[((size_t)buf * fpb + j) * 16 + lane] = d;
+                    }
+                }
+                __syncwarp();
+            }
+            if (lane < cnt) {
+                float* rec0 = rec_b + (size_t)lane * W * kRecStride;
+                fr_solve_frame(W > 1 ? nullptr : rec0, dsum_s + ((size_t)buf * fpb + lane) * 16, rec0, rs_s, p.inv_n_sel,
+                               fbase + lane, p);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&solved[buf]);
+        }
+        return;
+    }
+
+    // ================================================================== streaming warps
+    // W == 1: a warp is cut into 32/Lt lane groups, one frame each: T * 32/Lt frames per pass of the T warps;
+    // W  > 1: W warps share a frame (fpb * W <= T, warps beyond that idle), all 32 lanes on it
+    const int Lt = W > 1 ? 32 : p.lanes;
+    const int fpi = 32 / Lt;
+    const int sj = lane / Lt;
+    const int wj = W > 1 ? warp / W : 0, ts = W > 1 ? warp - wj * W : 0;
+    const int ttid = W > 1 ? ts * 32 + lane : lane - sj * Lt, tthreads = W > 1 ? W * 32 : Lt;
+    const int j_first = W > 1 ? wj : warp * fpi, j_step = W > 1 ? kFrWarps : T * fpi;  // W > 1: a single pass
+    if (p.idx)
+        for (int k = threadIdx.x; k < p.n_sel; k += T * 32) idx_s[k] = __ldg(p.idx + k);
+    mbar_wait(ref_bar, 0);
+    asm volatile("bar.sync 1, %0;" ::"r"(T * 32) : "memory");  // idx_s visible to all streaming warps
+
+#pragma unroll 1
+    for (int i = 0; i < n_slots + D; ++i) {
+        if (i < n_slots) {
+            // ---- sums over the align selection of every frame of slot i (pivot = first selected atom)
+            const int buf = i % nbuf;
+            const int64_t left = n - (int64_t)i * fpb;
+            const int cnt = (int)(left < fpb ? left : fpb);
+            const float* slot_s = reinterpret_cast<const float*>(smem + L.buf_off + (size_t)buf * L.buf_bytes);
+            float* rec_b = rec_all + (size_t)buf * fpb * W * kRecStride;
+            mbar_wait(&full[buf], (uint32_t)((i / nbuf) & 1));
+#pragma unroll 1
+            for (int j0 = j_first; j0 < cnt; j0 += j_step) {
+                const bool act = j0 + sj < cnt;            // idle lane groups of a partial pass still take part in shuffles
+                const int j = act ? j0 + sj : j0;
+                const int n_sel_t = act ? p.n_sel : 0, units_t = act ? units : 0;
+                const float* frame_s = slot_s + (size_t)j * frame_floats;
+                const float4* xs = reinterpret_cast<const float4*>(frame_s);
+                float v[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = 0.f;
+                const int a0 = p.idx ? idx_s[0] : 0;
+                const float px = frame_s[3 * a0], py = frame_s[3 * a0 + 1], pz = frame_s[3 * a0 + 2];
+                if (p.idx) {
+#pragma unroll 4
+                    for (int k = ttid; k < n_sel_t; k += tthreads) {
+                        const int a = idx_s[k];
+                        const float ax = frame_s[3 * a] - px, ay = frame_s[3 * a + 1] - py, az = frame_s[3 * a + 2] - pz;
+                        const float bx = ref_s[3 * k], by = ref_s[3 * k + 1], bz = ref_s[3 * k + 2];
+                        v[0] += ax; v[1] += ay; v[2] += az;
+                        v[3] = fmaf(ax, ax, v[3]); v[3] = fmaf(ay, ay, v[3]); v[3] = fmaf(az, az, v[3]);
+                        v[4] = fmaf(ax, bx, v[4]); v[5] = fmaf(ax, by, v[5]); v[6] = fmaf(ax, bz, v[6]);
+                        v[7] = fmaf(ay, bx, v[7]); v[8] = fmaf(ay, by, v[8]); v[9] = fmaf(ay, bz, v[9]);
+                        v[10] = fmaf(az, bx, v[10]); v[11] = fmaf(az, by, v[11]); v[12] = fmaf(az, bz, v[12]);
+                    }
+                } else {
+                    const float4* ys = reinterpret_cast<const float4*>(ref_s);
+#pragma unroll 2
+                    for (int u = ttid; u < units_t; u += tthreads) {
+                        const float4 a0v = xs[3 * u], a1v = xs[3 * u + 1], a2v = xs[3 * u + 2];
+                        const float4 b0v = ys[3 * u], b1v = ys[3 * u + 1], b2v = ys[3 * u + 2];
+                        acc_unit<false>(v, a0v, a1v, a2v, b0v, b1v, b2v, px, py, pz, p.n_atoms - 4 * u);
+                    }
+                }
+                if (ttid == 0 && act) { v[13] = px; v[14] = py; v[15] = pz; }
+                float* rec_s = rec_b + ((size_t)j * W + ts) * kRecStride;
+                switch (Lt) {
+                    case 2: team_reduce_store<2>(v, lane, act, rec_s); break;
+                    case 4: team_reduce_store<4>(v, lane, act, rec_s); break;
+                    case 8: team_reduce_store<8>(v, lane, act, rec_s); break;
+                    case 16: team_reduce_store<16>(v, lane, act, rec_s); break;
+                    default:
+                        warp_reduce_scatter16(v, lane);
+                        if (!(lane & 1)) rec_s[lane >> 1] = v[0];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&reduced[buf]);
+        }
+        const int k = i - D;
+        if (k >= 0) {
+            // ---- transform of every atom of every frame of slot k, in shared memory
+            const int buf = k % nbuf;
+            const int64_t left = n - (int64_t)k * fpb;
+            const int cnt = (int)(left < fpb ? left : fpb);
+            float* slot_s = reinterpret_cast<float*>(smem + L.buf_off + (size_t)buf * L.buf_bytes);
+            const float* rec_b = rec_all + (size_t)buf * fpb * W * kRecStride;
+            mbar_wait(&solved[buf], (uint32_t)((k / nbuf) & 1));
+#pragma unroll 1
+            for (int j0 = j_first; j0 < cnt; j0 += j_step) {
+                const int j = j0 + sj;
+                if (j >= cnt) continue;
+                float4* xs = reinterpret_cast<float4*>(slot_s + (size_t)j * frame_floats);
+                float t[15];
+#pragma unroll
+                for (int c = 0; c < 15; ++c) t[c] = rec_b[(size_t)j * W * kRecStride + c];
+#pragma unroll 2
+                for (int u = ttid; u < units; u += tthreads) {
+                    float4 a0v = xs[3 * u], a1v = xs[3 * u + 1], a2v = xs[3 * u + 2];
+                    const int nvalid = p.n_atoms - 4 * u;
+                    xf_atom(a0v.x, a0v.y, a0v.z, t);
+                    if (nvalid > 1) xf_atom(a0v.w, a1v.x, a1v.y, t);
+                    if (nvalid > 2) xf_atom(a1v.z, a1v.w, a2v.x, t);
+                    if (nvalid > 3) xf_atom(a2v.y, a2v.z, a2v.w, t);
+                    xs[3 * u] = a0v; xs[3 * u + 1] = a1v; xs[3 * u + 2] = a2v;
+                }
+            }
+            fence_proxy_async_smem();  // the modified slot must be visible to the bulk store
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&done[buf]);
+        }
+    }
+}
+
+static bool pipe_fits(const FusedParams& p, int nbuf, int fpb, int W)
+{
+    const int n_sel_pad = (p.n_sel + 3) & ~3;
+    return pipe_layout(p.n_pad, nbuf, n_sel_pad, p.idx ? p.n_sel : 0, fpb, W).total <= 232448;
+}
+
+// Geometry of the stage-pipelined superpose: slots of ~20 KB (at most 32 frames), as many buffers as fit (<= 12),
+// S = solve latency / slot period + 1 solver warps, the same number of slots between the sums and the transform.
+static bool pipe_config(FusedParams& p)
+{
+    const size_t frame_bytes = (size_t)p.n_pad * 12;
+    if (frame_bytes > 100000) return false;
+    const bool contiguous = p.frame_stride == (int64_t)p.n_pad * 3;
+    int fpb = contiguous ? (int)(20480 / frame_bytes) : 1;
+    fpb = fpb < 1 ? 1 : (fpb > kPipeMaxFrames ? kPipeMaxFrames : fpb);
+    const double kSolveCycles = 6000.0;   // float64 QCP solve with rotation, one frame per lane (tools/fused_trace.py)
+    for (;; --fpb) {
+        const double period = (double)fpb * frame_bytes * 2.0 / 22.5;  // cycles a slot takes at the HBM rate of one SM
+        int S = (int)(kSolveCycles / period) + 2;
+        S = S < 2 ? 2 : (S > 8 ? 8 : S);
+        int T = kFrWarps - S;
+        int W = 1, lanes = 32;
+        if (fpb >= T) {
+            while (lanes > 2 && T * (32 / lanes) < fpb) lanes >>= 1;  // the widest lane group that covers the slot in one pass
+        } else {
+            W = T / fpb;
+        }
+        int nbuf = 12;
+        while (nbuf >= 2 && !pipe_fits(p, nbuf, fpb, W)) --nbuf;
+        if (nbuf < 2) {
+            if (fpb > 1) continue;
+            return false;
+        }
+        if (S > nbuf) { S = nbuf; T = kFrWarps - S; if (W > 1) W = T / fpb; }
+        int D = (int)(kSolveCycles / period) + 2;
+        if (D > nbuf - 3) D = nbuf - 3;
+        if (D < 1) D = 1;
+        p.pipe = 1; p.batch = S; p.nbuf = nbuf; p.fpb = fpb; p.team_warps = W; p.lanes = lanes; p.depth = D;
+        return true;
+    }
+}
+
 static int fr_team_warps(int G, int fpb)
 {
     const int wpf = kFrWarps / G;
@@ -550,6 +879,8 @@ bool fused_config(FusedParams& p, int op)
 {
     const size_t frame_bytes = (size_t)p.n_pad * 12;
     if (frame_bytes >= (1u << 20)) return false;
+    p.pipe = 0;
+    if (op == OP_SUPERPOSE && (int64_t)frame_bytes >= g_fr_pipe_min_bytes && pipe_config(p)) return true;
     const bool contiguous = p.frame_stride == (int64_t)p.n_pad * 3;
     if (op == OP_CENTER && frame_bytes <= 12288) {
         // centring is light enough to be HBM-bound in the model whatever the geometry; measured best (0.96-0.99x for
@@ -612,9 +943,31 @@ bool fused_config(FusedParams& p, int op)
     return false;
 }
 
+// Frames of at least this many bytes take the stage-pipelined superpose kernel, smaller ones the ring kernel: a slot of
+// small frames costs every streaming warp of the pipelined kernel its fixed per-pass overhead (~900 cycles against a slot
+// period of 800-1600), which the ring kernel pays once per slot (profiles/r02_fused_sweep_pipe*.jsonl).
+int g_fr_pipe_min_bytes = 30000;
+extern "C" int b200rmsd_debug_fused_pipe_min_bytes(int min_frame_bytes)  // development / sweeps; returns the old value
+{
+    const int was = g_fr_pipe_min_bytes;
+    g_fr_pipe_min_bytes = min_frame_bytes;
+    return was;
+}
+
 // development override: frames per slot, G concurrent groups, ring depth, lanes per frame (checked against shared memory)
 bool fused_override(FusedParams& p, int op, int G, int nbuf, int fpb, int lanes)
 {
+    if (p.pipe) {  // pipelined superpose: G = solver warps, nbuf, fpb; lanes = depth
+        if (G > 0) p.batch = G;
+        if (nbuf > 0) p.nbuf = nbuf;
+        if (lanes > 0) p.depth = lanes;
+        if (fpb > 0 && fpb != p.fpb) return false;
+        if (p.batch < 1 || p.batch > 8 || p.nbuf < 2 || p.nbuf < p.batch || p.depth < 1 || p.depth > p.nbuf - 1) return false;
+        const int T = kFrWarps - p.batch;
+        if (p.team_warps > 1) p.team_warps = T / p.fpb;
+        else if (T * (32 / p.lanes) < p.fpb) return false;
+        return p.team_warps >= 1 && pipe_fits(p, p.nbuf, p.fpb, p.team_warps);
+    }
     if (G <= 0) G = p.batch;
     if (fpb <= 0) fpb = p.fpb;
     if (nbuf <= 0) nbuf = G * (p.nbuf / p.batch);
@@ -659,6 +1012,12 @@ extern "C" int b200rmsd_debug_fused_geometry(int op, int n_atoms, int n_sel, int
     p.idx = has_idx ? reinterpret_cast<const int*>(0x10) : nullptr;  // only tested against nullptr
     if (!fused_config(p, op)) return 0;
     const int n_sel_pad = (p.n_sel + 3) & ~3;
+    if (p.pipe) {  // returns 2: {solver warps, nbuf, fpb, streaming warps per frame, lanes per frame, bytes}; depth in out[6]
+        const PipeLayout PL = pipe_layout(p.n_pad, p.nbuf, n_sel_pad, p.idx ? p.n_sel : 0, p.fpb, p.team_warps);
+        out[0] = p.batch; out[1] = p.nbuf; out[2] = p.fpb; out[3] = p.team_warps; out[4] = p.lanes; out[5] = (int)PL.total;
+        out[6] = p.depth;
+        return 2;
+    }
     const FrLayout L = fr_layout(p.n_pad, p.nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0, p.batch, p.fpb,
                                  p.team_warps, op == OP_SUPERPOSE);
     out[0] = p.batch; out[1] = p.nbuf; out[2] = p.fpb; out[3] = p.team_warps; out[4] = p.lanes; out[5] = (int)L.total;
@@ -677,6 +1036,19 @@ extern "C" int b200rmsd_debug_fused_trace(long long* host_out, size_t n)
 cudaError_t launch_frame_resident(const FusedParams& p, int op, int sm_count, cudaStream_t st)
 {
     if (p.n_frames <= 0) return cudaSuccess;
+    if (op == OP_SUPERPOSE && p.pipe) {
+        const int n_sel_pad = (p.n_sel + 3) & ~3;
+        const PipeLayout L = pipe_layout(p.n_pad, p.nbuf, n_sel_pad, p.idx ? p.n_sel : 0, p.fpb, p.team_warps);
+        cudaError_t e = cudaFuncSetAttribute(superpose_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        if (e != cudaSuccess) return e;
+        int64_t ctas = sm_count;
+        const int64_t need = (p.n_frames + p.fpb - 1) / p.fpb;
+        if (ctas > need) ctas = need;
+        FusedParams q = p;
+        q.inv_n_sel = 1.0 / (double)(p.n_sel > 0 ? p.n_sel : 1);
+        superpose_pipe_kernel<<<(unsigned)ctas, kFrThreads, L.total, st>>>(q);
+        return cudaGetLastError();
+    }
     fr_trace_buffer((size_t)(p.n_frames / (sm_count > 0 ? sm_count : 1) + 2) + 64);
     const int n_sel_pad = (p.n_sel + 3) & ~3;
     const FrLayout L = fr_layout(p.n_pad, p.nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0, p.batch, p.fpb,

@@ -76,6 +76,11 @@ struct FusedParams {
     int team_warps;         // warps sharing one frame inside a group: 16/G or 1
     int lanes;              // team_warps == 1: lanes sharing one frame inside a warp (2, 4, 8, 16, 32)
     double inv_n_sel;       // 1 / n_sel (set by launch_frame_resident)
+    // stage-pipelined superpose (superpose_pipe_kernel): pipe != 0, then batch = solver warps S, team_warps = streaming
+    // warps per frame W, lanes = lanes per frame when W == 1, nbuf = slot buffers, depth = slots between the sums of a
+    // slot and its transform
+    int pipe;
+    int depth;
 };
 bool fused_config(FusedParams& p, int op);
 bool fused_override(FusedParams& p, int op, int G, int nbuf, int fpb, int lanes);

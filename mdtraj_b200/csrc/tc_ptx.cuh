@@ -9,13 +9,6 @@
 namespace b200 {
 
 // ---- tcgen05 / TMA PTX wrappers -------------------------------------------------------------
-// one lane of the (converged) warp: the idiom that lets a warp-uniform loop issue single-thread instructions
-__device__ __forceinline__ bool elect_one_sync()
-{
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
 {
     asm volatile(

@@ -146,18 +146,32 @@ def test_frame_resident_geometry_invariants():
     L = ctypes.CDLL(_capi.LIB_PATH)
     geo = L.b200rmsd_debug_fused_geometry
     geo.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_int)]
-    out = (ctypes.c_int * 6)()
-    seen_multi = False
+    out = (ctypes.c_int * 8)()
+    seen_multi = seen_pipe = False
     for op in (0, 1):
         for n in list(range(1, 70)) + [99, 100, 127, 128, 200, 255, 256, 300, 500, 999, 1000, 1500, 2000, 2500, 3000, 4000,
                                         5000, 6000, 9000, 20000]:
             for has_idx in ((0, 1) if op == 0 else (0,)):
                 for contiguous in (1, 0):
                     n_sel = max(1, n // 5) if has_idx else n
-                    if not geo(op, n, n_sel, has_idx, contiguous, out):
+                    kind = geo(op, n, n_sel, has_idx, contiguous, out)
+                    if not kind:
                         assert n * 12 * 3 > 150000, f"single-pass kernel refused a small frame: op={op} n={n}"
                         continue
-                    G, nbuf, fpb, tw, lanes, smem = list(out)
+                    if kind == 2:   # stage-pipelined superpose (superpose_pipe_kernel)
+                        S, nbuf, fpb, W, lanes, smem, depth = list(out)[:7]
+                        T = 16 - S
+                        assert op == 0 and 1 <= S <= 8 and S <= nbuf and 2 <= nbuf <= 12 and smem <= 232448
+                        assert 1 <= fpb <= 32 and (contiguous or fpb == 1)    # one solver lane per frame of a slot
+                        assert 1 <= depth <= nbuf - 1                          # the transform of slot i - depth frees a buffer in time
+                        if W == 1:
+                            assert lanes in (2, 4, 8, 16, 32) and T * (32 // lanes) >= fpb   # one pass of the streaming warps
+                        else:
+                            assert lanes == 32 and W * fpb <= T
+                        seen_multi |= fpb > 1
+                        seen_pipe = True
+                        continue
+                    G, nbuf, fpb, tw, lanes, smem = list(out)[:6]
                     assert 1 <= G <= 16 and nbuf % G == 0 and nbuf >= 2 and nbuf >= G
                     assert smem <= 232448
                     assert fpb >= 1 and (contiguous or fpb == 1)
@@ -168,7 +182,7 @@ def test_frame_resident_geometry_invariants():
                     if tw != 1:
                         assert lanes == 32
                     seen_multi |= fpb > 1
-    assert seen_multi
+    assert seen_multi and seen_pipe
 
 
 def test_allpairs_tile_walk_covers_every_pair_once():

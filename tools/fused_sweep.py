@@ -15,6 +15,9 @@ PEAK = 6540.8
 dev = torch.device("cuda", 0)
 L = _capi.lib()
 quick = os.environ.get("SWEEP_QUICK") == "1"
+if "SWEEP_PIPE_MIN" in os.environ:  # frames of at least this many bytes take the stage-pipelined superpose kernel
+    import ctypes
+    ctypes.CDLL(_capi.LIB_PATH).b200rmsd_debug_fused_pipe_min_bytes(int(os.environ["SWEEP_PIPE_MIN"]))
 
 
 def timed(fn, reps=5):

@@ -6,6 +6,10 @@ os.environ["B200RMSD_FUSED_TRACE"] = "1"
 import numpy as np, torch
 import mdtraj_b200 as mdb
 from mdtraj_b200 import _capi
+libs = [a[6:] for a in sys.argv[1:] if a.startswith("--lib=")]   # a dev build: tools/build_variants.sh name:""
+sys.argv = [a for a in sys.argv if not a.startswith("--lib=")]
+if libs:
+    _capi.LIB_PATH = os.path.abspath(libs[0])
 from mdtraj_b200.device import _Scratch, _stream_ptr, prepare_reference
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 40000
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
@@ -22,7 +26,7 @@ def run():
                 scratch.numel(), _stream_ptr(torch, dev)), "superpose")
 for _ in range(3): run()
 torch.cuda.synchronize()
-geo = (ctypes.c_int * 6)()
+geo = (ctypes.c_int * 8)()
 ctypes.CDLL(_capi.LIB_PATH).b200rmsd_debug_fused_geometry(0, N, int(idx.numel()), 1, 1, geo)
 print("geometry: G=%d nbuf=%d fpb=%d team_warps=%d lanes=%d smem=%d" % tuple(geo))
 per = (F // 148 + 2) * 8
