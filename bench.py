@@ -512,6 +512,7 @@ def run_allpairs(c, name, steps, warmup, full, tf32):
             else:  # frames broadcast from rank 0 over NCCL, symmetric block plan, transposed blocks exchanged
                 _, _, blk = DD.rmsd_matrix_sharded(dt, None, broadcast=True, symmetric=True)
                 state["blk"] = blk
+                state["peer"] = any(e.ok and e.block.data_ptr() == blk.data_ptr() for e in DD._EXCHANGES.values())
     ms, kern_ms, clocks = timed_region(c, step, steps, warmup)
     tiles = allpairs_tiles(c, F)
     kpad = (N + 31) // 32 * 32
@@ -522,7 +523,9 @@ def run_allpairs(c, name, steps, warmup, full, tf32):
            "data": "synthetic",
            "config": {"workload": desc, "frames_total": F, "n_atoms": N,
                       "parallelism": "1 GPU" if c.world == 1 else
-                      "frames NCCL-broadcast, %d row blocks, symmetric block plan, transposed blocks sent over NVLink" % c.world,
+                      "frames NCCL-broadcast, %d row blocks, symmetric block plan, transposed blocks %s" % (
+                          c.world, "written into their owner's row block over NVLink by the computing kernel (peer memory)"
+                          if state.get("peer") else "sent over NVLink with NCCL send/recv"),
                       "l2_policy": "the %.1f GB of matrix written per GPU and step flushes the 126 MB L2 between steps; the "
                                    "operands (%.2f GB) are meant to stay L2-resident inside a step" % (
                                        F * F * 4 / 1e9 / c.world, F * kpad * 3 * 4 * 4 / 1e9)},
@@ -639,11 +642,19 @@ def main():
         if not args.no_subs:
             tf32 = measure_tf32_peak(c)
             sub = {}
+
+            def rested(fn):
+                # a few idle seconds before each record: the board's power limiter keeps the SM clock down for a while
+                # after a tensor-core workload (the 2-GPU run of this bench measured ovm25k at 1305 MHz, 0.77 of the
+                # HBM peak, straight after the 100k x 100k matrix; 1.0 when it runs first), and the HBM-bound records go
+                # before the tensor-bound ones for the same reason
+                time.sleep(3.0)
+                return _try(fn)
+            sub["ovm25k"] = rested(lambda: run_ovm(c, "ovm25k", sub_steps, 3, full and world == 1))
             if world == 1:
-                sub["superpose"] = _try(lambda: run_superpose(c, sub_steps, 3, full))
-                sub["allpairs_20k"] = _try(lambda: run_allpairs(c, "allpairs_20k", sub_steps, 3, full, tf32))
-            sub["allpairs_100k"] = _try(lambda: run_allpairs(c, "allpairs_100k", 3, 3, False, tf32))
-            sub["ovm25k"] = _try(lambda: run_ovm(c, "ovm25k", sub_steps, 3, full and world == 1))
+                sub["superpose"] = rested(lambda: run_superpose(c, sub_steps, 3, full))
+                sub["allpairs_20k"] = rested(lambda: run_allpairs(c, "allpairs_20k", sub_steps, 3, full, tf32))
+            sub["allpairs_100k"] = rested(lambda: run_allpairs(c, "allpairs_100k", 3, 3, False, tf32))
             line["sub"] = sub
             line["tf32_peak"] = tf32
             line["gpu_launches"] = int(line["gpu_launches"] + sum((s.get("gpu_launches") or 0) for s in sub.values()
@@ -651,6 +662,8 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        from mdtraj_b200 import distributed as DD
+        DD.release_peer_exchanges()
         dist.destroy_process_group()
 
 

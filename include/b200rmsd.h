@@ -207,6 +207,37 @@ int b200rmsd_allpairs_block_dev(const void* workspace, size_t workspace_bytes, i
                                 int64_t row0, int64_t row1, int64_t col0, int64_t col1, float* out, int64_t ld,
                                 float* out_t, int64_t ld_t, unsigned flags, void* stream);
 
+/* The same block with the superposition of every pair: besides out (as above) the epilogue writes the rotation that
+ * carries frame j onto frame i,
+ *     out_rot[((i-row0)*(col1-col0) + (j-col0))*9 + 3a + b] = U[a][b],   (x_j - centroid_j) U ~ x_i - centroid_i,
+ * row vector times U as in rot_atom_major (rotation_generic.h:40-42) -- the rotation md.rmsd / Trajectory.superpose
+ * would find for target frame j against reference frame i (theobald_rmsd.cpp:280-334), i.e. row i of out_rot equals
+ * out_rot of b200rmsd_rmsd_dev(frames, reference = frame i).  Entries (i, i) are the identity when
+ * B200RMSD_DIAG_ZERO is set.  36 bytes per pair leave the device, so this is meant for blocks (cluster centres x
+ * members), not for a 100k x 100k matrix; every pair is computed (no mirroring).  The inner products still never
+ * touch HBM: the rotation comes out of the same accumulator tile as the RMSD. */
+int b200rmsd_allpairs_block_rot_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,
+                                    int64_t row0, int64_t row1, int64_t col0, int64_t col1, float* out, int64_t ld,
+                                    float* out_rot, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------ peer-visible buffers
+ *
+ * Multi-process all-pairs (one process per GPU): rank r computes block (r,s) of the symmetric matrix once and its
+ * epilogue writes the transposed copy straight into rank s's row block over NVLink -- out_t of
+ * b200rmsd_allpairs_block_dev is then an address inside a buffer rank s allocated here and rank r opened.  The transfer
+ * rides under the tensor-core work of the same kernel; there is no staging buffer, no separate send/receive kernel
+ * and no copy on arrival (mdtraj_b200.distributed.rmsd_matrix_sharded(exchange="peer")).
+ *   peer_alloc: cudaMalloc + cudaIpcGetMemHandle; `handle` receives B200RMSD_PEER_HANDLE_BYTES bytes to pass to the
+ *               other processes by any means (torch.distributed.all_gather_object in the Python layer);
+ *   peer_open:  maps another process's buffer (enables peer access on first use); peer_close unmaps it;
+ *   peer_free:  releases a buffer of peer_alloc (after every process that opened it has closed it).
+ * The caller orders the accesses: stream-synchronise every writer and meet at a barrier before reading. */
+#define B200RMSD_PEER_HANDLE_BYTES 64
+int b200rmsd_peer_alloc(size_t bytes, void** dev_ptr, void* handle);
+int b200rmsd_peer_open(const void* handle, void** dev_ptr);
+int b200rmsd_peer_close(void* dev_ptr);
+int b200rmsd_peer_free(void* dev_ptr);
+
 /* ------------------------------------------------------------ consumers of the matrix */
 
 /* The reference's example notebooks post-process the (F,F) matrix on the host with numpy / scipy.  These entry points

@@ -49,7 +49,12 @@ SIGNATURES = {
     "b200rmsd_allpairs_info_dev": (_i32, [_vp, _sz, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_f32), _vp, _i32, _vp]),
     "b200rmsd_allpairs_prepare_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _sz, _vp]),
     "b200rmsd_allpairs_block_dev": (_i32, [_vp, _sz, _i64, _i32, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _u32, _vp]),
+    "b200rmsd_allpairs_block_rot_dev": (_i32, [_vp, _sz, _i64, _i32, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _u32, _vp]),
     "b200rmsd_allpairs_rows_dev": (_i32, [_vp, _sz, _i64, _i32, _i64, _i64, _vp, _i64, _u32, _vp]),
+    "b200rmsd_peer_alloc": (_i32, [_sz, C.POINTER(_vp), _vp]),
+    "b200rmsd_peer_open": (_i32, [_vp, C.POINTER(_vp)]),
+    "b200rmsd_peer_close": (_i32, [_vp]),
+    "b200rmsd_peer_free": (_i32, [_vp]),
     "b200rmsd_matrix_moments_dev": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "b200rmsd_exp_rowsum_dev": (_i32, [_vp, _i64, _i64, _i64, _f32, _i32, _vp, _vp]),
     "b200rmsd_row_argmin_dev": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),

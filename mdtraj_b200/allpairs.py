@@ -105,10 +105,12 @@ def rows(prep: PreparedAllPairs, row0: int, row1: int, out=None, diag_zero=True,
     return out
 
 
-def block(prep: PreparedAllPairs, row0, row1, col0, col1, out, out_t=None, diag_zero=True, precise=True):
+def block(prep: PreparedAllPairs, row0, row1, col0, col1, out, out_t=None, diag_zero=True, precise=True, out_t_ptr=None,
+          ld_t=None):
     """Rows [row0,row1) x columns [col0,col1) into ``out`` (a (row1-row0, >=col1) CUDA tensor, absolute column index);
     ``out_t`` (col1-col0, row1-row0), when given, also receives the transposed block (for shipping to the rank that
-    owns rows [col0,col1), see distributed.rmsd_matrix_sharded)."""
+    owns rows [col0,col1), see distributed.rmsd_matrix_sharded).  ``out_t_ptr``/``ld_t``: the same as a raw device
+    address and leading dimension -- a window of another process's buffer opened with ``b200rmsd_peer_open``."""
     torch = _torch()
     dev = prep.device
     assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape[0] == row1 - row0
@@ -120,12 +122,39 @@ def block(prep: PreparedAllPairs, row0, row1, col0, col1, out, out_t=None, diag_
     with torch.cuda.device(dev):
         rc = L.b200rmsd_allpairs_block_dev(prep.workspace.data_ptr(), prep.workspace.numel(), prep.n_frames, prep.n_sel,
                                            row0, row1, col0, col1, out.data_ptr(), out.stride(0),
-                                           None if out_t is None else out_t.data_ptr(),
-                                           0 if out_t is None else out_t.stride(0),
+                                           out_t_ptr if out_t is None else out_t.data_ptr(),
+                                           (ld_t or 0) if out_t is None else out_t.stride(0),
                                            (DIAG_ZERO if diag_zero else 0) | (0 if precise else FAST_SOLVE),
                                            _stream_ptr(torch, dev))
     _capi.check(rc, "b200rmsd_allpairs_block_dev")
     return out
+
+
+def block_rotations(prep: PreparedAllPairs, row0, row1, col0, col1, diag_zero=True, precise=True):
+    """Rows [row0,row1) x columns [col0,col1) with the superposition of every pair (``b200rmsd_allpairs_block_rot_dev``):
+    returns ``(D, U)`` -- ``D`` (row1-row0, col1-col0) float32 RMSDs and ``U`` (row1-row0, col1-col0, 3, 3) float32
+    rotations with ``(x_j - centroid_j) @ U[i-row0, j-col0] ~ x_i - centroid_i`` over the selected atoms: what
+    ``md.rmsd`` / ``Trajectory.superpose`` find for target frame j against reference frame i.  Both come out of the same
+    accumulator tile of the fused epilogue; 40 bytes per pair are written, so ask for blocks (centres x members)."""
+    torch = _torch()
+    dev = prep.device
+    F = prep.n_frames
+    if not (0 <= row0 <= row1 <= F and 0 <= col0 <= col1 <= F):
+        raise ValueError("block out of range")
+    nr, nc = row1 - row0, col1 - col0
+    D = torch.empty((nr, nc), dtype=torch.float32, device=dev)
+    U = torch.empty((nr, nc, 3, 3), dtype=torch.float32, device=dev)
+    if nr == 0 or nc == 0:
+        return D, U
+    L = _capi.lib()
+    with torch.cuda.device(dev):
+        # `out` is addressed with the absolute column index: pass the address column 0 would have
+        rc = L.b200rmsd_allpairs_block_rot_dev(prep.workspace.data_ptr(), prep.workspace.numel(), F, prep.n_sel, row0, row1,
+                                               col0, col1, D.data_ptr() - 4 * col0, nc, U.data_ptr(),
+                                               (DIAG_ZERO if diag_zero else 0) | (0 if precise else FAST_SOLVE),
+                                               _stream_ptr(torch, dev))
+    _capi.check(rc, "b200rmsd_allpairs_block_rot_dev")
+    return D, U
 
 
 def rmsd_matrix_device(traj: DeviceTrajectory, atom_indices=None, row_block=None, diag_zero=True, precise=True):

@@ -16,6 +16,8 @@
 //                            for small problems and as the on-device accuracy check of the
 //                            tensor-core path (allpairs_tc.cu).
 #include "../../include/b200rmsd.h"
+#include <cstring>
+
 #include "allpairs_layout.cuh"
 #include "common.cuh"
 #include "kernels.cuh"
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restr
                                                             int64_t n_frames, int n_sel, int k_pad, int64_t row0,
                                                             int64_t row1, int64_t col0, int64_t col1,
                                                             float* __restrict__ out, int64_t ld, float* __restrict__ out_t,
-                                                            int64_t ld_t, unsigned flags)
+                                                            int64_t ld_t, float* __restrict__ out_rot, unsigned flags)
 {
     __shared__ __align__(16) float As[kTile * 3 * kRow];
     __shared__ __align__(16) float Bs[kTile * 3 * kRow];
@@ -140,8 +142,14 @@ __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restr
             const int64_t i = i0 + ti + 16 * si, j = j0 + tj + 16 * sj;
             if (i >= row1 || j >= col1) continue;
             float r;
+            // optional rotation of frame j onto frame i (row vector x R, rotation_generic.h:40-42), 9 floats per pair
+            float* rot = out_rot ? out_rot + ((size_t)(i - row0) * (size_t)(col1 - col0) + (size_t)(j - col0)) * 9 : nullptr;
             if (i == j && (flags & 1u)) {
                 r = 0.f;  // a frame against itself in the same memory: theobald_rmsd_sse.h:256-262
+                if (rot) {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) rot[c] = (c % 4 == 0) ? 1.0f : 0.0f;
+                }
             } else {
                 QcpInput q;
                 q.inv_n = inv_n;
@@ -149,7 +157,7 @@ __global__ void __launch_bounds__(256) allpairs_simt_kernel(const float* __restr
                 q.Gb = (double)traces[i];
 #pragma unroll
                 for (int c = 0; c < 9; ++c) q.M[c] = (double)acc[si][sj][c];
-                r = sqrtf((float)qcp_solve(q, nullptr, nullptr));
+                r = sqrtf((float)qcp_solve(q, rot, nullptr));
             }
             out[(size_t)(i - row0) * ld + j] = r;
             if (out_t) out_t[(size_t)(j - col0) * ld_t + (i - row0)] = r;
@@ -184,6 +192,47 @@ int b200rmsd_allpairs_set_cta_pair(int cta_pair)
     const int was = g_ap_cta_pair;
     g_ap_cta_pair = cta_pair != 0;
     return was;
+}
+
+// ---- peer-visible buffers (multi-process all-pairs: transposed blocks are written into the owner's row block over NVLink)
+int b200rmsd_peer_alloc(size_t bytes, void** dev_ptr, void* handle)
+{
+    if (!dev_ptr || !handle || bytes == 0) return fail(B200RMSD_EINVAL, "peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200RMSD_PEER_HANDLE_BYTES, "handle size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(B200RMSD_ECUDA, "peer_alloc: %s", cudaGetErrorString(e));
+    e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle), p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(B200RMSD_ECUDA, "peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    *dev_ptr = p;
+    return 0;
+}
+
+int b200rmsd_peer_open(const void* handle, void** dev_ptr)
+{
+    if (!dev_ptr || !handle) return fail(B200RMSD_EINVAL, "peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(B200RMSD_ECUDA, "peer_open: %s", cudaGetErrorString(e));
+    *dev_ptr = p;
+    return 0;
+}
+
+int b200rmsd_peer_close(void* dev_ptr)
+{
+    const cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+    return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "peer_close: %s", cudaGetErrorString(e));
+}
+
+int b200rmsd_peer_free(void* dev_ptr)
+{
+    const cudaError_t e = cudaFree(dev_ptr);
+    return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "peer_free: %s", cudaGetErrorString(e));
 }
 
 int b200rmsd_allpairs_info_dev(const void* workspace, size_t workspace_bytes, int* n_refs, int* n_far, float* cover_radius,
@@ -242,9 +291,9 @@ int b200rmsd_allpairs_prepare_dev(const float* xyz, int64_t n_frames, int n_atom
     return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "allpairs_prepare: %s", cudaGetErrorString(e));
 }
 
-int b200rmsd_allpairs_block_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,
-                                int64_t row0, int64_t row1, int64_t col0, int64_t col1, float* out, int64_t ld,
-                                float* out_t, int64_t ld_t, unsigned flags, void* stream)
+static int ap_block(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel, int64_t row0, int64_t row1,
+                    int64_t col0, int64_t col1, float* out, int64_t ld, float* out_t, int64_t ld_t, float* out_rot,
+                    unsigned flags, void* stream)
 {
     if (!workspace || !out || n_frames <= 0 || n_sel <= 0 || row0 < 0 || row1 > n_frames || row0 > row1 || col0 < 0 ||
         col1 > n_frames || col0 > col1 || ld < col1 - col0 || (out_t && ld_t < row1 - row0))
@@ -254,15 +303,33 @@ int b200rmsd_allpairs_block_dev(const void* workspace, size_t workspace_bytes, i
     if (row0 == row1 || col0 == col1) return 0;
     const char* base = (const char*)workspace;
     if (g.tc)
-        return launch_allpairs_tc144_block(g, base, n_sel, n_frames, row0, row1, col0, col1, out, ld, out_t, ld_t, flags,
-                                           ap_sm_count(), (cudaStream_t)stream);
+        return launch_allpairs_tc144_block(g, base, n_sel, n_frames, row0, row1, col0, col1, out, ld, out_t, ld_t, out_rot,
+                                           flags, ap_sm_count(), (cudaStream_t)stream);
     dim3 grid((unsigned)((col1 - col0 + kTile - 1) / kTile), (unsigned)((row1 - row0 + kTile - 1) / kTile));
     if (grid.y > 65535) return fail(B200RMSD_EINVAL, "allpairs_block: at most 65535*32 rows per call");
     allpairs_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)(base + g.x_off),
                                                                  (const float*)(base + g.traces_off), n_frames, n_sel,
-                                                                 g.k_pad, row0, row1, col0, col1, out, ld, out_t, ld_t, flags);
+                                                                 g.k_pad, row0, row1, col0, col1, out, ld, out_t, ld_t,
+                                                                 out_rot, flags);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail(B200RMSD_ECUDA, "allpairs_block: %s", cudaGetErrorString(e));
+}
+
+int b200rmsd_allpairs_block_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,
+                                int64_t row0, int64_t row1, int64_t col0, int64_t col1, float* out, int64_t ld,
+                                float* out_t, int64_t ld_t, unsigned flags, void* stream)
+{
+    return ap_block(workspace, workspace_bytes, n_frames, n_sel, row0, row1, col0, col1, out, ld, out_t, ld_t, nullptr,
+                    flags, stream);
+}
+
+int b200rmsd_allpairs_block_rot_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,
+                                    int64_t row0, int64_t row1, int64_t col0, int64_t col1, float* out, int64_t ld,
+                                    float* out_rot, unsigned flags, void* stream)
+{
+    if (!out_rot) return fail(B200RMSD_EINVAL, "allpairs_block_rot: out_rot is NULL");
+    return ap_block(workspace, workspace_bytes, n_frames, n_sel, row0, row1, col0, col1, out, ld, nullptr, 0, out_rot,
+                    flags, stream);
 }
 
 int b200rmsd_allpairs_rows_dev(const void* workspace, size_t workspace_bytes, int64_t n_frames, int n_sel,

@@ -105,6 +105,6 @@ cudaError_t launch_allpairs_tc144_prepare(const float* xyz, int64_t n_frames, in
                                           cudaStream_t st);
 int launch_allpairs_tc144_block(const ApGeometry& g, const char* base, int n_sel, int64_t n_frames, int64_t row0,
                                 int64_t row1, int64_t col0, int64_t col1, float* out, int64_t ld, float* out_t,
-                                int64_t ld_t, unsigned flags, int sm_count, cudaStream_t st);
+                                int64_t ld_t, float* out_rot, unsigned flags, int sm_count, cudaStream_t st);
 
 }  // namespace b200

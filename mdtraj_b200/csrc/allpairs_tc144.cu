@@ -78,6 +78,8 @@ struct Tc144Params {
     int64_t col0, col1;      // output columns [col0, col1)
     float* out_t;            // optional transposed copy of the block: out_t[(j-col0)*ld_t + (i-row0)]
     int64_t ld_t;
+    float* out_rot;          // optional (ROT kernels): 9 floats per pair, out_rot[((i-row0)*(col1-col0) + (j-col0))*9 + 3a+b]
+    const float* frame_rot;  // the rotation every frame got in the prepare step (x' = (x - centroid) R_f), 9 floats each
     int64_t n_slots;         // super-block slots to walk (tiles outside the block or under the diagonal are skipped)
     int tiles_i0, tiles_j0;  // first i-tile (= row0 / 40) and j-tile (= col0 / 48)
     int tiles_i, tiles_j;    // tile grid
@@ -262,7 +264,7 @@ allpairs_tc144_prepare_kernel(const float* __restrict__ xyz, int64_t n_frames, i
 
 // EPI_WARPS in {8, 16}: epilogue warps (each TMEM lane quarter is served by EPI_WARPS/4 warps that split the four
 // 36-column segments of the accumulator); NP in {1, 2}: independent solves interleaved per lane.
-template <int EPI_WARPS, int NP, bool PAIR>
+template <int EPI_WARPS, int NP, bool PAIR, bool ROT>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_g_a, const __grid_constant__ CUtensorMap map_g_b,
@@ -449,6 +451,11 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const int64_t fi = (int64_t)ti * kIFrames + ew * 10 + tq;  // row frame of this lane
             const bool i_ok = row_valid && fi >= p.row0 && fi < p.row1;
             const float Gi = i_ok ? __ldg(p.traces + fi) : 1.0f;
+            float Ri[ROT ? 9 : 1];
+            if constexpr (ROT) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Ri[k] = i_ok ? __ldg(p.frame_rot + fi * 9 + k) : 0.f;
+            }
             ap_wait(&tfull[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -527,6 +534,58 @@ allpairs_tc144_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
                         for (int u = 0; u < NP; ++u) {
                             if (!trusted[u]) res[u] = trusted2[u] ? res2[u] : qcp_rmsd_closed(M2[u], Ga[u], Gb[u], inv_n);
+                        }
+                    }
+                    if constexpr (ROT) {
+                        // The rotation that superposes frame j onto frame i (north_star: "plus a rotation matrix for
+                        // superpose"; the convention of b200rmsd_rmsd_dev's out_rot and rotation_generic.h:40-42:
+                        // (x_j - centroid_j) U ~ x_i - centroid_i).  The blocks are fetched once more (M is dead after the
+                        // solve, as on the fall-back route) and go through the float64 solver with the quaternion
+                        // (qcp_solve: cofactors of row 0 of K - lambda I, theobald_rmsd.cpp:280-334), with rows = the frame
+                        // that is rotated (j).  The block belongs to the frames as the prepare step aligned them
+                        // (x' = (x - centroid) R_f) and its axes are in this lane's cyclic order, so the result W' is
+                        // first put back into x,y,z order (W[(c+r)%3][(c+q)%3] = W'[r][q]) and then carried to the frames'
+                        // own orientations: X'_j W ~ X'_i  =>  U = R_j W R_i^T.
+                        float M3[NP][9];
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) gather(NP * jp + u, M3[u]);
+#pragma unroll
+                        for (int u = 0; u < NP; ++u) {
+                            if (!ok[u]) continue;
+                            float* dst = p.out_rot + ((size_t)(fi - p.row0) * (size_t)(p.col1 - p.col0) + (size_t)(fj[u] - p.col0)) * 9;
+                            if (fi == fj[u] && (p.flags & B200RMSD_DIAG_ZERO)) {
+#pragma unroll
+                                for (int k = 0; k < 9; ++k) dst[k] = (k % 4 == 0) ? 1.0f : 0.0f;
+                                continue;
+                            }
+                            QcpInput qi;
+                            qi.inv_n = (double)inv_n;
+                            qi.Ga = (double)Ga[u];
+                            qi.Gb = (double)Gb[u];
+#pragma unroll
+                            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) qi.M[3 * r + q] = (double)M3[u][3 * q + r];
+                            float Wp[9], W[9], Rj[9], T[9];
+                            qcp_solve(qi, Wp, nullptr);
+#pragma unroll
+                            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                for (int b = 0; b < 3; ++b)
+                                    W[3 * a + b] = sel3(c, Wp[3 * a + b], Wp[3 * ((a + 2) % 3) + (b + 2) % 3],
+                                                        Wp[3 * ((a + 1) % 3) + (b + 1) % 3]);
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) Rj[k] = __ldg(p.frame_rot + fj[u] * 9 + k);
+#pragma unroll
+                            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                for (int b = 0; b < 3; ++b)
+                                    T[3 * a + b] = fmaf(Rj[3 * a + 2], W[6 + b], fmaf(Rj[3 * a + 1], W[3 + b], Rj[3 * a] * W[b]));
+#pragma unroll
+                            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                for (int b = 0; b < 3; ++b)
+                                    dst[3 * a + b] = fmaf(T[3 * a + 2], Ri[3 * b + 2], fmaf(T[3 * a + 1], Ri[3 * b + 1], T[3 * a] * Ri[3 * b]));
                         }
                     }
 #ifdef B200RMSD_DEV_SWITCHES
@@ -640,10 +699,11 @@ cudaError_t launch_allpairs_tc144_prepare(const float* xyz, int64_t n_frames, in
 
 int launch_allpairs_tc144_block(const ApGeometry& g, const char* base, int n_sel, int64_t n_frames, int64_t row0,
                                 int64_t row1, int64_t col0, int64_t col1, float* out, int64_t ld, float* out_t,
-                                int64_t ld_t, unsigned flags, int sm_count, cudaStream_t st)
+                                int64_t ld_t, float* out_rot, unsigned flags, int sm_count, cudaStream_t st)
 {
     (void)n_frames;
-    bool pair = g_ap_cta_pair != 0 && sm_count >= 2;
+    // rotations: single-CTA geometry, every pair computed (the mirrored entry would need the transposed rotation)
+    bool pair = g_ap_cta_pair != 0 && sm_count >= 2 && !out_rot;
 #ifdef B200RMSD_DEV_SWITCHES
     if (const char* v = getenv("B200RMSD_TC_PAIR")) pair = atoi(v) != 0 && sm_count >= 2;
 #endif
@@ -655,7 +715,9 @@ int launch_allpairs_tc144_block(const ApGeometry& g, const char* base, int n_sel
         !make_a_operand_map(&map_g_a, op(g.aug_a_hi_off), g.rows_pad, kApAugCols, g.aug_a_lo_off - g.aug_a_hi_off) ||
         !make_operand_map(&map_g_b, op(g.aug_b_off), g.rows_pad, kApAugCols, b_box))
         return set_error(B200RMSD_ECUDA, "allpairs: cuTensorMapEncodeTiled failed");
-    Tc144Params p = tc144_tiling(row0, row1, col0, col1, out_t != nullptr, pair);
+    Tc144Params p = tc144_tiling(row0, row1, col0, col1, out_t != nullptr || out_rot != nullptr, pair);
+    p.out_rot = out_rot;
+    p.frame_rot = op(g.rot_off);
     p.traces = op(g.traces_off);
     p.out = out;
     p.ld = ld;
@@ -689,21 +751,22 @@ int launch_allpairs_tc144_block(const ApGeometry& g, const char* base, int n_sel
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-#define B200_LAUNCH_TC144(EW, NP, PAIR)                                                                                    \
+#define B200_LAUNCH_TC144(EW, NP, PAIR, ROT)                                                                               \
     do {                                                                                                                   \
-        auto kern = allpairs_tc144_kernel<EW, NP, PAIR>;                                                                   \
+        auto kern = allpairs_tc144_kernel<EW, NP, PAIR, ROT>;                                                                \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                            \
         cfg.blockDim = dim3(64 + 32 * EW);                                                                                 \
         if (e == cudaSuccess)                                                                                              \
             e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_g_a, map_g_b, p);                                        \
     } while (0)
 #ifdef B200RMSD_DEV_SWITCHES
-    if (ew == 8 && np == 2) B200_LAUNCH_TC144(8, 2, false);
-    else if (ew == 16 && np == 1) B200_LAUNCH_TC144(16, 1, false);
+    if (ew == 8 && np == 2 && !out_rot) B200_LAUNCH_TC144(8, 2, false, false);
+    else if (ew == 16 && np == 1 && !out_rot) B200_LAUNCH_TC144(16, 1, false, false);
     else
 #endif
-    if (pair) B200_LAUNCH_TC144(16, 2, true);
-    else B200_LAUNCH_TC144(16, 2, false);
+    if (out_rot) B200_LAUNCH_TC144(16, 2, false, true);
+    else if (pair) B200_LAUNCH_TC144(16, 2, true, false);
+    else B200_LAUNCH_TC144(16, 2, false, false);
 #undef B200_LAUNCH_TC144
     if (e != cudaSuccess) return set_error(B200RMSD_ECUDA, "allpairs: %s", cudaGetErrorString(e));
     e = cudaGetLastError();

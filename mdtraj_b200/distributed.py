@@ -170,15 +170,179 @@ def symmetric_plan(n_frames: int, world: int):
     return plan
 
 
+class _PeerBuffer:
+    """A float32 (rows, cols) device buffer other processes can map (``b200rmsd_peer_alloc``); ``torch.as_tensor`` wraps
+    it without a copy through ``__cuda_array_interface__`` and keeps this object (and so the allocation) alive."""
+
+    def __init__(self, rows, cols):
+        import ctypes
+        from . import _capi
+        self.shape = (int(rows), int(cols))
+        self._ptr = ctypes.c_void_p()
+        self._handle = ctypes.create_string_buffer(64)
+        _capi.check(_capi.lib().b200rmsd_peer_alloc(max(1, rows * cols * 4), ctypes.byref(self._ptr), self._handle),
+                    "b200rmsd_peer_alloc")
+        self.ptr = int(self._ptr.value)
+        self.handle = bytes(self._handle.raw)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": "<f4", "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def free(self):
+        from . import _capi
+        if getattr(self, "ptr", 0):
+            _capi.lib().b200rmsd_peer_free(self.ptr)
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+class PeerExchange:
+    """Peer-visible row blocks of an (n_frames, n_frames) matrix, one per rank of ``group``, each mapped into every rank
+    that writes into it (CUDA IPC over NVLink).  Building one is a collective and costs tens of milliseconds (a
+    ``cudaMalloc`` of the row block, one handle exchange, one ``cudaIpcOpenMemHandle`` per peer), so it is built once per
+    (group, n_frames) and reused: ``rmsd_matrix_sharded`` keeps the exchanges it has built in a small cache.
+
+    ``block`` is this rank's (row1-row0, n_frames) CUDA tensor.  It is the memory the other ranks' kernels write into,
+    so a matrix computed through this exchange lives there until the next one is computed through the same exchange
+    (``.clone()`` what must outlive it).  ``ok`` is False on every rank when any rank could not allocate or map."""
+
+    def __init__(self, n_frames: int, group=None, device=None):
+        import ctypes
+        import torch
+        from . import _capi
+        dist = _dist()
+        L = _capi.lib()
+        self.group, self.n_frames = group, int(n_frames)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.bounds = all_shard_bounds(self.n_frames, self.world)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.plan = symmetric_plan(self.n_frames, self.world)[self.rank]
+        self.opened, self._buf, self.block, self.uses = {}, None, None, 0
+        r0, r1 = self.bounds[self.rank]
+        err = None
+        try:
+            with torch.cuda.device(self.device):
+                self._buf = _PeerBuffer(r1 - r0, self.n_frames)
+        except Exception as e:  # noqa: BLE001
+            err = repr(e)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, None if self._buf is None else self._buf.handle, group)
+        if all(h is not None for h in handles):
+            try:
+                with torch.cuda.device(self.device):
+                    for dst in sorted({c[4] for c in self.plan["compute"] if c[4] is not None}):
+                        p = ctypes.c_void_p()
+                        _capi.check(L.b200rmsd_peer_open(handles[dst], ctypes.byref(p)), "b200rmsd_peer_open")
+                        self.opened[dst] = int(p.value)
+            except Exception as e:  # noqa: BLE001
+                err = repr(e)
+        else:
+            err = err or "a peer could not allocate"
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err, group)
+        self.error = next((e for e in oks if e is not None), None)
+        self.ok = self.error is None
+        if self.ok:
+            self.block = torch.as_tensor(self._buf, device=self.device)
+            self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
+        else:
+            self.close(collective=False)
+
+    def handshake(self):
+        """Stream-ordered meeting point of the ranks (a one-float all-reduce, no host synchronisation): the work every
+        rank queued before it has completed, on every rank, before anything queued after it starts."""
+        _dist().all_reduce(self._token, group=self.group)
+
+    def close(self, collective=True):
+        """Unmap the peers' blocks and free this rank's (a collective when the exchange was usable: nobody frees a
+        block another rank may still be writing to)."""
+        import torch
+        from . import _capi
+        if collective and self.ok:
+            torch.cuda.synchronize(self.device)
+            _dist().barrier(self.group)
+        with torch.cuda.device(self.device):
+            for p in self.opened.values():
+                _capi.lib().b200rmsd_peer_close(p)
+        self.opened = {}
+        self.block = None
+        if self._buf is not None:
+            self._buf.free()
+            self._buf = None
+        self.ok = False
+
+
+_EXCHANGES = {}       # (group id, world, n_frames, device index) -> PeerExchange, most recently used last
+_MAX_EXCHANGES = 2
+
+
+def peer_exchange(n_frames: int, group=None, device=None):
+    """The cached ``PeerExchange`` of (group, n_frames), built on first use (collective: every rank of ``group`` calls
+    this with the same arguments, which ``rmsd_matrix_sharded`` guarantees).  At most two stay alive; the least recently
+    used one is closed first -- the same decision on every rank, since every rank sees the same sequence of calls."""
+    import torch
+    dist = _dist()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (id(group) if group is not None else 0, dist.get_world_size(group), int(n_frames), dev.index)
+    ex = _EXCHANGES.pop(key, None)
+    if ex is None:
+        while len(_EXCHANGES) >= _MAX_EXCHANGES:
+            _EXCHANGES.pop(next(iter(_EXCHANGES))).close()
+        ex = PeerExchange(n_frames, group, dev)
+    _EXCHANGES[key] = ex
+    return ex
+
+
+def release_peer_exchanges():
+    """Close every cached exchange (collective; call before ``destroy_process_group``)."""
+    while _EXCHANGES:
+        _EXCHANGES.pop(next(iter(_EXCHANGES))).close()
+
+
+def _matrix_sharded_peer(prep, ex, diag_zero, precise):
+    """The symmetric block plan with the transposed blocks written straight into their owners' row blocks over NVLink
+    by the kernel that computes them.  Two stream-ordered handshakes bracket the kernels: nobody writes into a block
+    its owner may still be reading from the previous matrix, and nobody reads its block before every writer is done."""
+    from . import allpairs
+    F, (r0, _) = ex.n_frames, ex.bounds[ex.rank]
+    out = ex.block
+    if ex.uses:
+        ex.handshake()
+    ex.uses += 1
+    for (a0, a1, c0, c1, dst) in sorted(ex.plan["compute"], key=lambda c: c[4] is None):  # remote blocks first
+        rows_view = out[a0 - r0: a1 - r0]
+        if dst is None:
+            allpairs.block(prep, a0, a1, c0, c1, rows_view, None, diag_zero, precise)
+        else:   # element (j, i) of rank dst's block: rows of dst start at bounds[dst][0], leading dimension F
+            addr = ex.opened[dst] + ((c0 - ex.bounds[dst][0]) * F + a0) * 4
+            allpairs.block(prep, a0, a1, c0, c1, rows_view, None, diag_zero, precise, out_t_ptr=addr, ld_t=F)
+    ex.handshake()
+    return out
+
+
 def rmsd_matrix_sharded(traj_dev, atom_indices=None, group=None, broadcast=True, diag_zero=True, precise=True,
-                        symmetric=True):
+                        symmetric=True, exchange="auto"):
     """Row-block sharded all-pairs matrix.  ``traj_dev``: a DeviceTrajectory with identical shape on every rank
     (rank 0's coordinates are broadcast over NCCL unless ``broadcast=False``).  Returns ``(row0, row1, block)`` where
     ``block`` is this rank's ``(row1-row0, F)`` CUDA tensor; the matrix is never gathered.
 
     ``symmetric=True`` (default): every unordered pair of frames is computed once (``symmetric_plan``); the ranks
-    exchange transposed blocks with NCCL send/recv over NVLink -- half the tensor work for F^2/(2W) floats of traffic
-    per rank.  ``symmetric=False``: every rank computes its whole row block, no exchange.
+    exchange transposed blocks over NVLink -- half the tensor work for F^2/(2W) floats of traffic per rank.
+    ``exchange="peer"``: the kernel that computes a block writes its transposed copy straight into the owner's row block
+    (a buffer mapped through CUDA IPC): the transfer rides under the tensor-core work, nothing is staged or copied on
+    arrival.  The row blocks then live in a ``PeerExchange`` that is built on the first call for (group, F) and reused:
+    **the returned block is overwritten by the next sharded matrix of the same size** -- ``.clone()`` it to keep it, or
+    pass your own ``PeerExchange`` as ``exchange``.  ``exchange="nccl"``: the transposed blocks go through NCCL send/recv
+    into a fresh tensor, one group per round of the plan, each issued while the next block is computed.  ``"auto"``
+    (default) tries ``"peer"`` and falls back to ``"nccl"`` on every rank when any rank cannot map its peers.
+    ``symmetric=False``: every rank computes its whole row block, no exchange.  Call ``release_peer_exchanges()`` before
+    ``destroy_process_group``.
     """
     import torch
     from . import allpairs
@@ -192,24 +356,51 @@ def rmsd_matrix_sharded(traj_dev, atom_indices=None, group=None, broadcast=True,
     if not symmetric or world == 1:
         return r0, r1, allpairs.rows(prep, r0, r1, diag_zero=diag_zero, precise=precise)
     dev = traj_dev.device
-    out = torch.empty((r1 - r0, F), dtype=torch.float32, device=dev)
     plan = symmetric_plan(F, world)[rank]
-    sends = []
-    for (a0, a1, c0, c1, dst) in plan["compute"]:
-        rows_view = out[a0 - r0: a1 - r0]
-        if dst is None:
-            allpairs.block(prep, a0, a1, c0, c1, rows_view, None, diag_zero, precise)
-        else:
+    if isinstance(exchange, PeerExchange):
+        ex = exchange
+        if not ex.ok or ex.n_frames != F or ex.world != world:
+            raise ValueError("rmsd_matrix_sharded: the PeerExchange does not match this matrix / group")
+        return r0, r1, _matrix_sharded_peer(prep, ex, diag_zero, precise)
+    if exchange not in ("auto", "peer", "nccl"):
+        raise ValueError("exchange must be 'auto', 'peer', 'nccl' or a PeerExchange")
+    if exchange != "nccl":
+        ex = peer_exchange(F, group, dev)
+        if ex.ok:
+            return r0, r1, _matrix_sharded_peer(prep, ex, diag_zero, precise)
+        if exchange == "peer":
+            raise RuntimeError("rmsd_matrix_sharded(exchange='peer'): the peer mapping could not be set up on every "
+                               "rank: " + str(ex.error))
+    out = torch.empty((r1 - r0, F), dtype=torch.float32, device=dev)
+    # Rounds d = 1 .. W/2: in round d every rank computes its block against rank + d, then sends the transposed copy
+    # there and receives the one rank - d computed for it -- one send and one receive per rank and round, issued as one
+    # NCCL group right after the block's kernel (the group waits for it on the compute stream) while the next block is
+    # already being computed.  The diagonal block comes last and covers the last round's transfer.  Every rank walks
+    # the rounds in the same order, so the groups pair up.
+    local = [c for c in plan["compute"] if c[4] is None]
+    by_round = {}
+    for c in plan["compute"]:
+        if c[4] is not None:
+            by_round.setdefault((c[4] - rank) % world, {"send": [], "recv": []})["send"].append(c)
+    for rc in plan["recv"]:
+        by_round.setdefault((rank - rc[0]) % world, {"send": [], "recv": []})["recv"].append(rc)
+    works, recvs = [], []
+    for d in sorted(by_round):
+        ops = []
+        for (a0, a1, c0, c1, dst) in by_round[d]["send"]:
             t = torch.empty((c1 - c0, a1 - a0), dtype=torch.float32, device=dev)
-            allpairs.block(prep, a0, a1, c0, c1, rows_view, t, diag_zero, precise)
-            sends.append((dst, t))
-    recvs = [(src, a0, a1, c0, c1, torch.empty((a1 - a0, c1 - c0), dtype=torch.float32, device=dev))
-             for (src, a0, a1, c0, c1) in plan["recv"]]
-    ops = [dist.P2POp(dist.isend, t, dst, group) for dst, t in sends] + \
-          [dist.P2POp(dist.irecv, buf, src, group) for (src, _, _, _, _, buf) in recvs]
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    for (_, a0, a1, c0, c1, buf) in recvs:
+            allpairs.block(prep, a0, a1, c0, c1, out[a0 - r0: a1 - r0], t, diag_zero, precise)
+            ops.append(dist.P2POp(dist.isend, t, dst, group))
+        for (src, a0, a1, c0, c1) in by_round[d]["recv"]:
+            buf = torch.empty((a1 - a0, c1 - c0), dtype=torch.float32, device=dev)
+            recvs.append((a0, a1, c0, c1, buf))
+            ops.append(dist.P2POp(dist.irecv, buf, src, group))
+        if ops:
+            works.extend(dist.batch_isend_irecv(ops))
+    for (a0, a1, c0, c1, _) in local:
+        allpairs.block(prep, a0, a1, c0, c1, out[a0 - r0: a1 - r0], None, diag_zero, precise)
+    for w in works:
+        w.wait()
+    for (a0, a1, c0, c1, buf) in recvs:
         out[a0 - r0: a1 - r0, c0:c1] = buf
     return r0, r1, out

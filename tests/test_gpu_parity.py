@@ -719,6 +719,53 @@ def test_allpairs_block_api(mdb, oracle_mod, ap_path):
         assert (blk - full[123:313, 123:313]).abs().max().item() < 2e-6
 
 
+@pytest.mark.parametrize("path,F,N,basins", [("tc", 700, 300, 1), ("tc", 900, 130, 3), ("simt", 300, 64, 1)])
+def test_allpairs_block_rotations(mdb, oracle_mod, ap_path, path, F, N, basins):
+    """north_star: the fused epilogue turns each 3x3 block "into an RMSD, plus a rotation matrix for superpose"
+    (b200rmsd_allpairs_block_rot_dev).  Row i of the rotations == what the one-vs-many path (and the reference's
+    md.rmsd / superpose, theobald_rmsd.cpp:280-334) finds for every frame against reference frame i: 1e-5 per element
+    against the float64 truth on MD-like frames, in one and in three basins (frames aligned onto different references
+    in the prepare step), on both kernels; the RMSDs of the same call are the matrix's own."""
+    import torch
+    from mdtraj_b200 import allpairs as AP
+    O = oracle_mod
+    if basins == 1:
+        X = O.synth_md(F, N, seed=91, rg=1.0, sigma=0.1)
+    else:
+        X = O.synth_md_basins(F, N, basins, seed=92, rg=1.0, sigma=0.1, separation=1.4, interleave=True)[0]
+    X = (X + np.float32(1.0)).astype(np.float32)           # off-centre frames: the rotations must not care
+    ap_path(path)
+    dt = mdb.DeviceTrajectory.from_host(X)
+    prep = AP.prepare(dt)
+    r0, r1, c0, c1 = 37, 37 + 83, 5, F - 11                # windows that start inside tiles
+    D, U = AP.block_rotations(prep, r0, r1, c0, c1)
+    full = unmirrored_matrix(dt)
+    assert torch.equal(D, full[r0:r1, c0:c1])
+    U = U.cpu().numpy()
+    assert U.shape == (r1 - r0, c1 - c0, 3, 3)
+    assert np.abs(np.linalg.det(U.astype(np.float64)) - 1).max() < 1e-5
+    impl = "reference" if O.ref_available() else "port"
+    for i in (r0, r0 + 41, r1 - 1):
+        _, truth_R = O.truth_superpose(X, X, i, None)      # frame j onto frame i, float64 Kabsch
+        got = U[i - r0]
+        err = np.abs(got - truth_R[c0:c1]).max()
+        assert err < 1e-5, f"row {i}: rotation elements {err:.2e} from the float64 truth"
+        _, want_R = O.superpose(X, X, i, None, impl=impl, return_rot=True)
+        assert_three_way(got, want_R[c0:c1], truth_R[c0:c1], f"all-pairs rotations, row {i}")
+        # the same rotations from the one-vs-many kernel of this library
+        d2 = mdb.DeviceTrajectory.from_host(X)
+        _, R1 = d2.superpose(d2, i, return_rotations=True)
+        assert np.abs(got - R1.cpu().numpy()[c0:c1]).max() < 1e-5
+        if c0 <= i < c1:
+            assert np.array_equal(got[i - c0], np.eye(3, dtype=np.float32))
+    # applying row i's rotations superposes the frames: plain RMSD after == QCP RMSD
+    i = r0 + 41
+    Xc = X.astype(np.float64) - X.astype(np.float64).mean(1, keepdims=True)
+    moved = np.einsum("jna,jab->jnb", Xc[c0:c1], U[i - r0].astype(np.float64))
+    plain = np.sqrt(((moved - Xc[i][None]) ** 2).sum((1, 2)) / N)
+    assert np.abs(plain - D[i - r0].cpu().numpy().astype(np.float64)).max() < 1e-5
+
+
 # ------------------------------------------------------------------ consumers of the matrix (SURVEY.md 8(f) next #3)
 def test_clustering_consumers_ala2_known_answers(mdb, golden, ala2):
     """examples/centroids.ipynb:117 -> centroid index 83 on the heavy atoms; examples/clustering.ipynb:101 -> squareform."""

@@ -28,7 +28,7 @@ for _ in range(3): run()
 torch.cuda.synchronize()
 geo = (ctypes.c_int * 8)()
 ctypes.CDLL(_capi.LIB_PATH).b200rmsd_debug_fused_geometry(0, N, int(idx.numel()), 1, 1, geo)
-print("geometry: G=%d nbuf=%d fpb=%d team_warps=%d lanes=%d smem=%d" % tuple(geo))
+print("geometry: G=%d nbuf=%d fpb=%d team_warps=%d lanes=%d smem=%d" % tuple(geo)[:6])
 per = (F // 148 + 2) * 8
 n = F // 148 // max(1, geo[2]) - 1   # slots per CTA
 buf = (ctypes.c_longlong * (per + 148 * 2))()
