@@ -121,7 +121,7 @@ int b200rmsd_superpose_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t fr
 int b200rmsd_rotate_dev(float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const float* rot,
                         void* scratch, size_t scratch_bytes, void* stream);
 
-/* ------------------------------------------------- "next" rows: rmsf, align/displace */
+/* ------------------------------------------------- "next" rows: rmsf, align/displace, lprmsd */
 
 /* Per-atom root-mean-square fluctuation over frames of  y = (x - c_f) . R_f  for the listed atoms
  * (idx int32 or NULL = all n_atoms).  rot (F,9) and centroid (F,3 doubles) come from b200rmsd_rmsd_dev
@@ -140,6 +140,27 @@ int b200rmsd_rmsf_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t f
  * _rmsd.pyx:746-749). */
 int b200rmsd_rot_msd_dev(const float* a_frame, const float* b_xyz, int64_t n_frames, int n_atoms, int64_t frame_stride,
                          const float* rot, int transpose, float* rot_out, float* out_rmsd, void* stream);
+
+/* LP-RMSD of every frame to one reference conformation: the RMSD minimised over rigid motions AND over the labels of
+ * exchangeable atoms.  Replaces the frame loop of md.lprmsd, _lprmsd.pyx:186-224, and the C++ under it
+ * (fancy_index2d, inplace_center_and_trace_atom_major, msd_atom_major, rot_atom_major, euclidean_permutation +
+ * Munkres::solve, sgemm33).  Per frame: rotation from the distinguishable atoms -> minimum-cost matching of squared
+ * distances inside every permute group -> QCP RMSD of the relabelled selection.
+ *   xyz          padded atom-major frames (as above); idx (n_sel sorted unique atom indices) or NULL = all n_atoms;
+ *   ref_sel      (n_sel,3) floats: the reference conformation's selected atoms, as they are (not centred);
+ *   dis, n_dis   positions INSIDE the selection (0 .. n_sel-1) of the atoms in no permute group; may be empty;
+ *   group_atoms  positions inside the selection of the permutable atoms, group after group; group_off: n_groups + 1
+ *                offsets into it; max_group: size of the largest group (sizes the shared-memory solver state);
+ *   out_rmsd     (F); out_rot (F,9) optional: rot1 . rot2, the rotation md.lprmsd(superpose=True) applies to the frame
+ *                after centring ALL its atoms (_lprmsd.pyx:217-220; apply with b200rmsd_center_trace_dev +
+ *                b200rmsd_rotate_dev); out_map (F,n_sel) optional: the matching, out_map[f*n_sel + i] = position of the
+ *                target atom paired with reference atom i.
+ * A frame is solved by one warp in shared memory: B200RMSD_EINVAL when the selection does not fit (about 3,500 atoms
+ * with one group of all of them). */
+int b200rmsd_lprmsd_dev(const float* xyz, int64_t n_frames, int n_atoms, int64_t frame_stride, const int32_t* idx,
+                        int n_sel, const float* ref_sel, const int32_t* dis, int n_dis, const int32_t* group_atoms,
+                        const int32_t* group_off, int n_groups, int max_group, float* out_rmsd, float* out_rot,
+                        int32_t* out_map, void* stream);
 
 /* ------------------------------------------------------------ all-pairs matrix */
 

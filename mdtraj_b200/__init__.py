@@ -26,6 +26,9 @@ def __getattr__(name):
     if name in ("DeviceTrajectory", "rmsd_device", "prepare_reference"):
         from . import device
         return getattr(device, name)
+    if name == "lprmsd":
+        from .lprmsd_impl import lprmsd
+        return lprmsd
     if name in ("rmsd_matrix", "rmsd_matrix_device"):
         from . import allpairs
         return getattr(allpairs, name)
@@ -42,7 +45,7 @@ def patch_mdtraj():
     """Swap this implementation into an importable ``mdtraj``.
 
     Replaces the Cython module ``mdtraj._rmsd`` (``mdtraj/rmsd/_rmsd.pyx``), the two names ``mdtraj/__init__.py:118``
-    re-exports from it (``mdtraj.rmsd``, ``mdtraj.rmsf``) and ``Trajectory.superpose`` (trajectory.py:1083-1173, fused into
+    re-exports from it (``mdtraj.rmsd``, ``mdtraj.rmsf``), ``mdtraj.lprmsd`` (``_lprmsd.pyx:71``) and ``Trajectory.superpose`` (trajectory.py:1083-1173, fused into
     one call here).  ``Trajectory.center_coordinates`` is left alone: upstream's unweighted branch (trajectory.py:2130-2135)
     looks ``mdtraj._rmsd._center_inplace_atom_major`` up at call time and so lands in the CUDA library, and its
     mass-weighted branch keeps working.  Everything else of mdtraj is untouched.  tests/test_reference_integration.py runs
@@ -59,5 +62,12 @@ def patch_mdtraj():
     mdtraj._rmsd = ours
     mdtraj.rmsd = ours.rmsd
     mdtraj.rmsf = ours.rmsf
+    try:   # md.lprmsd (mdtraj/__init__.py:117 imports the name from the Cython module mdtraj._lprmsd)
+        from . import lprmsd_impl
+        import mdtraj._lprmsd as ref_lp
+        ref_lp.lprmsd = lprmsd_impl.lprmsd
+        mdtraj.lprmsd = lprmsd_impl.lprmsd
+    except ImportError:  # a reference build without the optional LP-RMSD extension
+        pass
     mdtraj.Trajectory.superpose = superpose_host
     return mdtraj

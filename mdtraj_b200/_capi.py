@@ -47,6 +47,7 @@ SIGNATURES = {
     "b200rmsd_allpairs_configure": (_i32, [_i32, _i32]),
     "b200rmsd_allpairs_set_cta_pair": (_i32, [_i32]),
     "b200rmsd_allpairs_info_dev": (_i32, [_vp, _sz, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_f32), _vp, _i32, _vp]),
+    "b200rmsd_lprmsd_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200rmsd_allpairs_prepare_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _sz, _vp]),
     "b200rmsd_allpairs_block_dev": (_i32, [_vp, _sz, _i64, _i32, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _u32, _vp]),
     "b200rmsd_allpairs_block_rot_dev": (_i32, [_vp, _sz, _i64, _i32, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _u32, _vp]),

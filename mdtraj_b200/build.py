@@ -17,7 +17,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200rmsd.so")
-SOURCES = ["capi.cu", "host_pipeline.cu", "one_vs_many.cu", "aux_kernels.cu", "frame_resident.cu", "allpairs.cu", "allpairs_refs.cu", "allpairs_tc144.cu", "cluster_ops.cu"]
+SOURCES = ["capi.cu", "host_pipeline.cu", "one_vs_many.cu", "aux_kernels.cu", "frame_resident.cu", "allpairs.cu", "allpairs_refs.cu", "allpairs_tc144.cu", "cluster_ops.cu", "lprmsd.cu"]
 HEADERS = ["host_pipeline.cu", "allpairs_refs.cu", "common.cuh", "kernels.cuh", "qcp.cuh", "allpairs_layout.cuh", "tc_ptx.cuh", "../../include/b200rmsd.h"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -150,6 +150,17 @@ def msd_atom_major(a, b, Ga, Gb, want_rot=False, impl="port"):
     return (m, rot.reshape(3, 3)) if want_rot else m
 
 
+def rot_atom_major(a, rot, impl="port"):
+    """rot_atom_major (rotation.h:7): (n,3) float32 C-contiguous ``a`` <- a . rot, in place."""
+    assert a.dtype == np.float32 and a.flags.c_contiguous
+    rot = _c32(rot).reshape(9)
+    if impl == "port":
+        port_lib().oracle_rot_atom_major(a.shape[0], _ptr(a), _ptr(rot))
+    else:
+        ref_lib().rot_atom_major(a.shape[0], _ptr(a), _ptr(rot))
+    return a
+
+
 def one_vs_many_centered(target, target_g, ref_frame, ref_g, impl="port", parallel=True):
     """Loop of _rmsd.pyx:217-224 on already-centred float32 data."""
     target = _c32(target); ref_frame = _c32(ref_frame); target_g = _c32(target_g)
@@ -255,6 +266,102 @@ def superpose(xyz, ref_xyz, frame=0, atom_indices=None, ref_atom_indices=None, i
 # --------------------------------------------------------------------------
 # float64 truth (independent of both C routes)
 # --------------------------------------------------------------------------
+# --------------------------------------------------------------------------
+# md.lprmsd semantics (mdtraj/rmsd/_lprmsd.pyx:71-221) on raw arrays
+# --------------------------------------------------------------------------
+def min_cost_matching(cost):
+    """Minimum-cost perfect matching of a square float64 cost matrix: row i -> column ``result[i]``.  Stands in for
+    Munkres::solve (mdtraj/rmsd/src/Munkres.cpp; used at euclidean_permutation.cpp:56) -- both are exact, so they agree
+    whenever the optimum is unique; pinned to the reference's own known answer (tests/test_lprmsd.py:12-22) and to
+    md.lprmsd outputs in tests/test_oracle.py."""
+    from scipy.optimize import linear_sum_assignment
+    rows, cols = linear_sum_assignment(np.asarray(cost, dtype=np.float64))
+    out = np.empty(len(rows), dtype=np.int64)
+    out[rows] = cols
+    return out
+
+
+def euclidean_permutation(ref, tgt, groups):
+    """euclidean_permutation.cpp:16-72 with its call-site roles (``_lprmsd.pyx:210``: rows = reference atoms, columns =
+    target atoms): mapping[i] = target atom matched to reference atom i; atoms in no group map to themselves.  Costs are
+    float32 differences and squares summed in float64 (lines 34-38).  Groups never interact (cross-group entries are
+    DBL_MAX), so each is matched on its own."""
+    ref = _c32(ref); tgt = _c32(tgt)
+    mapping = np.arange(ref.shape[0], dtype=np.int64)
+    for g in groups:
+        g = np.asarray(g, dtype=np.int64)
+        if len(g) < 2:
+            continue
+        d = (ref[g][:, None, :] - tgt[g][None, :, :]).astype(np.float32)
+        cost = (d * d).astype(np.float32).astype(np.float64).sum(-1)
+        mapping[g] = g[min_cost_matching(cost)]
+    return mapping
+
+
+def lprmsd(target_xyz, ref_xyz, frame=0, atom_indices=None, permute_groups=None, superpose=False, impl="port",
+           return_mapping=False):
+    """md.lprmsd on raw (F,N,3) arrays, step by step as _lprmsd.pyx:131-227 does it.  Returns the (F,) float32 distances
+    (and, with ``superpose``, the modified copy of ``target_xyz``; with ``return_mapping`` the (F,n_sel) matchings)."""
+    xyz = np.array(target_xyz, dtype=np.float32, order="C", copy=True)
+    ref_xyz = np.asarray(ref_xyz)
+    F, N, _ = xyz.shape
+    atom_indices = np.arange(N) if atom_indices is None else np.unique(np.asarray(atom_indices, dtype=np.int64))
+    groups = [atom_indices] if permute_groups is None else [np.unique(np.asarray(g, dtype=np.int64)) for g in permute_groups]
+    groups_rel = [np.searchsorted(atom_indices, g) for g in groups]                                        # :139
+    flat = np.concatenate(groups_rel) if groups_rel else np.zeros(0, dtype=np.int64)
+    dis = np.setdiff1d(np.arange(len(atom_indices)), flat)                                                 # :140-141
+    n = len(atom_indices)
+    ref = np.array(ref_xyz[frame, atom_indices, :], dtype=np.float32, copy=True)[None]                    # :160
+    ref_g = float(center_and_trace(ref, impl)[0])                                                          # :163
+    if len(dis):
+        ref_dis = np.array(ref_xyz[frame, atom_indices[dis], :], dtype=np.float32, copy=True, order="C")[None]   # :176-177
+        ref_g_dis = float(center_and_trace(ref_dis, impl)[0])
+    out = np.zeros(F, dtype=np.float32)
+    maps = np.empty((F, n), dtype=np.int64)
+    for i in range(F):
+        t = np.ascontiguousarray(xyz[i, atom_indices, :])[None]                                            # :188-190
+        t_g = float(center_and_trace(t, impl)[0])
+        rot1 = np.eye(3, dtype=np.float32)
+        if len(dis):
+            t_dis = np.ascontiguousarray(t[0][dis])[None]                                                  # :197-199
+            t_g_dis = float(center_and_trace(t_dis, impl)[0])
+            _, rot1 = msd_atom_major(t_dis[0], ref_dis[0], t_g_dis, ref_g_dis, True, impl)                 # :202-204
+            rot_atom_major(t[0], rot1, impl)                                                               # :207
+        mapping = euclidean_permutation(ref[0], t[0], groups_rel)                                          # :210
+        maps[i] = mapping
+        t2 = np.ascontiguousarray(t[0][mapping])                                                           # :212
+        if superpose:
+            msd, rot2 = msd_atom_major(t2, ref[0], t_g, ref_g, True, impl)                                 # :217
+            whole = np.ascontiguousarray(xyz[i])[None]
+            center_and_trace(whole, impl)                                                                  # :218
+            rot3 = np.zeros((3, 3), dtype=np.float32)                                                      # :219 sgemm33:
+            for a in range(3):                                                                             # float32, k ascending
+                for b in range(3):
+                    o = np.float32(0)
+                    for k in range(3):
+                        o = np.float32(o + np.float32(rot1[a, k] * rot2[k, b]))
+                    rot3[a, b] = o
+            xyz[i] = rot_atom_major(whole[0], rot3, impl)                                                  # :220
+        else:
+            msd = msd_atom_major(ref[0], t2, t_g, ref_g, False, impl)                                      # :222
+        out[i] = np.sqrt(np.float32(max(msd, 0.0)))
+    res = (out, xyz) if superpose else out
+    if return_mapping:
+        return (res + (maps,)) if isinstance(res, tuple) else (res, maps)
+    return res
+
+
+def truth_lprmsd_given_mapping(target_xyz, ref_frame, atom_indices, mapping):
+    """float64 Kabsch RMSD of the relabelled selection: what step 3 should give for a fixed matching."""
+    atom_indices = np.asarray(atom_indices, dtype=np.int64)
+    ref = np.asarray(ref_frame, dtype=np.float64)[atom_indices]
+    out = np.empty(len(target_xyz))
+    for i in range(len(target_xyz)):
+        t = np.asarray(target_xyz[i], dtype=np.float64)[atom_indices][np.asarray(mapping[i], dtype=np.int64)]
+        out[i] = truth_kabsch(t, ref)[1]
+    return out
+
+
 def truth_kabsch(mobile, target):
     """Optimal rotation R (3,3) with mobile_c @ R ~ target_c, and the RMSD, float64."""
     P = np.asarray(mobile, dtype=np.float64); Q = np.asarray(target, dtype=np.float64)

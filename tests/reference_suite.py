@@ -8,7 +8,7 @@ top-level `tests` package never leak into the main pytest process).  The referen
 not in /root/reference, and PyTables is not installed, so `md.load` is replaced by a stand-in that returns seeded
 MD-like trajectories with a real mdtraj.Topology (22 atoms, 11 residues) for the file names the tests ask for; the test
 bodies -- /root/reference/tests/test_rmsd.py:36-334, test_rmsd_memmap.py:11-56, test_alignment.py:39-65,
-test_trajectory.py:316-347 -- run as they are.  The reference's conftest.py is not loaded (its pytest_configure untars the
+test_trajectory.py:316-347, test_lprmsd.py:25-79,110-130 -- run as they are.  The reference's conftest.py is not loaded (its pytest_configure untars the
 missing data); the two fixtures the tests use, get_fn and the parametrised flags, are passed as plain arguments.
 """
 import importlib.util
@@ -48,6 +48,12 @@ CASES = [  # (file, function, kwargs)
     ("test_alignment.py", "test_rmsd_nonzero", None),
     ("test_alignment.py", "test_transform", None),
     ("test_alignment.py", "test_transform2", None),
+    ("test_lprmsd.py", "test_lprmsd_null", None),
+    ("test_lprmsd.py", "test_lprmsd_0", None),
+    ("test_lprmsd.py", "test_lprmsd_1", None),
+    ("test_lprmsd.py", "test_lprmsd_2", None),
+    ("test_lprmsd.py", "test_lprmsd_4", {}),
+    ("test_lprmsd.py", "test_lprmsd_5", {}),
     ("test_trajectory.py", "test_center", {}),
     ("test_trajectory.py", "test_center_aind", {}),
 ]
@@ -96,6 +102,8 @@ def main():
         mdtraj_b200.patch_mdtraj()
         import mdtraj_b200._rmsd as ours
         assert md.rmsd is ours.rmsd and md.rmsf is ours.rmsf and md._rmsd is ours
+        from mdtraj_b200 import lprmsd_impl
+        assert md.lprmsd is lprmsd_impl.lprmsd
     md.load = make_loader(md)
     results = {}
     mods = {}

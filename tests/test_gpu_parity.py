@@ -9,6 +9,7 @@ elements 1e-5; superposed coordinates 1e-5 nm (float32 coordinates of magnitude 
 ~5e-7 nm of rounding each way); atom selection / frame order exact.
 Mirrors the reference's tests/test_rmsd.py where noted.
 """
+import os
 import warnings
 
 import numpy as np
@@ -764,6 +765,104 @@ def test_allpairs_block_rotations(mdb, oracle_mod, ap_path, path, F, N, basins):
     moved = np.einsum("jna,jab->jnb", Xc[c0:c1], U[i - r0].astype(np.float64))
     plain = np.sqrt(((moved - Xc[i][None]) ** 2).sum((1, 2)) / N)
     assert np.abs(plain - D[i - r0].cpu().numpy().astype(np.float64)).max() < 1e-5
+
+
+# ------------------------------------------------------------------ md.lprmsd (last "next" row)
+def _lprmsd_case(gold, name):
+    from test_oracle import lprmsd_case
+    return lprmsd_case(gold, name)
+
+
+def test_lprmsd_matches_real_reference_goldens(mdb, oracle_mod):
+    """Every golden case of the real md.lprmsd (tests/golden/make_golden_lprmsd.py): distances within 1e-5 nm (or, for the
+    float32 reference's own noise, at least as close to the float64 Kabsch RMSD of the same matching), the matching equal
+    to the oracle's, superposed coordinates within 1e-5 of what the reference leaves in target.xyz."""
+    O = oracle_mod
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "lprmsd_outputs.npz"))
+    for name in map(str, gold["cases"]):
+        X, ref, idx, groups = _lprmsd_case(gold, name)
+        t, r = mdb.Trajectory(X.copy()), mdb.Trajectory(ref.copy())
+        d, mapping = mdb.lprmsd(t, r, 0, atom_indices=idx, permute_groups=groups, return_mapping=True)
+        assert np.array_equal(t.xyz, X), "lprmsd without superpose must not touch the target"
+        _, want_map = O.lprmsd(X, ref, 0, idx, groups, return_mapping=True)
+        assert np.array_equal(mapping, want_map), name
+        sel = np.arange(X.shape[1]) if idx is None else np.unique(idx)
+        truth = O.truth_lprmsd_given_mapping(X, ref[0], sel, want_map)
+        assert_three_way(d, gold[name + "_lprmsd"], truth, f"lprmsd {name}")
+        d2 = mdb.lprmsd(t, r, 0, atom_indices=idx, permute_groups=groups, superpose=True)
+        assert_three_way(d2, gold[name + "_lprmsd_superpose"], truth, f"lprmsd superpose {name}")
+        assert np.abs(t.xyz - gold[name + "_xyz_superposed"]).max() < 1e-5, name
+        # a DeviceTrajectory goes the same way and is modified in place
+        dt = mdb.DeviceTrajectory.from_host(X)
+        d3 = mdb.lprmsd(dt, r, 0, atom_indices=idx, permute_groups=groups, superpose=True)
+        assert np.array_equal(d3, d2) and np.array_equal(dt.xyz, t.xyz)
+
+
+def test_lprmsd_reference_test_semantics(mdb):
+    """/root/reference/tests/test_lprmsd.py:25-79 restated on seeded data: identical frames, a pure relabelling, a pure
+    rotation, both; and permute_groups=[[]] == md.rmsd (test_lprmsd_4, :110-120)."""
+    rng = np.random.RandomState(0)
+    ref = rng.randn(1, 10, 3).astype(np.float32)
+    T = mdb.Trajectory
+    assert mdb.lprmsd(T(ref.copy()), T(ref.copy()))[0] < 1e-3
+    assert mdb.lprmsd(T(ref[:, rng.permutation(10)].copy()), T(ref.copy()))[0] < 1e-3
+    ref = rng.randn(1, 50, 3).astype(np.float32)
+    from oracle import oracle as O
+    rot = O.random_rotations(1, np.random.default_rng(3))[0]
+    new = ref.dot(rot).astype(np.float32)
+    assert mdb.lprmsd(T(new.copy()), T(ref.copy()), permute_groups=[[]])[0] < 1e-2
+    mapping = np.concatenate((rng.permutation(10), 10 + np.arange(40)))
+    new = ref[:, mapping].dot(rot).astype(np.float32)
+    assert mdb.lprmsd(T(new.copy()), T(ref.copy()), permute_groups=[np.arange(10)])[0] < 1e-2
+    X = (ref + 0.05 * rng.randn(20, 50, 3)).astype(np.float32)
+    idx = rng.permutation(50)[:45]
+    got = mdb.lprmsd(T(X.copy()), T(ref.copy()), atom_indices=idx, permute_groups=[[]])
+    want = mdb.rmsd(T(X.copy()), T(ref.copy()), atom_indices=np.unique(idx))
+    assert np.abs(got - want).max() < 1e-5
+
+
+def test_lprmsd_water_box_vs_oracle(mdb, oracle_mod):
+    """2000 frames of 60 distinguishable atoms + two groups of 120 exchangeable ones, every frame relabelled at random and
+    moved rigidly: the matching undoes the relabelling, distances agree with the oracle three ways on a sample of
+    frames; a long group (600) runs through the same kernel."""
+    O = oracle_mod
+    rng = np.random.default_rng(7)
+    F, N = 2000, 300
+    groups = [np.arange(60, 180), np.arange(180, 300)]
+    ref = (rng.standard_normal((1, N, 3)) * 1.2).astype(np.float32)
+    X = np.repeat(ref, F, 0) + 0.02 * rng.standard_normal((F, N, 3))
+    perms = np.tile(np.arange(N), (F, 1))
+    for f in range(F):
+        for g in groups:
+            perms[f, g] = rng.permutation(g)
+    X = np.take_along_axis(X, perms[:, :, None], 1)            # target atom k is the reference's atom perms[f, k]
+    X = (np.einsum("fni,fij->fnj", X, O.random_rotations(F, rng)) + rng.uniform(-3, 3, (F, 1, 3))).astype(np.float32)
+    d, mapping = mdb.lprmsd(mdb.Trajectory(X), mdb.Trajectory(ref), permute_groups=groups, return_mapping=True)
+    inv = np.empty_like(perms)
+    np.put_along_axis(inv, perms, np.tile(np.arange(N), (F, 1)), 1)   # reference atom i sits at target position inv[f, i]
+    # the optimum undoes the relabelling except where two atoms of a group happen to sit within the noise of each other
+    # (a random cloud has a few such pairs); the exact comparison is the one with the oracle's solver below
+    assert (mapping == inv).mean() > 0.999, (mapping == inv).mean()
+    assert all(np.array_equal(np.sort(m), np.arange(N)) for m in mapping[::50]), "every matching is a permutation"
+    assert 0.025 < d.min() and d.max() < 0.045                         # ~ sigma * sqrt(3)
+    sample = np.arange(0, F, 97)
+    want, want_map = O.lprmsd(X[sample], ref, 0, None, groups, impl="reference" if O.ref_available() else "port",
+                              return_mapping=True)
+    assert np.array_equal(mapping[sample], want_map)
+    truth = O.truth_lprmsd_given_mapping(X[sample], ref[0], np.arange(N), want_map)
+    assert_three_way(d[sample], want, truth, "lprmsd water box")
+    # one long group
+    N2 = 640
+    ref2 = (rng.standard_normal((1, N2, 3)) * 1.5).astype(np.float32)
+    X2 = np.repeat(ref2, 6, 0) + 0.01 * rng.standard_normal((6, N2, 3))
+    g2 = np.arange(40, N2)
+    for f in range(6):
+        X2[f, g2] = X2[f, rng.permutation(g2)]
+    X2 = X2.astype(np.float32)
+    d2, m2 = mdb.lprmsd(mdb.Trajectory(X2), mdb.Trajectory(ref2), permute_groups=[g2], return_mapping=True)
+    w2, wm2 = O.lprmsd(X2, ref2, 0, None, [g2], return_mapping=True)
+    assert np.array_equal(m2, wm2)
+    assert_three_way(d2, w2, O.truth_lprmsd_given_mapping(X2, ref2[0], np.arange(N2), wm2), "lprmsd long group")
 
 
 # ------------------------------------------------------------------ consumers of the matrix (SURVEY.md 8(f) next #3)

@@ -264,3 +264,20 @@ def test_allpairs_workspace_geometry():
     assert 3.8e8 < wb(100000, 300) < 3.9e8             # SIMT layout: one (F,3,320) float copy + traces
     assert L.b200rmsd_allpairs_configure(512, 0) == 0
     assert 2.45e9 < wb(100000, 300) < 2.50e9
+
+
+def test_lprmsd_validation_mirrors_the_reference():
+    """md.lprmsd argument checks (_lprmsd.pyx:230-273) raise before any device work, with the reference's messages."""
+    import mdtraj_b200 as mdb
+    X = np.zeros((3, 10, 3), dtype=np.float32)
+    T = mdb.Trajectory
+    with pytest.raises(ValueError, match="Input trajectories must have same number of atoms. found 10 and 9."):
+        mdb.lprmsd(T(X), T(X[:, :9].copy()))
+    with pytest.raises(ValueError, match="Cannot calculate RMSD of frame 3: reference has only 3 frames."):
+        mdb.lprmsd(T(X), T(X), 3)
+    with pytest.raises(ValueError, match="atom_indices must be valid positive indices"):
+        mdb.lprmsd(T(X), T(X), atom_indices=[0, 10])
+    with pytest.raises(ValueError, match="must be a subset of atom_indices"):
+        mdb.lprmsd(T(X), T(X), atom_indices=[0, 1, 2], permute_groups=[[2, 3]])
+    with pytest.raises(ValueError, match="permute_groups must be mutually disjoint sets"):
+        mdb.lprmsd(T(X), T(X), permute_groups=[[1, 2], [2, 3]])

@@ -5,8 +5,12 @@
   * float64 Kabsch truth.
 Tolerance: the reference's SSE build sums M in four lanes, the restatement sequentially, so agreement is to
 float32 rounding noise: 1e-5 nm on iid / ala2 data (noise there is <= 3e-7)."""
+import os
+
 import numpy as np
 import pytest
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 SYNTH = [("iid", 64, 100, 11), ("iid", 33, 22, 12), ("iid", 16, 1000, 13), ("md", 40, 303, 14), ("iid", 5, 4100, 15)]
 IMPLS = ["port", "reference"]
@@ -116,3 +120,51 @@ def test_rotation_convention(oracle_mod):
     a = (b @ R.T).astype(np.float32); b = b.astype(np.float32)  # a @ R == b
     msd, rot = O.msd_atom_major(a, b, float((a * a).sum()), float((b * b).sum()), want_rot=True)
     assert msd < 1e-6 and np.abs(rot - R).max() < 1e-5 and abs(np.linalg.det(rot.astype(float)) - 1) < 1e-5
+
+
+# ------------------------------------------------------------------ md.lprmsd (last "next" row)
+def lprmsd_case(gold, name):
+    """(xyz, ref, atom_indices or None, permute_groups or None) of a case of tests/golden/lprmsd_outputs.npz."""
+    idx = gold[name + "_idx"] if bool(gold[name + "_has_idx"]) else None
+    groups = None
+    if bool(gold[name + "_has_groups"]):
+        flat, lens = gold[name + "_groups_flat"], gold[name + "_groups_len"]
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        groups = [flat[offs[i]: offs[i + 1]] for i in range(len(lens))]
+    return gold[name + "_xyz"], gold[name + "_ref"], idx, groups
+
+
+def test_min_cost_matching_pinned_to_munkres(oracle_mod):
+    """The oracle's exact assignment solver returns what Munkres::solve returns: the reference's own known answer
+    (tests/test_lprmsd.py:12-22) and six random 12x12 cost matrices run through mdtraj._lprmsd._munkres."""
+    O = oracle_mod
+    gold = np.load(os.path.join(GOLDEN_DIR, "lprmsd_outputs.npz"))
+    known = np.array([[0, 0, 1], [1, 0, 0], [0, 1, 0]], dtype=np.int32)
+    assert np.array_equal(gold["munkres_known"], known)
+    m = O.min_cost_matching(np.array([[7, 4, 3], [6, 8, 5], [9, 4, 4]], dtype=np.float64))
+    assert np.array_equal(np.eye(3, dtype=np.int32)[m], known)
+    for cost, mask in zip(gold["munkres_costs"], gold["munkres_masks"]):
+        assert np.array_equal(np.eye(12, dtype=np.int32)[O.min_cost_matching(cost)], mask)
+
+
+@pytest.mark.parametrize("impl", ["port", "reference"])
+def test_lprmsd_oracle_reproduces_real_mdtraj(oracle_mod, impl):
+    """oracle.lprmsd (restatement of _lprmsd.pyx:131-227) against the outputs of the real md.lprmsd on every golden
+    case, distances and superposed coordinates: bit for bit on the compiled reference's arithmetic, 3e-5 / 1e-5 on the port."""
+    O = oracle_mod
+    _impl_ok(O, impl)
+    gold = np.load(os.path.join(GOLDEN_DIR, "lprmsd_outputs.npz"))
+    for name in gold["cases"]:
+        X, ref, idx, groups = lprmsd_case(gold, str(name))
+        d = O.lprmsd(X, ref, 0, idx, groups, impl=impl)
+        d2, xyz = O.lprmsd(X, ref, 0, idx, groups, superpose=True, impl=impl)
+        if impl == "reference":
+            assert np.array_equal(d, gold[f"{name}_lprmsd"]), name
+            assert np.array_equal(d2, gold[f"{name}_lprmsd_superpose"]), name
+            assert np.abs(xyz - gold[f"{name}_xyz_superposed"]).max() < 2e-6, name  # rot_atom_major: SSE vs numpy order
+        else:
+            # float32 msd = (G_a + G_b - 2 lambda) / n in both, summed in a different order: at an RMSD of 0.03 nm under
+            # traces of ~50 nm^2 that is ~1e-5 nm of noise (the same class as SURVEY.md Appendix C)
+            assert np.abs(d - gold[f"{name}_lprmsd"]).max() < 3e-5, name
+            assert np.abs(d2 - gold[f"{name}_lprmsd_superpose"]).max() < 3e-5, name
+            assert np.abs(xyz - gold[f"{name}_xyz_superposed"]).max() < 1e-5, name

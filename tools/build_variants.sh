@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p variants
-SRC="capi.cu host_pipeline.cu one_vs_many.cu aux_kernels.cu frame_resident.cu allpairs.cu allpairs_refs.cu allpairs_tc144.cu cluster_ops.cu"
+SRC="capi.cu host_pipeline.cu one_vs_many.cu aux_kernels.cu frame_resident.cu allpairs.cu allpairs_refs.cu allpairs_tc144.cu cluster_ops.cu lprmsd.cu"
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   ( cd mdtraj_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared -Xcompiler -fPIC,-pthread \
