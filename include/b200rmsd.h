@@ -326,8 +326,18 @@ int b200rmsd_center_host_multi(float* xyz, int64_t n_frames, int n_atoms, float*
  *   copy_threads:    threads of the memcpy pool that stages pageable host memory through page-locked buffers (default:
  *                    all hardware threads but one, at most 24; takes effect before the pool's first use);
  *   chunk_mb:        MB of padded coordinates per chunk when the caller's memory is page-locked (default 64);
- *   staged_chunk_mb: the same for pageable memory (default 16: three staging lanes stay inside a 60 MB host L3). */
+ *   staged_chunk_mb: the same for pageable memory when whole chunks are staged (default 16: three staging lanes stay inside
+ *                    a 60 MB host L3); streamed staging (below) uses max(chunk_mb, staged_chunk_mb). */
 int b200rmsd_host_configure(int copy_threads, int chunk_mb, int staged_chunk_mb);
+
+/* How pageable coordinates reach the device.  piece_kb >= 0 (default 0): STREAMED staging -- every thread of the memcpy
+ * pool copies a piece of the chunk (whole frames, piece_kb KB; 0 = chosen so that all slots of all threads of all ranks on
+ * the host together stay near 24 MB) into one of its two page-locked slots and sends it to its place in the device chunk
+ * at once, so staging writes and DMA reads stay in the host's last-level cache and DRAM sees one pass per byte instead of
+ * three (eight ranks on one 32-thread host: 5.1e6 -> 9.4e6 rmsd/s at 1,000 atoms; profiles/r02_host_staging.jsonl).
+ * piece_kb < 0: the whole chunk is staged into one buffer and sent with one copy (round-1 behaviour).  Frames
+ * larger than 2 MB always take the latter. */
+int b200rmsd_host_configure_staging(int piece_kb);
 
 /* Release the internal per-device workspaces of the host API. */
 void b200rmsd_release_workspaces(void);

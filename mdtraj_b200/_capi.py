@@ -42,6 +42,7 @@ SIGNATURES = {
                                              _i32]),
     "b200rmsd_center_host_multi": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32]),
     "b200rmsd_host_configure": (_i32, [_i32, _i32, _i32]),
+    "b200rmsd_host_configure_staging": (_i32, [_i32]),
     "b200rmsd_release_workspaces": (None, []),
     "b200rmsd_allpairs_workspace_bytes": (_sz, [_i64, _i32]),
     "b200rmsd_allpairs_configure": (_i32, [_i32, _i32]),

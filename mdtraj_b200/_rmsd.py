@@ -56,12 +56,15 @@ def set_devices(indices) -> None:
     _state["devices"] = None if indices is None else [int(i) for i in indices]
 
 
-def set_host_pipeline(copy_threads=None, chunk_mb=None, staged_chunk_mb=None) -> None:
+def set_host_pipeline(copy_threads=None, chunk_mb=None, staged_chunk_mb=None, stage_piece_kb=None) -> None:
     """Settings of the host-array pipeline (``b200rmsd_host_configure``): threads of the memcpy pool that stages pageable
     memory through page-locked buffers (before its first use), MB of coordinates per chunk for page-locked (default 64)
-    and for pageable (default 16) caller memory."""
+    and for pageable (default 16) caller memory.  ``stage_piece_kb`` (``b200rmsd_host_configure_staging``): KB per piece of
+    the streamed staging of pageable memory (0 = automatic, the default; -1 = stage whole chunks)."""
     _capi.check(_capi.lib().b200rmsd_host_configure(int(copy_threads or 0), int(chunk_mb or 0), int(staged_chunk_mb or 0)),
                 "b200rmsd_host_configure")
+    if stage_piece_kb is not None:
+        _capi.check(_capi.lib().b200rmsd_host_configure_staging(int(stage_piece_kb)), "b200rmsd_host_configure_staging")
 
 
 def current_device() -> int:

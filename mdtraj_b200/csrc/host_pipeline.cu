@@ -21,6 +21,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -44,15 +45,78 @@ int g_staged_chunk_mb = 16;    // pageable caller memory: three lanes of staging
                                // so that the DMA engine reads what the memcpy pool has just written from cache
                                // (measured on a 16-core Xeon, 60 MB L3: 16 MB 52 GB/s, 64 MB 46 GB/s, page-locked 55 GB/s)
 
+int g_stage_piece_kb = 0;       // streamed staging (below): 0 = automatic piece size, > 0 = KB per piece, < 0 = off (the whole
+                               // chunk is staged into the lane's buffer and sent with one copy)
+
+// ---------------------------------------------------------------------------------------------
+// Streamed staging of pageable memory.  Staging a whole 16 MB chunk and then sending it costs the host's memory system
+// three passes per byte (read the caller's array, write the staging buffer, DMA-read the staging buffer): measured on the
+// 8-GPU box (one socket, 32 hardware threads, ~200 GB/s of DRAM bandwidth) the eight ranks of a torchrun job together
+// staged 63-67 GB/s whatever the chunk size, against 187 GB/s from page-locked arrays.  Here every pool thread owns two
+// small page-locked slots: it copies a PIECE of the chunk (a few hundred KB of whole rows) into a slot, sends that slot
+// to its place in the device chunk on the lane's stream right away and records an event; when it comes back to the slot two
+// pieces later it waits for that event.  All slots of all threads (and of all ranks sharing the host) together are a few
+// tens of MB, so the staging writes and the DMA reads stay in the last-level cache and DRAM sees one pass per byte.
+// ---------------------------------------------------------------------------------------------
+constexpr size_t kSlotCap = 2u << 20;   // bytes per slot (allocation); a piece is whole frames, at most this large
+
+struct StageSlot {
+    char* buf = nullptr;
+    cudaEvent_t ev[64] = {};
+    int last_dev = -1;
+};
+std::atomic<bool> g_pool_exiting{false};   // set when the pool is torn down at process exit: CUDA may be gone by then
+
+struct StageSlots {            // thread-local; freed when a (per-call device) thread ends, left to the OS at process exit
+    StageSlot slot[2];
+    int next = 0, dev = -1;
+    ~StageSlots()
+    {
+        if (g_pool_exiting.load()) return;
+        for (StageSlot& s : slot) {
+            if (s.last_dev >= 0) cudaEventSynchronize(s.ev[s.last_dev]);
+            for (cudaEvent_t e : s.ev)
+                if (e) cudaEventDestroy(e);
+            if (s.buf) cudaFreeHost(s.buf);
+        }
+        cudaGetLastError();
+    }
+};
+thread_local StageSlots tl_stage;
+
+struct StageGroup {            // the streamed staging of one chunk
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    std::atomic<int> err{0};   // first cudaError_t seen by any piece
+};
+
+size_t stage_piece_bytes(int pool_threads)
+{
+    if (g_stage_piece_kb > 0) return std::min<size_t>((size_t)g_stage_piece_kb << 10, kSlotCap);
+    // automatic: ~32 MB of slots per HOST (half of a 60 MB L3), shared by the ranks torchrun started on it; every piece
+    // costs three CUDA calls on a stream the pool threads contend for (~15 us together), so pieces stay >= 384 KB.
+    // Measured (profiles/r02_host_staging.jsonl): 16 threads, one rank: 1 MB pieces 38-42 GB/s, 768 KB 33-37, 256 KB
+    // 14-19, whole chunks 28-38; eight ranks x 4 threads: 512 KB 8.9-9.4e6 rmsd/s, 1 MB 7.7-8.4e6, 2 MB (128 MB of
+    // slots) 5.5-6.4e6, whole chunks 4.9-5.1e6, page-locked input 15.6e6
+    size_t budget = 32u << 20;
+    if (const char* lw = getenv("LOCAL_WORLD_SIZE")) {
+        const int n = atoi(lw);
+        if (n > 1) budget /= (size_t)n;
+    }
+    const size_t piece = budget / (2 * (size_t)(pool_threads + 1));
+    return std::min<size_t>(1u << 20, std::max<size_t>(384u << 10, piece));
+}
+
 // ---------------------------------------------------------------------------------------------
 // memcpy pool: row-wise copies between the caller's (F, n_atoms, 3) array and the padded staging layout
 // ---------------------------------------------------------------------------------------------
 struct CopyTask {
-    char* dst;
+    char* dst;                 // plain copy: destination; streamed staging: DEVICE address of the piece
     const char* src;
     size_t dst_pitch, src_pitch, width, pad;  // per row: copy `width` bytes, then zero `pad` bytes
     int64_t rows;
     std::atomic<int>* pending;
+    StageGroup* stage;         // non-null: rows go through one of this thread's slots and on to the device
 };
 
 class CopyPool {
@@ -78,7 +142,7 @@ public:
             for (int p = 0; p < parts; ++p) {
                 const int64_t r0 = (int64_t)p * per, r1 = std::min(rows, r0 + per);
                 CopyTask t{dst + (size_t)r0 * dst_pitch, src + (size_t)r0 * src_pitch, dst_pitch, src_pitch, width, pad,
-                           std::max<int64_t>(0, r1 - r0), &pending};
+                           std::max<int64_t>(0, r1 - r0), &pending, nullptr};
                 if (p == 0) mine = t; else q_.push_back(t);
             }
         }
@@ -89,6 +153,34 @@ public:
             CopyTask t;
             if (try_pop(t)) run(t); else std::this_thread::yield();
         }
+    }
+    // Streamed staging of `rows` rows into the device chunk at `dev_dst` (row pitch dst_pitch there and in the slots), in
+    // pieces of `piece_rows` rows; blocking until every piece has been ISSUED on grp.stream (stream order then carries
+    // the dependency to whatever the caller enqueues next).  Returns the first CUDA error of any piece.
+    cudaError_t stage_rows(StageGroup& grp, char* dev_dst, size_t dst_pitch, const char* src, size_t src_pitch, size_t width,
+                           size_t pad, int64_t rows, int64_t piece_rows)
+    {
+        if (rows <= 0) return cudaSuccess;
+        ensure_started();
+        const int64_t parts = (rows + piece_rows - 1) / piece_rows;
+        std::atomic<int> pending((int)parts);
+        CopyTask mine{};
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (int64_t p = 0; p < parts; ++p) {
+                const int64_t r0 = p * piece_rows, r1 = std::min(rows, r0 + piece_rows);
+                CopyTask t{dev_dst + (size_t)r0 * dst_pitch, src + (size_t)r0 * src_pitch, dst_pitch, src_pitch, width, pad,
+                           r1 - r0, &pending, &grp};
+                if (p == 0) mine = t; else q_.push_back(t);
+            }
+        }
+        cv_.notify_all();
+        run(mine);
+        while (pending.load(std::memory_order_acquire) > 0) {
+            CopyTask t;
+            if (try_pop(t)) run(t); else std::this_thread::yield();
+        }
+        return (cudaError_t)grp.err.load();
     }
     int threads()
     {
@@ -104,8 +196,43 @@ private:
     bool stop_ = false, started_ = false;
     int n_threads_ = 0;
 
+    static void run_staged(const CopyTask& t)
+    {
+        StageGroup& g = *t.stage;
+        StageSlots& tl = tl_stage;
+        auto check = [&](cudaError_t e) {
+            int zero = 0;
+            if (e != cudaSuccess) g.err.compare_exchange_strong(zero, (int)e);
+            return e == cudaSuccess;
+        };
+        if (g.err.load() != 0) return;
+        if (tl.dev != g.dev) {
+            if (!check(cudaSetDevice(g.dev))) return;
+            tl.dev = g.dev;
+        }
+        StageSlot& sl = tl.slot[tl.next];
+        tl.next ^= 1;
+        if (!sl.buf && !check(cudaHostAlloc((void**)&sl.buf, kSlotCap, cudaHostAllocPortable))) return;
+        if (sl.last_dev >= 0 && !check(cudaEventSynchronize(sl.ev[sl.last_dev]))) return;  // the copy that last read it
+        if (t.pad == 0 && t.src_pitch == t.width) {
+            memcpy(sl.buf, t.src, (size_t)t.rows * t.width);
+        } else {
+            for (int64_t r = 0; r < t.rows; ++r) {
+                memcpy(sl.buf + (size_t)r * t.dst_pitch, t.src + (size_t)r * t.src_pitch, t.width);
+                if (t.pad) memset(sl.buf + (size_t)r * t.dst_pitch + t.width, 0, t.pad);
+            }
+        }
+        if (!check(cudaMemcpyAsync(t.dst, sl.buf, (size_t)t.rows * t.dst_pitch, cudaMemcpyHostToDevice, g.stream))) return;
+        if (!sl.ev[g.dev] && !check(cudaEventCreateWithFlags(&sl.ev[g.dev], cudaEventDisableTiming))) return;
+        if (check(cudaEventRecord(sl.ev[g.dev], g.stream))) sl.last_dev = g.dev;
+    }
     static void run(const CopyTask& t)
     {
+        if (t.stage) {
+            run_staged(t);
+            t.pending->fetch_sub(1, std::memory_order_release);
+            return;
+        }
         if (t.pad == 0 && t.dst_pitch == t.width && t.src_pitch == t.width) {
             memcpy(t.dst, t.src, (size_t)t.rows * t.width);
         } else {
@@ -153,6 +280,7 @@ private:
     CopyPool() = default;
     ~CopyPool()
     {
+        g_pool_exiting.store(true);
         {
             std::lock_guard<std::mutex> lk(mu_);
             stop_ = true;
@@ -309,6 +437,7 @@ struct HostJob {
     float* out_traces = nullptr;
     int64_t fpc = 0, n_chunks = 0;
     bool src_locked = false;     // caller's coordinates are page-locked: DMA them directly
+    int64_t stage_piece_rows = 0;  // > 0: pageable coordinates go up by streamed staging, this many frames per piece
     std::atomic<int64_t> next_chunk{0};
     std::atomic<int> rc{0};
     std::atomic<unsigned> degenerate{0};
@@ -346,6 +475,8 @@ int sm_count_of(int dev, int* sm)
     return 0;
 }
 
+inline int job_device(const Workspace& w) { return (int)(&w - g_ws); }
+
 // results of the chunk in lane L -> the caller's buffers (runs after L.done)
 void finalize_lane(HostJob& job, Lane& L)
 {
@@ -375,6 +506,12 @@ int issue_chunk(HostJob& job, Workspace& w, Lane& L, int64_t c, int sm)
             CUW(cudaMemcpy2DAsync(L.xyz, (size_t)n_pad * 12, src, (size_t)n_atoms * 12, (size_t)n_atoms * 12, (size_t)nf,
                                   cudaMemcpyHostToDevice, st));
         }
+    } else if (job.stage_piece_rows > 0) {  // streamed staging through the pool threads' cache-resident slots
+        StageGroup grp;
+        grp.dev = job_device(w);
+        grp.stream = st;
+        CUW(CopyPool::get().stage_rows(grp, (char*)L.xyz, (size_t)n_pad * 12, (const char*)src, (size_t)n_atoms * 12,
+                                       (size_t)n_atoms * 12, (size_t)(n_pad - n_atoms) * 12, nf, job.stage_piece_rows));
     } else {
         CopyPool::get().copy_rows(L.up, (size_t)n_pad * 12, (const char*)src, (size_t)n_atoms * 12, (size_t)n_atoms * 12,
                                   (size_t)(n_pad - n_atoms) * 12, nf);
@@ -435,7 +572,8 @@ void run_device(HostJob& job, int dev)
         rc = ws_prepare(w, (size_t)job.fpc * job.n_pad * 12, (size_t)job.fpc,
                         job.op == HOP_CENTER ? 256 : b200rmsd_scratch_bytes(job.fpc, job.n_atoms),
                         job.op == HOP_CENTER ? 4 : (size_t)std::max(job.n_atoms_ref, n_use), job.idx ? (size_t)job.n_sel : 0,
-                        !job.src_locked, writes_back && !(job.src_locked && job.n_pad == job.n_atoms));
+                        !job.src_locked && job.stage_piece_rows == 0,
+                        writes_back && !(job.src_locked && job.n_pad == job.n_atoms));
     auto cu = [&](cudaError_t e) {
         if (e != cudaSuccess && !rc) rc = fail(B200RMSD_ECUDA, "host pipeline (device %d): %s", dev, cudaGetErrorString(e));
     };
@@ -558,9 +696,17 @@ int run_job(HostJob& job, const int* devices, int n_devices, const char* what)
     job.n_pad = (job.n_atoms + 3) / 4 * 4;
     const size_t frame_bytes = (size_t)job.n_pad * 12;
     job.src_locked = is_page_locked(job.in);
-    job.fpc = (int64_t)std::max<size_t>(1, ((size_t)(job.src_locked ? g_chunk_mb : g_staged_chunk_mb) << 20) / frame_bytes);
+    const bool streamed = !job.src_locked && g_stage_piece_kb >= 0 && frame_bytes <= kSlotCap;
+    // streamed staging keeps the cache footprint in its slots, so its chunks can be as large as the page-locked ones
+    // (64 MB chunks measured 5-10 % faster than 16 MB); whole-chunk staging wants three lanes of chunks inside the L3
+    const int chunk_mb = job.src_locked ? g_chunk_mb : streamed ? std::max(g_chunk_mb, g_staged_chunk_mb) : g_staged_chunk_mb;
+    job.fpc = (int64_t)std::max<size_t>(1, ((size_t)chunk_mb << 20) / frame_bytes);
     job.fpc = std::min<int64_t>(job.fpc, job.n_frames);
     job.n_chunks = (job.n_frames + job.fpc - 1) / job.fpc;
+    if (streamed) {
+        const size_t piece = stage_piece_bytes(CopyPool::get().threads());
+        job.stage_piece_rows = (int64_t)std::max<size_t>(1, piece / frame_bytes);
+    }
     const int n_use = (int)std::min<int64_t>(n_devices, job.n_chunks);
     std::vector<std::thread> th;
     for (int i = 1; i < n_use; ++i) th.emplace_back(run_device, std::ref(job), devices[i]);
@@ -579,6 +725,12 @@ int b200rmsd_host_configure(int copy_threads, int chunk_mb, int staged_chunk_mb)
     if (copy_threads > 0) g_copy_threads = std::min(copy_threads, 64);  // takes effect before the pool's first use
     if (chunk_mb > 0) g_chunk_mb = std::min(chunk_mb, 1024);
     if (staged_chunk_mb > 0) g_staged_chunk_mb = std::min(staged_chunk_mb, 1024);
+    return 0;
+}
+
+int b200rmsd_host_configure_staging(int piece_kb)
+{
+    g_stage_piece_kb = piece_kb < 0 ? -1 : std::min(piece_kb, (int)(kSlotCap >> 10));
     return 0;
 }
 

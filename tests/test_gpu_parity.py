@@ -974,6 +974,20 @@ def test_host_pipeline_pageable_pinned_and_chunking_agree(mdb, oracle_mod, small
     one = mdb.rmsd(mdb.Trajectory(X.copy()), ref, 1)
     mdb.set_host_pipeline(chunk_mb=1, staged_chunk_mb=1)
     assert np.array_equal(got["pageable"][0], got["pinned"][0]) and np.array_equal(got["pageable"][0], one)
+    # pageable memory goes up by streamed staging (pieces through the pool threads' slots) by default: whole-chunk
+    # staging and other piece sizes move the same bytes
+    try:
+        for kb in (-1, 16, 2048):
+            mdb.set_host_pipeline(stage_piece_kb=kb)
+            t = mdb.Trajectory(X.copy())
+            assert np.array_equal(mdb.rmsd(t, ref, 1), one), f"stage_piece_kb={kb}"
+            t.superpose(ref, 0, atom_indices=idx)
+            if kb == -1:
+                whole = t.xyz.copy()
+            else:
+                assert np.array_equal(t.xyz, whole), f"stage_piece_kb={kb}"
+    finally:
+        mdb.set_host_pipeline(stage_piece_kb=0)
     assert np.array_equal(got["pageable"][1], got["pinned"][1])
     want = O.rmsd(X, X[:3], 1, impl="reference" if O.ref_available() else "port")
     m = np.arange(F) != 1   # the reference frame against itself: noise floor here, exactly 0 in the reference (same memory)
