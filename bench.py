@@ -379,8 +379,10 @@ def run_ovm(c, name, steps, warmup, full):
                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo}}
     if full:
         e2e_steps = 3
-        for memory, pinned in (("pageable", False), ("pinned", True)):
-            if pinned and (c.world > 1 or name != "ovm"):
+        staging = ("streamed through cache-resident page-locked slots: %d ranks share the host" % c.world) if c.world > 1 \
+            else "whole 16 MB chunks through three page-locked lanes"
+        for memory, pinned in (("pageable (%s)" % staging, False), ("pinned", True)):
+            if pinned and name != "ovm":
                 continue
             host = host_copies(c, dt.xyz_dev, N, pinned)
             ht = host_traj(mdb, host.numpy())
@@ -395,6 +397,15 @@ def run_ovm(c, name, steps, warmup, full):
         rec["cpu_baseline"] = _try(lambda: cpu_reference_run(name, 3, 1))
         rec["parity"] = _try(lambda: parity_block(name, mdb))
     return rec
+
+
+def superpose_kernel_name(c, n_atoms, n_sel):
+    """Which single-pass kernel b200rmsd_superpose_dev launches for this frame size (host-side geometry hook)."""
+    import ctypes
+    geo = (ctypes.c_int * 8)()
+    kind = ctypes.CDLL(c.capi.LIB_PATH).b200rmsd_debug_fused_geometry(0, n_atoms, n_sel, 1, 1, geo)
+    return {1: "frame_resident_kernel<OP_SUPERPOSE>", 2: "superpose_pipe_kernel (stage-pipelined, frames >= 30 KB)"}.get(
+        kind, "two-pass: ovm kernel + apply_transform_kernel")
 
 
 def run_superpose(c, steps, warmup, full):
@@ -425,7 +436,7 @@ def run_superpose(c, steps, warmup, full):
            "config": {"workload": desc, "frames_per_gpu": F, "n_atoms": N, "n_aligned": len(idx_np), "frame": 0,
                       "l2_policy": "inputs (%.1f GB per GPU) are larger than the 126 MB L2" % (F * N * 12 / 1e9)},
            "clocks": clocks, "gpu_launches": 2 * steps,
-           "roofline": {"bound": "hbm", "kernel": "frame_resident_kernel<OP_SUPERPOSE>", "achieved": algo / (kern_ms * 1e-3) / 1e9,
+           "roofline": {"bound": "hbm", "kernel": superpose_kernel_name(c, N, len(idx_host)), "achieved": algo / (kern_ms * 1e-3) / 1e9,
                         "peak": peak, "unit": "GB/s", "frac": algo / (kern_ms * 1e-3) / 1e9 / peak,
                         "traffic": ncu_fact("superpose"), "peak_source": peak_src, "kernel_ms": kern_ms,
                         "algorithmic_bytes_per_launch": algo}}

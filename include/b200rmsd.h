@@ -330,13 +330,16 @@ int b200rmsd_center_host_multi(float* xyz, int64_t n_frames, int n_atoms, float*
  *                    a 60 MB host L3); streamed staging (below) uses max(chunk_mb, staged_chunk_mb). */
 int b200rmsd_host_configure(int copy_threads, int chunk_mb, int staged_chunk_mb);
 
-/* How pageable coordinates reach the device.  piece_kb >= 0 (default 0): STREAMED staging -- every thread of the memcpy
- * pool copies a piece of the chunk (whole frames, piece_kb KB; 0 = chosen so that all slots of all threads of all ranks on
- * the host together stay near 24 MB) into one of its two page-locked slots and sends it to its place in the device chunk
- * at once, so staging writes and DMA reads stay in the host's last-level cache and DRAM sees one pass per byte instead of
- * three (eight ranks on one 32-thread host: 5.1e6 -> 9.4e6 rmsd/s at 1,000 atoms; profiles/r02_host_staging.jsonl).
- * piece_kb < 0: the whole chunk is staged into one buffer and sent with one copy (round-1 behaviour).  Frames
- * larger than 2 MB always take the latter. */
+/* How pageable coordinates reach the device in b200rmsd_rmsd_host*.  Whole-chunk staging: the memcpy pool fills a lane's
+ * page-locked buffer, one copy sends it (three passes over host memory per byte; three 16 MB lanes stay inside the L3 of
+ * ONE process).  Streamed staging: every pool thread copies a piece of the chunk (whole frames) into one of its two small
+ * page-locked slots and sends it to its place in the device chunk at once, so that the staging writes and DMA reads of ALL
+ * ranks on the host stay in its last-level cache (eight ranks on one 32-thread host: 5.1e6 -> 9.4e6 rmsd/s at 1,000 atoms,
+ * four ranks 5.4e6 -> 7.6e6, two 5.9e6 -> 6.7e6; one rank is not faster; profiles/r02_host_staging.jsonl).
+ *   piece_kb == 0 (default): streamed when $LOCAL_WORLD_SIZE (set by torchrun) says several ranks share the host, with
+ *                 pieces of 512 KB - 1 MB; whole chunks otherwise;
+ *   piece_kb > 0: streamed, piece_kb KB per piece (at most 2048);   piece_kb < 0: whole chunks always.
+ * In-place operations (superpose, centring) and frames larger than 2 MB always stage whole chunks. */
 int b200rmsd_host_configure_staging(int piece_kb);
 
 /* Release the internal per-device workspaces of the host API. */

@@ -530,8 +530,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) superpose_pipe_kernel(const Fus
     extern __shared__ __align__(128) unsigned char smem[];
     const int n_sel_pad = (p.n_sel + 3) & ~3;
     const int S = p.batch, T = kFrWarps - S, D = p.depth, W = p.team_warps, fpb = p.fpb, nbuf = p.nbuf;
-    const PipeLayout L = pipe_layout(p.n_pad, nbuf, n_sel_pad, p.idx ? p.n_sel : 0, fpb, W);
-    const float* ref_s = reinterpret_cast<const float*>(smem + L.ref_off);
+    const PipeLayout L = pipe_layout(p.n_pad, nbuf, p.ref_global ? 0 : n_sel_pad, p.idx ? p.n_sel : 0, fpb, W);
+    const float* ref_s = p.ref_global ? p.ref : reinterpret_cast<const float*>(smem + L.ref_off);
     int* idx_s = reinterpret_cast<int*>(smem + L.idx_off);
     float* rec_all = reinterpret_cast<float*>(smem + L.rec_off);
     double* dsum_s = reinterpret_cast<double*>(smem + L.dsum_off);
@@ -565,9 +565,13 @@ __global__ void __launch_bounds__(kFrThreads, 1) superpose_pipe_kernel(const Fus
     // ================================================================== loader
     if (warp == kFrWarps) {
         if (elect_one_sync()) {
-            const uint32_t bytes = (uint32_t)n_sel_pad * 12u;
-            mbar_arrive_expect_tx(ref_bar, bytes);
-            bulk_g2s(smem + L.ref_off, p.ref, bytes, ref_bar);
+            if (p.ref_global) {
+                mbar_arrive(ref_bar);
+            } else {
+                const uint32_t bytes = (uint32_t)n_sel_pad * 12u;
+                mbar_arrive_expect_tx(ref_bar, bytes);
+                bulk_g2s(smem + L.ref_off, p.ref, bytes, ref_bar);
+            }
         }
         for (int s = 0; s < n_slots; ++s) {
             const int buf = s % nbuf;
@@ -752,10 +756,10 @@ __global__ void __launch_bounds__(kFrThreads, 1) superpose_pipe_kernel(const Fus
     }
 }
 
-static bool pipe_fits(const FusedParams& p, int nbuf, int fpb, int W)
+static bool pipe_fits(const FusedParams& p, int nbuf, int fpb, int W, bool ref_global = false)
 {
     const int n_sel_pad = (p.n_sel + 3) & ~3;
-    return pipe_layout(p.n_pad, nbuf, n_sel_pad, p.idx ? p.n_sel : 0, fpb, W).total <= 232448;
+    return pipe_layout(p.n_pad, nbuf, ref_global ? 0 : n_sel_pad, p.idx ? p.n_sel : 0, fpb, W).total <= 232448;
 }
 
 // Geometry of the stage-pipelined superpose: slots of ~20 KB (at most 32 frames), as many buffers as fit (<= 12),
@@ -781,6 +785,15 @@ static bool pipe_config(FusedParams& p)
         }
         int nbuf = 12;
         while (nbuf >= 2 && !pipe_fits(p, nbuf, fpb, W)) --nbuf;
+        p.ref_global = 0;
+        if (nbuf < 3 && fpb == 1) {
+            // one frame per slot and fewer than three buffers next to a resident reference (all atoms selected on
+            // ~5,000-atom frames): leave the reference in global memory -- every CTA reads the same <= 100 KB, so it stays
+            // in L2 -- and keep load / compute / store of three frames overlapped instead of two passes over HBM
+            int nb = 12;
+            while (nb >= 3 && !pipe_fits(p, nb, fpb, W, true)) --nb;
+            if (nb >= 3) { nbuf = nb; p.ref_global = 1; }
+        }
         if (nbuf < 2) {
             if (fpb > 1) continue;
             return false;
@@ -1013,9 +1026,9 @@ extern "C" int b200rmsd_debug_fused_geometry(int op, int n_atoms, int n_sel, int
     if (!fused_config(p, op)) return 0;
     const int n_sel_pad = (p.n_sel + 3) & ~3;
     if (p.pipe) {  // returns 2: {solver warps, nbuf, fpb, streaming warps per frame, lanes per frame, bytes}; depth in out[6]
-        const PipeLayout PL = pipe_layout(p.n_pad, p.nbuf, n_sel_pad, p.idx ? p.n_sel : 0, p.fpb, p.team_warps);
+        const PipeLayout PL = pipe_layout(p.n_pad, p.nbuf, p.ref_global ? 0 : n_sel_pad, p.idx ? p.n_sel : 0, p.fpb, p.team_warps);
         out[0] = p.batch; out[1] = p.nbuf; out[2] = p.fpb; out[3] = p.team_warps; out[4] = p.lanes; out[5] = (int)PL.total;
-        out[6] = p.depth;
+        out[6] = p.depth; out[7] = p.ref_global;
         return 2;
     }
     const FrLayout L = fr_layout(p.n_pad, p.nbuf, op == OP_SUPERPOSE ? n_sel_pad : 0, p.idx ? p.n_sel : 0, p.batch, p.fpb,
@@ -1038,7 +1051,7 @@ cudaError_t launch_frame_resident(const FusedParams& p, int op, int sm_count, cu
     if (p.n_frames <= 0) return cudaSuccess;
     if (op == OP_SUPERPOSE && p.pipe) {
         const int n_sel_pad = (p.n_sel + 3) & ~3;
-        const PipeLayout L = pipe_layout(p.n_pad, p.nbuf, n_sel_pad, p.idx ? p.n_sel : 0, p.fpb, p.team_warps);
+        const PipeLayout L = pipe_layout(p.n_pad, p.nbuf, p.ref_global ? 0 : n_sel_pad, p.idx ? p.n_sel : 0, p.fpb, p.team_warps);
         cudaError_t e = cudaFuncSetAttribute(superpose_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
         if (e != cudaSuccess) return e;
         int64_t ctas = sm_count;

@@ -45,8 +45,8 @@ int g_staged_chunk_mb = 16;    // pageable caller memory: three lanes of staging
                                // so that the DMA engine reads what the memcpy pool has just written from cache
                                // (measured on a 16-core Xeon, 60 MB L3: 16 MB 52 GB/s, 64 MB 46 GB/s, page-locked 55 GB/s)
 
-int g_stage_piece_kb = 0;       // streamed staging (below): 0 = automatic piece size, > 0 = KB per piece, < 0 = off (the whole
-                               // chunk is staged into the lane's buffer and sent with one copy)
+int g_stage_piece_kb = 0;       // streamed staging (below): 0 = automatic (stage_piece_bytes), > 0 = KB per piece, < 0 = off (the
+                               // whole chunk is staged into the lane's buffer and sent with one copy)
 
 // ---------------------------------------------------------------------------------------------
 // Streamed staging of pageable memory.  Staging a whole 16 MB chunk and then sending it costs the host's memory system
@@ -90,21 +90,30 @@ struct StageGroup {            // the streamed staging of one chunk
     std::atomic<int> err{0};   // first cudaError_t seen by any piece
 };
 
+int local_ranks()   // processes torchrun started on this host (they share its memory system); 1 when not under torchrun
+{
+    const char* lw = getenv("LOCAL_WORLD_SIZE");
+    const int n = lw ? atoi(lw) : 1;
+    return n > 1 ? n : 1;
+}
+
+// Piece size of the streamed staging; 0 = stage whole chunks.  Measured, md.rmsd on 1,000-atom frames
+// (profiles/r02_host_staging.jsonl; rmsd/s aggregate, whole chunks -> streamed):
+//   8 ranks x 4 threads   5.1e6 -> 9.4e6 (512 KB pieces; 1 MB 8.4e6; 2 MB = 128 MB of slots 6.4e6; page-locked input 15.6e6)
+//   4 ranks x 8 threads   5.4e6 -> 7.6e6 (1 MB; 512 KB 7.4e6)
+//   2 ranks x 16 threads  5.9e6 -> 6.7e6 (1 MB; 512 KB 3.8e6: every piece costs three CUDA calls on a stream all the
+//                         threads of a process contend for, ~24 us together, i.e. ~42k pieces/s per process)
+//   1 rank x 16 threads   52 GB/s -> 42 GB/s on one box, 38 -> 42 on another: three 16 MB lanes already fit the 60 MB L3
+// so: streamed when several ranks share the host, ~32 MB of slots per host, pieces of 512 KB (few threads per rank) to 1 MB.
 size_t stage_piece_bytes(int pool_threads)
 {
+    if (g_stage_piece_kb < 0) return 0;
     if (g_stage_piece_kb > 0) return std::min<size_t>((size_t)g_stage_piece_kb << 10, kSlotCap);
-    // automatic: ~32 MB of slots per HOST (half of a 60 MB L3), shared by the ranks torchrun started on it; every piece
-    // costs three CUDA calls on a stream the pool threads contend for (~15 us together), so pieces stay >= 384 KB.
-    // Measured (profiles/r02_host_staging.jsonl): 16 threads, one rank: 1 MB pieces 38-42 GB/s, 768 KB 33-37, 256 KB
-    // 14-19, whole chunks 28-38; eight ranks x 4 threads: 512 KB 8.9-9.4e6 rmsd/s, 1 MB 7.7-8.4e6, 2 MB (128 MB of
-    // slots) 5.5-6.4e6, whole chunks 4.9-5.1e6, page-locked input 15.6e6
-    size_t budget = 32u << 20;
-    if (const char* lw = getenv("LOCAL_WORLD_SIZE")) {
-        const int n = atoi(lw);
-        if (n > 1) budget /= (size_t)n;
-    }
-    const size_t piece = budget / (2 * (size_t)(pool_threads + 1));
-    return std::min<size_t>(1u << 20, std::max<size_t>(384u << 10, piece));
+    const int ranks = local_ranks();
+    if (ranks < 2) return 0;
+    const size_t piece = ((size_t)32 << 20) / ((size_t)ranks * 2 * (size_t)(pool_threads + 1));
+    const size_t lo = pool_threads + 1 >= 12 ? (1u << 20) : (512u << 10);
+    return std::min<size_t>(1u << 20, std::max<size_t>(lo, piece));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -484,9 +493,10 @@ void finalize_lane(HostJob& job, Lane& L)
     if (job.out_rmsd) memcpy(job.out_rmsd + f0, L.res, (size_t)nf * 4);
     if (job.out_traces) memcpy(job.out_traces + f0, L.res, (size_t)nf * 4);
     if (job.out_rot) memcpy(job.out_rot + f0 * 9, L.res + job.fpc, (size_t)nf * 36);
-    if (job.inout && !(job.src_locked && job.n_pad == job.n_atoms))
+    if (job.inout && !(job.src_locked && job.n_pad == job.n_atoms)) {
         CopyPool::get().copy_rows((char*)(job.inout + (size_t)f0 * job.n_atoms * 3), (size_t)job.n_atoms * 12, L.down,
                                   (size_t)job.n_pad * 12, (size_t)job.n_atoms * 12, 0, nf);
+    }
 }
 
 // issue one chunk into lane L (stream-ordered; returns after the host-side staging copy)
@@ -696,17 +706,18 @@ int run_job(HostJob& job, const int* devices, int n_devices, const char* what)
     job.n_pad = (job.n_atoms + 3) / 4 * 4;
     const size_t frame_bytes = (size_t)job.n_pad * 12;
     job.src_locked = is_page_locked(job.in);
-    const bool streamed = !job.src_locked && g_stage_piece_kb >= 0 && frame_bytes <= kSlotCap;
+    // in-place operations keep whole-chunk staging both ways: a streamed download (piece by piece through the same slots)
+    // measured slower at every rank count (the thread waits for its own piece's DMA before it can copy it out)
+    const size_t piece = (job.src_locked || job.op != HOP_RMSD || frame_bytes > kSlotCap)
+                             ? 0 : stage_piece_bytes(CopyPool::get().threads());
+    const bool streamed = piece > 0;
     // streamed staging keeps the cache footprint in its slots, so its chunks can be as large as the page-locked ones
     // (64 MB chunks measured 5-10 % faster than 16 MB); whole-chunk staging wants three lanes of chunks inside the L3
     const int chunk_mb = job.src_locked ? g_chunk_mb : streamed ? std::max(g_chunk_mb, g_staged_chunk_mb) : g_staged_chunk_mb;
     job.fpc = (int64_t)std::max<size_t>(1, ((size_t)chunk_mb << 20) / frame_bytes);
     job.fpc = std::min<int64_t>(job.fpc, job.n_frames);
     job.n_chunks = (job.n_frames + job.fpc - 1) / job.fpc;
-    if (streamed) {
-        const size_t piece = stage_piece_bytes(CopyPool::get().threads());
-        job.stage_piece_rows = (int64_t)std::max<size_t>(1, piece / frame_bytes);
-    }
+    if (streamed) job.stage_piece_rows = (int64_t)std::max<size_t>(1, piece / frame_bytes);
     const int n_use = (int)std::min<int64_t>(n_devices, job.n_chunks);
     std::vector<std::thread> th;
     for (int i = 1; i < n_use; ++i) th.emplace_back(run_device, std::ref(job), devices[i]);

@@ -81,6 +81,8 @@ struct FusedParams {
     // slot and its transform
     int pipe;
     int depth;
+    int ref_global;         // pipe: the reference stays in global memory (L2-resident, read through L1) because frame buffers
+                            // plus a resident copy would not fit shared memory (all atoms selected on ~5,000-atom frames)
 };
 bool fused_config(FusedParams& p, int op);
 bool fused_override(FusedParams& p, int op, int G, int nbuf, int fpb, int lanes);

@@ -1136,6 +1136,27 @@ def test_baseline_shapes_vs_oracle_three_way(mdb, oracle_mod, F, N, step, gen):
         assert np.abs(a.xyz - sup_truth).max() < 1e-5
 
 
+@pytest.mark.parametrize("N", [4800, 5000, 6200])
+def test_superpose_all_atoms_large_frames(mdb, oracle_mod, N):
+    """All atoms selected on ~5,000-atom frames: three frame buffers and a resident reference do not fit shared memory
+    together, so superpose_pipe_kernel reads the reference from global memory (round 1 ran two passes over HBM here).
+    Superposed coordinates and rotations against the float64 truth and the reference, through both entry points."""
+    O = oracle_mod
+    F = 600
+    X = O.synth_md(F, N, seed=50 + N // 100)
+    kind = "reference" if O.ref_available() else "port"
+    want_xyz = O.superpose(X, X, 3, None, impl=kind)
+    truth_xyz, truth_R = O.truth_superpose(X, X, 3, None)
+    dt = mdb.DeviceTrajectory.from_host(X)
+    _, R = dt.superpose(dt, 3, return_rotations=True)
+    assert_three_way(dt.xyz, want_xyz, truth_xyz, f"superposed coordinates, all atoms, N={N}")
+    assert np.abs(dt.xyz - truth_xyz).max() < 1e-5
+    assert np.abs(R.cpu().numpy().reshape(F, 3, 3) - truth_R).max() < 1e-5
+    t = mdb.Trajectory(X.copy())
+    t.superpose(mdb.Trajectory(X.copy()), 3)
+    assert np.array_equal(t.xyz, dt.xyz), "host entry point and device entry point run the same kernel"
+
+
 def test_nccl_two_ranks_match_single_gpu():
     """The NCCL paths (mdtraj_b200.distributed: frame-sharded md.rmsd / superpose with all_gather, all-pairs with the
     broadcast + symmetric block exchange) against the single-GPU results, two ranks under torchrun

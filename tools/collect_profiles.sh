@@ -14,7 +14,7 @@ for w in ovm superpose allpairs_20k; do
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_${w}_launches.csv \
       python bench.py --only $w --steps 2 --warmup 3 --no-e2e --no-subs > $O/${R}_${w}_launches.log 2>&1
 done
-for spec in ovm:ovm_tma_kernel superpose:frame_resident_kernel allpairs_20k:allpairs_tc144_kernel; do
+for spec in ovm:ovm_tma_kernel 'superpose:frame_resident_kernel|superpose_pipe_kernel' allpairs_20k:allpairs_tc144_kernel; do
   w=${spec%%:*}; k=${spec#*:}
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o $O/${R}_prof_$w \
       python bench.py --only $w --steps 1 --warmup 3 --no-e2e --no-subs > $O/${R}_prof_$w.log 2>&1
