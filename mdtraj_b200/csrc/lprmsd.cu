@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(256) lprmsd_kernel(const LpParams p)
                         if (cur < mj) { mj = cur; minv[j] = cur; way[j] = j0; }
                         if (mj < best) { best = mj; bj = j; }
                     }
+                    __syncwarp();  // minv / way of column j were written by lane j - 1, the update below reads them on lane j
                     const ArgMin am = warp_argmin(best, bj);
                     const double delta = am.v;
                     for (int j = lane; j <= g; j += 32) {
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(256) lprmsd_kernel(const LpParams p)
                     j0 = am.j;
                     if (pcol[j0] == 0) break;
                 }
+                __syncwarp();     // every lane has read pcol[j0] above
                 if (lane == 0) {  // flip the augmenting path
                     while (j0) {
                         const int j1 = way[j0];
