@@ -69,7 +69,7 @@ std::atomic<bool> g_pool_exiting{false};   // set when the pool is torn down at 
 
 struct StageSlots {            // thread-local; freed when a (per-call device) thread ends, left to the OS at process exit
     StageSlot slot[2];
-    int next = 0, dev = -1;
+    int next = 0;
     ~StageSlots()
     {
         if (g_pool_exiting.load()) return;
@@ -215,10 +215,15 @@ private:
             return e == cudaSuccess;
         };
         if (g.err.load() != 0) return;
-        if (tl.dev != g.dev) {
-            if (!check(cudaSetDevice(g.dev))) return;
-            tl.dev = g.dev;
-        }
+        // The piece may belong to another device than the one this thread last worked for -- also when the thread is a
+        // device's own host thread helping out while it waits (it must find its own device current again afterwards)
+        int home = -1;
+        if (!check(cudaGetDevice(&home))) return;
+        struct Restore {
+            int home, dev;
+            ~Restore() { if (home != dev) cudaSetDevice(home); }
+        } restore{home, g.dev};
+        if (home != g.dev && !check(cudaSetDevice(g.dev))) return;
         StageSlot& sl = tl.slot[tl.next];
         tl.next ^= 1;
         if (!sl.buf && !check(cudaHostAlloc((void**)&sl.buf, kSlotCap, cudaHostAllocPortable))) return;

@@ -88,6 +88,10 @@ def lprmsd(target, reference, frame=0, atom_indices=None, permute_groups=None, p
     dis = np.setdiff1d(np.arange(len(atom_indices)), flat).astype(np.int32)
     g_max = max([len(g) for g in groups_rel], default=0)
 
+    n_frames_t = target.n_frames if t_is_dev else np.asarray(target.xyz).shape[0]
+    if n_frames_t == 0:
+        empty = np.zeros(0, dtype=np.float32)
+        return (empty, np.zeros((0, len(atom_indices)), dtype=np.int32)) if return_mapping else empty
     torch = _torch()
     dev = target.device if t_is_dev else torch.device("cuda", current_device())
     dt = target if t_is_dev else DeviceTrajectory.from_trajectory(target, dev)

@@ -821,6 +821,34 @@ def test_lprmsd_reference_test_semantics(mdb):
     assert np.abs(got - want).max() < 1e-5
 
 
+def test_lprmsd_edge_cases(mdb, oracle_mod):
+    """Unsorted / repeated atom_indices and group members (the reference runs np.unique over both), one-atom groups,
+    a selection that is one atom, zero frames, a DeviceTrajectory as the reference, frame != 0."""
+    O = oracle_mod
+    rng = np.random.default_rng(11)
+    N = 37
+    ref = rng.standard_normal((4, N, 3)).astype(np.float32)
+    X = (ref[2][None] + 0.05 * rng.standard_normal((9, N, 3))).astype(np.float32)
+    idx = [30, 2, 2, 5, 7, 9, 11, 12, 30, 20, 21, 22, 3]
+    groups = [[9, 5, 5, 7], [22], [20, 21]]
+    X[:, [5, 7, 9]] = X[:, [9, 5, 7]]
+    X[:, [20, 21]] = X[:, [21, 20]]
+    got, gmap = mdb.lprmsd(mdb.Trajectory(X.copy()), mdb.Trajectory(ref.copy()), 2, atom_indices=idx, permute_groups=groups,
+                           return_mapping=True)
+    want, wmap = O.lprmsd(X, ref, 2, idx, groups, impl="reference" if O.ref_available() else "port", return_mapping=True)
+    assert np.array_equal(gmap, wmap)
+    sel = np.unique(idx)
+    assert_three_way(got, want, O.truth_lprmsd_given_mapping(X, ref[2], sel, wmap), "lprmsd edge cases")
+    assert got.max() < 0.15, "the relabelling must have been undone (noise 0.05 nm per coordinate: ~0.09 nm)"
+    # the reference held on the device; one selected atom (RMSD of a point onto a point is 0); zero frames
+    again = mdb.lprmsd(mdb.Trajectory(X.copy()), mdb.DeviceTrajectory.from_host(ref), 2, atom_indices=idx, permute_groups=groups)
+    assert np.array_equal(again, got)
+    one = mdb.lprmsd(mdb.Trajectory(X.copy()), mdb.Trajectory(ref.copy()), 1, atom_indices=[4])
+    assert one.shape == (9,) and np.all(one < 1e-6)
+    empty = mdb.lprmsd(mdb.Trajectory(X[:0].copy()), mdb.Trajectory(ref.copy()), 0)
+    assert empty.shape == (0,) and empty.dtype == np.float32
+
+
 def test_lprmsd_water_box_vs_oracle(mdb, oracle_mod):
     """2000 frames of 60 distinguishable atoms + two groups of 120 exchangeable ones, every frame relabelled at random and
     moved rigidly: the matching undoes the relabelling, distances agree with the oracle three ways on a sample of
@@ -1025,9 +1053,15 @@ def test_host_pipeline_several_devices(mdb, oracle_mod, small_chunks):
         mdb.set_devices(list(range(torch.cuda.device_count())))
         many = mdb.rmsd(mdb.Trajectory(X.copy()), ref, 0)
         s2 = mdb.Trajectory(X.copy()); s2.superpose(ref, 0)
+        # streamed staging with several devices: pool threads (and the devices' own host threads, which help) send pieces
+        # for whichever device a piece belongs to
+        mdb.set_host_pipeline(stage_piece_kb=64)
+        streamed = [mdb.rmsd(mdb.Trajectory(X.copy()), ref, 0) for _ in range(3)]
     finally:
+        mdb.set_host_pipeline(stage_piece_kb=0)
         mdb.set_devices(None)
     assert np.array_equal(one, many) and np.array_equal(s1.xyz, s2.xyz)
+    assert all(np.array_equal(one, s) for s in streamed)
 
 
 def test_host_pipeline_error_paths(mdb):
