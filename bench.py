@@ -436,7 +436,7 @@ def run_superpose(c, steps, warmup, full):
            "config": {"workload": desc, "frames_per_gpu": F, "n_atoms": N, "n_aligned": len(idx_np), "frame": 0,
                       "l2_policy": "inputs (%.1f GB per GPU) are larger than the 126 MB L2" % (F * N * 12 / 1e9)},
            "clocks": clocks, "gpu_launches": 2 * steps,
-           "roofline": {"bound": "hbm", "kernel": superpose_kernel_name(c, N, len(idx_host)), "achieved": algo / (kern_ms * 1e-3) / 1e9,
+           "roofline": {"bound": "hbm", "kernel": superpose_kernel_name(c, N, len(idx_np)), "achieved": algo / (kern_ms * 1e-3) / 1e9,
                         "peak": peak, "unit": "GB/s", "frac": algo / (kern_ms * 1e-3) / 1e9 / peak,
                         "traffic": ncu_fact("superpose"), "peak_source": peak_src, "kernel_ms": kern_ms,
                         "algorithmic_bytes_per_launch": algo}}
