@@ -1232,3 +1232,24 @@ def test_allpairs_cta_pair_geometry_is_bit_identical(mdb, oracle_mod):
             AP.configure(cta_pair=True)
         assert torch.equal(got[False][0], got[True][0]) and torch.equal(got[False][1], got[True][1])
         assert torch.isfinite(got[True][0]).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bench.py: every record builds (a typo in a record's dict once cost the driver's run its C3 numbers)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("only", ["ovm", "superpose", "allpairs_20k", "ovm25k"])
+def test_bench_records_build(only):
+    import json
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--only", only, "--steps", "1", "--warmup", "3",
+                          "--no-e2e", "--no-subs"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    rec = json.loads(res.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches", "roofline"):
+        assert key in rec, key
+    assert rec["value"] > 0 and rec["roofline"]["frac"] > 0.3 and "workload" in rec["config"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in rec["roofline"], key
