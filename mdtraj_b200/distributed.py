@@ -272,6 +272,8 @@ class PeerExchange:
                 _capi.lib().b200rmsd_peer_close(p)
         self.opened = {}
         self.block = None
+        if collective and self.ok:
+            _dist().barrier(self.group)   # every rank has unmapped this rank's block before it is freed
         if self._buf is not None:
             self._buf.free()
             self._buf = None

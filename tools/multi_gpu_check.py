@@ -88,6 +88,15 @@ def main():
             if rank == 0:
                 print(f'{{"what": "rmsd_matrix_sharded", "frames": {Fb}, "atoms": {N}, "gpus": {world}, "exchange": "{exchange}", "ms": {ms.item():.3f}}}', flush=True)
         del big
+    # more matrix sizes than the exchange cache holds: the oldest exchange is closed (a collective) and a new one built
+    for Fx in (1100, 1237, 1400, 1100):
+        Xx = X[:Fx]
+        dx = mdb.DeviceTrajectory.from_host(Xx, dev) if rank == 0 else \
+            mdb.DeviceTrajectory(torch.zeros((Fx, N, 3), dtype=torch.float32, device=dev), N)
+        a0, a1, bx = D.rmsd_matrix_sharded(dx, symmetric=True, exchange="peer")
+        want = mdb.rmsd_matrix_device(mdb.DeviceTrajectory.from_host(Xx, dev), row_block=(a0, a1))
+        assert (bx - want).abs().max().item() < 1e-5, f"peer exchange after cache turnover, F = {Fx}"
+    assert len(D._EXCHANGES) <= 2
     assert (r0, r1) == D.shard_bounds(F, rank, world)
     truth_row = single if r0 <= 5 < r1 else None
     if truth_row is not None:
