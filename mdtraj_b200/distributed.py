@@ -406,3 +406,52 @@ def rmsd_matrix_sharded(traj_dev, atom_indices=None, group=None, broadcast=True,
     for (a0, a1, c0, c1, buf) in recvs:
         out[a0 - r0: a1 - r0, c0:c1] = buf
     return r0, r1, out
+
+
+def similarity_scores_sharded(traj_dev, atom_indices=None, beta=1.0, group=None, broadcast=True, precise=True):
+    """``np.exp(-beta * D / D.std()).sum(axis=1)`` (``examples/centroids.ipynb:117``) for the all-pairs matrix of a
+    trajectory whose matrix is sharded over the ranks of ``group`` (``rmsd_matrix_sharded``): every rank reduces its own
+    row block on the device (``b200rmsd_matrix_moments_dev``, ``b200rmsd_exp_rowsum_dev``), the two moments are
+    all-reduced (16 bytes), the F scores all-gathered -- the matrix (40 GB at 100k frames) never leaves the GPUs.
+    Returns ``(scores float64 ndarray (F,), std)`` on every rank."""
+    import math
+    import torch
+    from . import _capi
+    from .device import _stream_ptr
+    dist = _dist()
+    world = dist.get_world_size(group)
+    F = traj_dev.n_frames
+    dev = traj_dev.device
+    r0, r1, blk = rmsd_matrix_sharded(traj_dev, atom_indices, group, broadcast=broadcast, precise=precise)
+    L = _capi.lib()
+    moments = torch.zeros(2, dtype=torch.float64, device=dev)
+    local = torch.zeros(max(r1 - r0, 1), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        stream = _stream_ptr(torch, dev)
+        if r1 > r0:
+            _capi.check(L.b200rmsd_matrix_moments_dev(blk.data_ptr(), r1 - r0, F, blk.stride(0), moments.data_ptr(), stream),
+                        "b200rmsd_matrix_moments_dev")
+        dist.all_reduce(moments, group=group)
+        s1, s2 = (float(v) for v in moments.cpu())
+        n = float(F) * float(F)
+        mean = s1 / n
+        std = math.sqrt(max(s2 / n - mean * mean, 0.0))
+        if not std > 0.0:
+            raise ValueError("all pairwise distances are equal: distances.std() == 0")
+        if r1 > r0:
+            _capi.check(L.b200rmsd_exp_rowsum_dev(blk.data_ptr(), r1 - r0, F, blk.stride(0), -float(beta) / std, 0,
+                                                  local.data_ptr(), stream), "b200rmsd_exp_rowsum_dev")
+    bounds = all_shard_bounds(F, world)
+    width = max(b - a for a, b in bounds)
+    padded = torch.zeros(width, dtype=torch.float64, device=dev)
+    padded[: r1 - r0] = local[: r1 - r0]
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    scores = torch.cat([p[: b - a] for p, (a, b) in zip(parts, bounds)])
+    return scores.cpu().numpy(), std
+
+
+def centroid_index_sharded(traj_dev, atom_indices=None, beta=1.0, group=None, broadcast=True, precise=True):
+    """Index of the frame most similar to all others (``centroids.ipynb:117-118``) from the sharded matrix; the same
+    integer on every rank."""
+    return int(np.argmax(similarity_scores_sharded(traj_dev, atom_indices, beta, group, broadcast, precise)[0]))

@@ -97,6 +97,15 @@ def main():
         want = mdb.rmsd_matrix_device(mdb.DeviceTrajectory.from_host(Xx, dev), row_block=(a0, a1))
         assert (bx - want).abs().max().item() < 1e-5, f"peer exchange after cache turnover, F = {Fx}"
     assert len(D._EXCHANGES) <= 2
+    # the clustering notebooks' reduction over the sharded matrix == the single-GPU one
+    Xc = X[:1500]
+    dc = mdb.DeviceTrajectory.from_host(Xc, dev) if rank == 0 else \
+        mdb.DeviceTrajectory(torch.zeros((1500, N, 3), dtype=torch.float32, device=dev), N)
+    sc, sd = D.similarity_scores_sharded(dc, beta=1.0)
+    from mdtraj_b200 import clustering
+    sc1, sd1 = clustering.similarity_scores(mdb.DeviceTrajectory.from_host(Xc, dev), beta=1.0)
+    assert abs(sd - sd1) < 1e-6 * sd1 and np.allclose(sc, sc1, rtol=1e-6, atol=0), "sharded similarity scores"
+    assert D.centroid_index_sharded(dc) == int(np.argmax(sc1))
     assert (r0, r1) == D.shard_bounds(F, rank, world)
     truth_row = single if r0 <= 5 < r1 else None
     if truth_row is not None:
