@@ -374,38 +374,57 @@ def rmsd_matrix_sharded(traj_dev, atom_indices=None, group=None, broadcast=True,
             raise RuntimeError("rmsd_matrix_sharded(exchange='peer'): the peer mapping could not be set up on every "
                                "rank: " + str(ex.error))
     out = torch.empty((r1 - r0, F), dtype=torch.float32, device=dev)
-    # Rounds d = 1 .. W/2: in round d every rank computes its block against rank + d, then sends the transposed copy
-    # there and receives the one rank - d computed for it -- one send and one receive per rank and round, issued as one
-    # NCCL group right after the block's kernel (the group waits for it on the compute stream) while the next block is
-    # already being computed.  The diagonal block comes last and covers the last round's transfer.  Every rank walks
-    # the rounds in the same order, so the groups pair up.
-    local = [c for c in plan["compute"] if c[4] is None]
+
+    def compute(a0, a1, c0, c1, rows_view, out_t):
+        allpairs.block(prep, a0, a1, c0, c1, rows_view, out_t, diag_zero, precise)
+    symmetric_exchange(plan, rank, world, r0, out, compute, group)
+    return r0, r1, out
+
+
+def exchange_rounds(plan_rank, rank: int, world: int):
+    """The blocks of one rank's ``symmetric_plan`` entry grouped into rounds: in round d = 1 .. W/2 the rank computes its
+    block against rank + d and sends the transposed copy there, and receives the one rank - d computed for it (the
+    antipodal round of an even world has half blocks going both ways).  Returns ``[(d, sends, recvs)]`` in the order
+    every rank walks them, so that the send/receive groups of a round pair up across ranks."""
     by_round = {}
-    for c in plan["compute"]:
+    for c in plan_rank["compute"]:
         if c[4] is not None:
             by_round.setdefault((c[4] - rank) % world, {"send": [], "recv": []})["send"].append(c)
-    for rc in plan["recv"]:
+    for rc in plan_rank["recv"]:
         by_round.setdefault((rank - rc[0]) % world, {"send": [], "recv": []})["recv"].append(rc)
+    return [(d, by_round[d]["send"], by_round[d]["recv"]) for d in sorted(by_round)]
+
+
+def symmetric_exchange(plan_rank, rank, world, row0, out, compute, group=None):
+    """Fill ``out`` (this rank's (rows, F) block, any device) from the symmetric block plan with send/recv exchange.
+    ``compute(a0, a1, c0, c1, rows_view, out_t)`` writes block rows [a0,a1) x columns [c0,c1) into ``rows_view`` (absolute
+    column index) and, when ``out_t`` is not None, its transpose into ``out_t``.  One send and one receive per rank and
+    round, issued as one group right after the block's kernel (on CUDA the group waits for it on the compute stream) while
+    the next block is already being computed; the diagonal block comes last and covers the last round's transfer.
+    Device-agnostic: the world_size 2-4 gloo tests run it on CPU tensors with a numpy stand-in for the kernel."""
+    import torch
+    dist = _dist()
     works, recvs = [], []
-    for d in sorted(by_round):
+    for _, sends, rcvs in exchange_rounds(plan_rank, rank, world):
         ops = []
-        for (a0, a1, c0, c1, dst) in by_round[d]["send"]:
-            t = torch.empty((c1 - c0, a1 - a0), dtype=torch.float32, device=dev)
-            allpairs.block(prep, a0, a1, c0, c1, out[a0 - r0: a1 - r0], t, diag_zero, precise)
+        for (a0, a1, c0, c1, dst) in sends:
+            t = torch.empty((c1 - c0, a1 - a0), dtype=out.dtype, device=out.device)
+            compute(a0, a1, c0, c1, out[a0 - row0: a1 - row0], t)
             ops.append(dist.P2POp(dist.isend, t, dst, group))
-        for (src, a0, a1, c0, c1) in by_round[d]["recv"]:
-            buf = torch.empty((a1 - a0, c1 - c0), dtype=torch.float32, device=dev)
+        for (src, a0, a1, c0, c1) in rcvs:
+            buf = torch.empty((a1 - a0, c1 - c0), dtype=out.dtype, device=out.device)
             recvs.append((a0, a1, c0, c1, buf))
             ops.append(dist.P2POp(dist.irecv, buf, src, group))
         if ops:
             works.extend(dist.batch_isend_irecv(ops))
-    for (a0, a1, c0, c1, _) in local:
-        allpairs.block(prep, a0, a1, c0, c1, out[a0 - r0: a1 - r0], None, diag_zero, precise)
+    for (a0, a1, c0, c1, dst) in plan_rank["compute"]:
+        if dst is None:
+            compute(a0, a1, c0, c1, out[a0 - row0: a1 - row0], None)
     for w in works:
         w.wait()
     for (a0, a1, c0, c1, buf) in recvs:
-        out[a0 - r0: a1 - r0, c0:c1] = buf
-    return r0, r1, out
+        out[a0 - row0: a1 - row0, c0:c1] = buf
+    return out
 
 
 def similarity_scores_sharded(traj_dev, atom_indices=None, beta=1.0, group=None, broadcast=True, precise=True):
