@@ -281,3 +281,30 @@ def test_lprmsd_validation_mirrors_the_reference():
         mdb.lprmsd(T(X), T(X), atom_indices=[0, 1, 2], permute_groups=[[2, 3]])
     with pytest.raises(ValueError, match="permute_groups must be mutually disjoint sets"):
         mdb.lprmsd(T(X), T(X), permute_groups=[[1, 2], [2, 3]])
+
+
+def test_superpose_pipe_reference_placement():
+    """Geometry of superpose_pipe_kernel for large selections (host-side hook): the reference stays in shared memory as long
+    as three frame buffers fit next to it, and moves to global memory -- keeping three buffers -- when they do not (all
+    atoms selected on ~5,000-atom frames); frames over 100 KB leave the single-pass kernels altogether."""
+    import ctypes
+
+    from mdtraj_b200 import _capi
+    geo = ctypes.CDLL(_capi.LIB_PATH).b200rmsd_debug_fused_geometry
+    geo.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_int)]
+    out = (ctypes.c_int * 8)()
+
+    def pipe(n, n_sel, has_idx):
+        for i in range(8):
+            out[i] = 0
+        kind = geo(0, n, n_sel, has_idx, 1, out)
+        return kind, list(out)
+    for n in (3000, 4000):                       # all atoms: reference (36-48 KB) resident, >= 3 buffers
+        kind, g = pipe(n, n, 0)
+        assert kind == 2 and g[7] == 0 and g[1] >= 3, (n, g)
+    for n in (4800, 5000, 5400, 6200):           # all atoms: reference in global memory, exactly the buffers that fit
+        kind, g = pipe(n, n, 0)
+        assert kind == 2 and g[7] == 1 and g[1] >= 3 and g[5] <= 232448, (n, g)
+    kind, g = pipe(5000, 1000, 1)                # C3: every 5th atom, reference (12 KB) resident
+    assert kind == 2 and g[7] == 0 and g[1] >= 3, g
+    assert pipe(9000, 9000, 0)[0] == 0           # 108 KB frames: two-pass path
